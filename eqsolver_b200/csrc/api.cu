@@ -1,0 +1,435 @@
+// api.cu -- the extern "C" boundary (include/eqsolver_b200.h): context, diagnostics, ParticleSwarm entry points.
+// CrossEntropy entry points live in ce.cu.  No exception crosses the boundary.
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+#include "common.cuh"
+#include "objectives.cuh"
+#include "philox.cuh"
+#include "pso.cuh"
+
+using namespace eqs;
+
+struct eqs_ctx {
+    Ctx c;
+};
+struct eqs_pso {
+    PsoSolver s;
+    explicit eqs_pso(Ctx *c) : s(c) {}
+};
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+template <class Obj> __global__ void objective_eval_kernel(const double *x, int n, long long count, double *out)
+{
+    // x is particle-major [count][n] as the caller (and the reference's closure) sees it
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = objective_strided<Obj>(x + i * n, n, 1);
+}
+
+__global__ void philox_blocks_kernel(const uint32_t *ctr, PhiloxKey key, long long count, uint32_t *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint4 r = philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key);
+    out[4 * i] = r.x;
+    out[4 * i + 1] = r.y;
+    out[4 * i + 2] = r.z;
+    out[4 * i + 3] = r.w;
+}
+
+__global__ void draws_kernel(int kind, PhiloxKey key, uint32_t t, long long first, long long count, int n, double *a, double *b)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const long long gi = first + i;
+    if (kind == 2) {
+        for (int p = 0; 2 * p < n; ++p) {
+            double z0, z1;
+            normal_pair(philox_draw(key, STREAM_CE, t, gi, (uint32_t)p), z0, z1);
+            a[i * n + 2 * p] = z0;
+            if (2 * p + 1 < n) a[i * n + 2 * p + 1] = z1;
+        }
+        return;
+    }
+    for (int d = 0; d < n; ++d) {
+        const uint4 w = philox_draw(key, kind == 0 ? STREAM_PSO_INIT : STREAM_PSO_STEP, t, gi, (uint32_t)d);
+        a[i * n + d] = u01(w.x, w.y);
+        b[i * n + d] = u01(w.z, w.w);
+    }
+}
+
+// DFMA issue-rate probe: 8 independent dependent-chains per thread, fully unrolled
+__global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, double a, double b)
+{
+    double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+            r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+        }
+    }
+    const double s = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    if (s == 123.456) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) copy_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, long long n2)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+} // namespace
+
+extern "C" {
+
+int eqs_abi_version(void) { return EQS_ABI_VERSION; }
+
+int eqs_ctx_create(int device, eqs_ctx **out)
+{
+    if (!out) return EQS_ERR_INCORRECT_INPUT;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        // no CPU fallback: fail loudly
+        g_create_error = std::string("no CUDA device available (") + (e == cudaSuccess ? "device count 0" : cudaGetErrorString(e)) +
+                         "); eqsolver_b200 has no CPU path";
+        return EQS_ERR_EXTERNAL;
+    }
+    if (device < 0 || device >= count) {
+        g_create_error = "device ordinal out of range";
+        return EQS_ERR_INCORRECT_INPUT;
+    }
+    eqs_ctx *ctx = new (std::nothrow) eqs_ctx;
+    if (!ctx) return EQS_ERR_EXTERNAL;
+    ctx->c.device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&ctx->c.sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = std::string("CUDA error: ") + cudaGetErrorString(e);
+        delete ctx;
+        return EQS_ERR_EXTERNAL;
+    }
+    *out = ctx;
+    return EQS_OK;
+}
+
+int eqs_ctx_destroy(eqs_ctx *ctx)
+{
+    if (!ctx) return EQS_OK;
+    cudaSetDevice(ctx->c.device);
+    comm_destroy(&ctx->c);
+    if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
+    delete ctx;
+    return EQS_OK;
+}
+
+const char *eqs_last_error(const eqs_ctx *ctx) { return ctx ? ctx->c.error.c_str() : g_create_error.c_str(); }
+
+int eqs_ctx_sm_count(const eqs_ctx *ctx, int *out)
+{
+    if (!ctx || !out) return EQS_ERR_INCORRECT_INPUT;
+    *out = ctx->c.sm_count;
+    return EQS_OK;
+}
+
+int eqs_comm_unique_id(void *out128)
+{
+    if (!out128) return EQS_ERR_INCORRECT_INPUT;
+    return comm_unique_id(out128, g_create_error);
+}
+
+int eqs_ctx_comm_init(eqs_ctx *ctx, int rank, int world, const void *id128)
+{
+    if (!ctx || (world > 1 && !id128)) return EQS_ERR_INCORRECT_INPUT;
+    return comm_init(&ctx->c, rank, world, id128);
+}
+
+int eqs_ctx_rank(const eqs_ctx *ctx, int *rank, int *world)
+{
+    if (!ctx) return EQS_ERR_INCORRECT_INPUT;
+    if (rank) *rank = ctx->c.rank;
+    if (world) *world = ctx->c.world;
+    return EQS_OK;
+}
+
+int eqs_shard_range(int64_t count, int world, int rank, int64_t *first, int64_t *local)
+{
+    if (count < 0 || world < 1 || rank < 0 || rank >= world) return EQS_ERR_INCORRECT_INPUT;
+    const int64_t base = count / world, rem = count % world;
+    const int64_t f = rank * base + std::min<int64_t>(rank, rem);
+    if (first) *first = f;
+    if (local) *local = base + (rank < rem ? 1 : 0);
+    return EQS_OK;
+}
+
+int64_t eqs_record_doubles(int32_t n) { return record_doubles(n); }
+
+// ---- diagnostics ---------------------------------------------------------------------------------------
+
+int eqs_objective_eval(eqs_ctx *ctx, int32_t objective_id, const double *x, int32_t n, int64_t count, double *out)
+{
+    if (!ctx || !x || !out || n <= 0 || count < 0) return EQS_ERR_INCORRECT_INPUT;
+    Ctx *c = &ctx->c;
+    if (objective_id == EQS_OBJ_THREE_CIRCLES && n != 2) return c->fail(EQS_ERR_INCORRECT_INPUT, "three-circles objective needs n = 2");
+    if (count == 0) return EQS_OK;
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    double *dx = nullptr, *dout = nullptr;
+    EQS_CUDA(c, cudaMalloc(&dx, sizeof(double) * n * count));
+    EQS_CUDA(c, cudaMalloc(&dout, sizeof(double) * count));
+    EQS_CUDA(c, cudaMemcpyAsync(dx, x, sizeof(double) * n * count, cudaMemcpyHostToDevice, c->stream));
+    const bool known = dispatch_objective(objective_id, [&]<class Obj>() {
+        objective_eval_kernel<Obj><<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(dx, n, count, dout);
+    });
+    int st = EQS_OK;
+    if (!known) st = c->fail(EQS_ERR_INCORRECT_INPUT, "unknown objective id %d", objective_id);
+    cudaError_t e = cudaMemcpyAsync(out, dout, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dx);
+    cudaFree(dout);
+    if (st == EQS_OK && e != cudaSuccess) st = c->fail(EQS_ERR_EXTERNAL, "CUDA error: %s", cudaGetErrorString(e));
+    return st;
+}
+
+int eqs_philox_blocks(eqs_ctx *ctx, const uint32_t *ctr, const uint32_t key[2], int64_t count, uint32_t *out)
+{
+    if (!ctx || !ctr || !key || !out || count < 0) return EQS_ERR_INCORRECT_INPUT;
+    Ctx *c = &ctx->c;
+    if (count == 0) return EQS_OK;
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    uint32_t *dc = nullptr, *dout = nullptr;
+    EQS_CUDA(c, cudaMalloc(&dc, 16 * count));
+    EQS_CUDA(c, cudaMalloc(&dout, 16 * count));
+    EQS_CUDA(c, cudaMemcpyAsync(dc, ctr, 16 * count, cudaMemcpyHostToDevice, c->stream));
+    philox_blocks_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(dc, PhiloxKey{key[0], key[1]}, count, dout);
+    cudaError_t e = cudaMemcpyAsync(out, dout, 16 * count, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dc);
+    cudaFree(dout);
+    if (e != cudaSuccess) return c->fail(EQS_ERR_EXTERNAL, "CUDA error: %s", cudaGetErrorString(e));
+    return EQS_OK;
+}
+
+int eqs_draws(eqs_ctx *ctx, int32_t kind, uint64_t seed, int64_t t, int64_t first, int64_t count, int32_t n, double *a, double *b)
+{
+    if (!ctx || !a || kind < 0 || kind > 2 || (kind != 2 && !b) || n <= 0 || count < 0) return EQS_ERR_INCORRECT_INPUT;
+    Ctx *c = &ctx->c;
+    if (count == 0) return EQS_OK;
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    double *da = nullptr, *db = nullptr;
+    const size_t bytes = sizeof(double) * n * count;
+    EQS_CUDA(c, cudaMalloc(&da, bytes));
+    EQS_CUDA(c, cudaMalloc(&db, bytes));
+    draws_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(kind, philox_key(seed), (uint32_t)t, first, count, n, da, db);
+    cudaError_t e = cudaMemcpyAsync(a, da, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && kind != 2) e = cudaMemcpyAsync(b, db, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(da);
+    cudaFree(db);
+    if (e != cudaSuccess) return c->fail(EQS_ERR_EXTERNAL, "CUDA error: %s", cudaGetErrorString(e));
+    return EQS_OK;
+}
+
+int eqs_measure_fp64(eqs_ctx *ctx, double *tflops)
+{
+    if (!ctx || !tflops) return EQS_ERR_INCORRECT_INPUT;
+    Ctx *c = &ctx->c;
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    double *dout = nullptr;
+    EQS_CUDA(c, cudaMalloc(&dout, 8));
+    cudaEvent_t e0, e1;
+    EQS_CUDA(c, cudaEventCreate(&e0));
+    EQS_CUDA(c, cudaEventCreate(&e1));
+    const int grid = c->sm_count * 8, iters = 2048;
+    dfma_kernel<<<grid, 256, 0, c->stream>>>(dout, 64, 1.0000001, 1e-9); // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, c->stream);
+        dfma_kernel<<<grid, 256, 0, c->stream>>>(dout, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1, c->stream);
+        EQS_CUDA(c, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8 * 16 * (double)iters * 256.0 * grid;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(dout);
+    *tflops = best;
+    return EQS_OK;
+}
+
+int eqs_measure_copy(eqs_ctx *ctx, int64_t bytes, double *gbps)
+{
+    if (!ctx || !gbps || bytes < 16) return EQS_ERR_INCORRECT_INPUT;
+    Ctx *c = &ctx->c;
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    const long long n2 = bytes / 16;
+    double2 *a = nullptr, *b = nullptr;
+    EQS_CUDA(c, cudaMalloc(&a, n2 * 16));
+    EQS_CUDA(c, cudaMalloc(&b, n2 * 16));
+    EQS_CUDA(c, cudaMemsetAsync(a, 0, n2 * 16, c->stream));
+    cudaEvent_t e0, e1;
+    EQS_CUDA(c, cudaEventCreate(&e0));
+    EQS_CUDA(c, cudaEventCreate(&e1));
+    const int grid = c->sm_count * 8;
+    copy_kernel<<<grid, 256, 0, c->stream>>>(a, b, n2);
+    double best = 0.0;
+    for (int rep = 0; rep < 10; ++rep) {
+        cudaEventRecord(e0, c->stream);
+        copy_kernel<<<grid, 256, 0, c->stream>>>(a, b, n2);
+        cudaEventRecord(e1, c->stream);
+        EQS_CUDA(c, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = std::max(best, 2.0 * n2 * 16 / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(a);
+    cudaFree(b);
+    *gbps = best;
+    return EQS_OK;
+}
+
+// ---- ParticleSwarm -------------------------------------------------------------------------------------
+
+int eqs_pso_validate(const eqs_pso_params *p) { return validate_pso_params(p, nullptr); }
+
+int eqs_pso_create(eqs_ctx *ctx, const eqs_pso_params *p, eqs_pso **out)
+{
+    if (!ctx || !out) return EQS_ERR_INCORRECT_INPUT;
+    *out = nullptr;
+    eqs_pso *h = new (std::nothrow) eqs_pso(&ctx->c);
+    if (!h) return ctx->c.fail(EQS_ERR_EXTERNAL, "out of host memory");
+    const int st = h->s.create(p);
+    if (st != EQS_OK) {
+        delete h;
+        return st;
+    }
+    *out = h;
+    return EQS_OK;
+}
+
+int eqs_pso_destroy(eqs_pso *h)
+{
+    delete h;
+    return EQS_OK;
+}
+
+#define H_OR_FAIL(h)                                                                                             \
+    if (!(h)) return EQS_ERR_INCORRECT_INPUT
+
+int eqs_pso_init(eqs_pso *h, const double *x0)
+{
+    H_OR_FAIL(h);
+    if (!x0) return h->s.ctx_->fail(EQS_ERR_INCORRECT_INPUT, "null x0");
+    return h->s.init(x0);
+}
+
+int eqs_pso_step(eqs_pso *h, int64_t iters, const double *replay_step)
+{
+    H_OR_FAIL(h);
+    if (iters < 0) return h->s.ctx_->fail(EQS_ERR_INCORRECT_INPUT, "negative iteration count");
+    return h->s.step(iters, replay_step);
+}
+
+int eqs_pso_sync(eqs_pso *h)
+{
+    H_OR_FAIL(h);
+    return h->s.sync();
+}
+
+int eqs_pso_last_step_ms(eqs_pso *h, double *ms, int64_t *kernel_launches)
+{
+    H_OR_FAIL(h);
+    Ctx *c = h->s.ctx_;
+    EQS_CUDA(c, cudaEventSynchronize(h->s.ev1_));
+    float f = 0.f;
+    EQS_CUDA(c, cudaEventElapsedTime(&f, h->s.ev0_, h->s.ev1_));
+    if (ms) *ms = f;
+    if (kernel_launches) *kernel_launches = h->s.last_launches_;
+    return EQS_OK;
+}
+
+int eqs_pso_read_gbest(eqs_pso *h, double *g, double *cost, int64_t *iters_run, int32_t *stalled, int64_t *improvements)
+{
+    H_OR_FAIL(h);
+    return h->s.read_gbest(g, cost, iters_run, stalled, improvements);
+}
+
+int eqs_pso_read_state(eqs_pso *h, double *x, double *v, double *pbest, double *pbest_cost)
+{
+    H_OR_FAIL(h);
+    return h->s.read_state(x, v, pbest, pbest_cost);
+}
+
+int eqs_pso_read_ring(eqs_pso *h, double *ring, int64_t *ring_i)
+{
+    H_OR_FAIL(h);
+    return h->s.read_ring(ring, ring_i);
+}
+
+int eqs_pso_local_range(eqs_pso *h, int64_t *first, int64_t *local)
+{
+    H_OR_FAIL(h);
+    if (first) *first = h->s.d_.first;
+    if (local) *local = h->s.d_.nloc;
+    return EQS_OK;
+}
+
+int eqs_pso_init_local(eqs_pso *h, const double *x0, int32_t phase)
+{
+    H_OR_FAIL(h);
+    if (phase < 0 || phase > 1 || (phase == 0 && !x0)) return h->s.ctx_->fail(EQS_ERR_INCORRECT_INPUT, "bad init phase");
+    return h->s.init_local(x0, phase);
+}
+
+int eqs_pso_init_apply(eqs_pso *h)
+{
+    H_OR_FAIL(h);
+    return h->s.init_apply();
+}
+
+int eqs_pso_step_local(eqs_pso *h, const double *replay_step)
+{
+    H_OR_FAIL(h);
+    return h->s.step_local(replay_step);
+}
+
+int eqs_pso_step_apply(eqs_pso *h)
+{
+    H_OR_FAIL(h);
+    return h->s.step_apply();
+}
+
+int eqs_pso_get_record(eqs_pso *h, double *record)
+{
+    H_OR_FAIL(h);
+    if (!record) return EQS_ERR_INCORRECT_INPUT;
+    return h->s.get_record(record);
+}
+
+int eqs_pso_set_records(eqs_pso *h, const double *records)
+{
+    H_OR_FAIL(h);
+    if (!records) return EQS_ERR_INCORRECT_INPUT;
+    return h->s.set_records(records);
+}
+
+int eqs_pso_solve(eqs_ctx *ctx, const eqs_pso_params *p, const double *x0, double *out_x, eqs_report *report)
+{
+    if (!ctx) return EQS_ERR_INCORRECT_INPUT;
+    if (!x0 || !out_x) return ctx->c.fail(EQS_ERR_INCORRECT_INPUT, "null x0 / out_x");
+    PsoSolver s(&ctx->c);
+    EQS_TRY(s.create(p));
+    return s.solve(x0, out_x, report);
+}
+
+} // extern "C"

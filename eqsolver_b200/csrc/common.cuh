@@ -1,0 +1,168 @@
+// common.cuh -- context, error plumbing, exchange-record layout, block-level reductions and scans.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/eqsolver_b200.h"
+
+namespace eqs {
+
+// ---- exchange record (doubles) --------------------------------------------------------------------------
+// One record per rank and exchange: the only data that ever crosses NVLink for ParticleSwarm.
+//   [0] cost   [1] global particle index (as f64, exact below 2^53; -1 = none)   [2] ring pushes of the
+//   init scan   [3] pad   [4..54) last <=50 pushed values in order   [54..54+n) the particle's position
+constexpr int REC_COST = 0, REC_IDX = 1, REC_PUSHES = 2, REC_RING = 4, REC_X = REC_RING + EQS_STALL_WINDOW;
+__host__ __device__ inline int64_t record_doubles(int n) { return (int64_t)REC_X + n; }
+
+// ---- context -------------------------------------------------------------------------------------------
+struct Comm; // comm.cu (NCCL resolved at run time; no link-time dependency)
+
+struct Ctx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    Comm *comm = nullptr;
+    int rank = 0, world = 1;
+    mutable std::string error;
+
+    int fail(int status, const char *fmt, ...) const
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        error = buf;
+        return status;
+    }
+};
+
+#define EQS_CUDA(ctx, expr)                                                                                      \
+    do {                                                                                                         \
+        cudaError_t _e = (expr);                                                                                 \
+        if (_e != cudaSuccess)                                                                                   \
+            return (ctx)->fail(EQS_ERR_EXTERNAL, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,   \
+                               __LINE__, cudaGetErrorString(_e));                                                \
+    } while (0)
+
+#define EQS_TRY(expr)                                                                                            \
+    do {                                                                                                         \
+        int _s = (expr);                                                                                         \
+        if (_s != EQS_OK) return _s;                                                                             \
+    } while (0)
+
+// comm.cu
+int comm_unique_id(void *out128, std::string &err);
+int comm_init(Ctx *ctx, int rank, int world, const void *id128);
+void comm_destroy(Ctx *ctx);
+int comm_allgather_f64(Ctx *ctx, const double *send, double *recv, int64_t count_per_rank, cudaStream_t s);
+int comm_allreduce_sum_u64(Ctx *ctx, unsigned long long *buf, int64_t count, cudaStream_t s);
+
+// ---- device helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ double sanitize_cost(double c) { return (c != c) ? __longlong_as_double(0x7ff0000000000000LL) : c; }
+
+__device__ __forceinline__ double shfl_down_f64(double v, int delta)
+{
+    return __shfl_down_sync(0xffffffffu, v, delta);
+}
+
+// (cost, index) min with the lowest index winning ties -- the reference's strict `<` in particle order
+struct MinLoc {
+    double c;
+    long long i;
+};
+
+__device__ __forceinline__ MinLoc minloc_better(MinLoc a, MinLoc b)
+{
+    const bool take_b = (b.c < a.c) || (b.c == a.c && b.i < a.i);
+    return take_b ? b : a;
+}
+
+__device__ __forceinline__ MinLoc warp_minloc(MinLoc v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MinLoc w;
+        w.c = __shfl_down_sync(0xffffffffu, v.c, o);
+        w.i = __shfl_down_sync(0xffffffffu, v.i, o);
+        v = minloc_better(v, w);
+    }
+    return v;
+}
+
+// all threads of the block must call; result valid in thread 0.  smem: >= 32 MinLoc
+__device__ __forceinline__ MinLoc block_minloc(MinLoc v, MinLoc *smem)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_minloc(v);
+    __syncthreads();
+    if (lane == 0) smem[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        MinLoc w = lane < nw ? smem[lane] : MinLoc{__longlong_as_double(0x7ff0000000000000LL), 0x7fffffffffffffffLL};
+        w = warp_minloc(w);
+        v = w;
+    }
+    return v;
+}
+
+__device__ __forceinline__ long long warp_min_i64(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long w = __shfl_down_sync(0xffffffffu, v, o);
+        v = w < v ? w : v;
+    }
+    return v;
+}
+
+// block-wide EXCLUSIVE scan with an associative op; every thread calls; `total` = reduction of the block.
+// smem: >= 33 T.  Ordered by threadIdx.x.
+template <class T, class Op> __device__ __forceinline__ T block_exclusive_scan(T v, T identity, Op op, T *smem, T &total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    T incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl = op(up, incl);
+    }
+    __syncthreads();
+    if (lane == 31) smem[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        T w = lane < nw ? smem[lane] : identity;
+        T winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const T up = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc = op(up, winc);
+        }
+        T wexc = __shfl_up_sync(0xffffffffu, winc, 1);
+        if (lane == 0) wexc = identity;
+        smem[lane] = wexc;
+        if (lane == 31) smem[32] = winc;
+    }
+    __syncthreads();
+    const T warp_prefix = smem[wid];
+    total = smem[32];
+    T excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = identity;
+    return op(warp_prefix, excl);
+}
+
+struct OpMin {
+    __device__ __forceinline__ double operator()(double a, double b) const { return b < a ? b : a; }
+};
+struct OpAddI {
+    __device__ __forceinline__ int operator()(int a, int b) const { return a + b; }
+};
+struct OpAddLL {
+    __device__ __forceinline__ long long operator()(long long a, long long b) const { return a + b; }
+};
+
+} // namespace eqs

@@ -1,0 +1,144 @@
+// objectives.cuh -- ahead-of-time compiled objective functors, selected by eqs_objective ID.
+//
+// Replaces the user closure `F: Fn(VectorType<T,D>) -> T` of the reference
+// (particle_swarm.rs:92,415; cross_entropy.rs:55,273), which cannot run on the device.
+//
+// A functor is either STREAMING -- begin / feed(x_d, d) for d = 0..n-1 in order / end -- so that the fused
+// step kernel evaluates it while the coordinates are still in registers, or STRIDED -- eval(x, n, stride)
+// reading the coordinates back from the structure-of-arrays column (stride = row pitch).  The operation
+// order of every functor equals the oracle's (oracle/eqs_oracle.c: orc_objective); the library is compiled
+// with -fmad=false because rustc never contracts a*b+c.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/eqsolver_b200.h"
+
+namespace eqs {
+
+struct ObjAcc {
+    double a, b, p;
+};
+
+constexpr double kTwoPi = 2.0 * 3.14159265358979323846; // (2.0 * PI), exact doubling
+constexpr double kE = 2.718281828459045235360287;
+
+template <int ID> struct Objective;
+
+template <> struct Objective<EQS_OBJ_SPHERE> {
+    static constexpr bool streaming = true;
+    __device__ __forceinline__ static void begin(ObjAcc &s, int) { s.a = 0.0; }
+    __device__ __forceinline__ static void feed(ObjAcc &s, double x, int) { s.a += x * x; }
+    __device__ __forceinline__ static double end(const ObjAcc &s, int) { return s.a; }
+};
+
+template <> struct Objective<EQS_OBJ_ROSENBROCK> {
+    static constexpr bool streaming = true;
+    __device__ __forceinline__ static void begin(ObjAcc &s, int) { s.a = 0.0; s.p = 0.0; }
+    __device__ __forceinline__ static void feed(ObjAcc &s, double x, int d)
+    {
+        if (d > 0) {
+            const double t = x - s.p * s.p;
+            const double u = 1.0 - s.p;
+            s.a += 100.0 * (t * t) + u * u;
+        }
+        s.p = x;
+    }
+    __device__ __forceinline__ static double end(const ObjAcc &s, int) { return s.a; }
+};
+
+// examples/global_optimisation.rs:9-17
+template <> struct Objective<EQS_OBJ_RASTRIGIN> {
+    static constexpr bool streaming = true;
+    __device__ __forceinline__ static void begin(ObjAcc &s, int n) { s.a = 10.0 * (double)n; }
+    __device__ __forceinline__ static void feed(ObjAcc &s, double x, int) { s.a += x * x - 10.0 * cos(kTwoPi * x); }
+    __device__ __forceinline__ static double end(const ObjAcc &s, int) { return s.a; }
+};
+
+template <> struct Objective<EQS_OBJ_ACKLEY> {
+    static constexpr bool streaming = true;
+    __device__ __forceinline__ static void begin(ObjAcc &s, int) { s.a = 0.0; s.b = 0.0; }
+    __device__ __forceinline__ static void feed(ObjAcc &s, double x, int)
+    {
+        s.a += x * x;
+        s.b += cos(kTwoPi * x);
+    }
+    __device__ __forceinline__ static double end(const ObjAcc &s, int n)
+    {
+        const double a = -20.0 * exp(-0.2 * sqrt(s.a / (double)n));
+        const double b = exp(s.b / (double)n);
+        return a - b + 20.0 + kE;
+    }
+};
+
+// examples/global_optimiser_as_solver.rs:22-42: || F(v) - b ||, circles (3,5,r3) (1,0,r4) (6,2,r2); n = 2
+template <> struct Objective<EQS_OBJ_THREE_CIRCLES> {
+    static constexpr bool streaming = true;
+    __device__ __forceinline__ static void begin(ObjAcc &s, int) { s.a = 0.0; s.p = 0.0; }
+    __device__ __forceinline__ static void feed(ObjAcc &s, double x, int d)
+    {
+        if (d == 0) s.p = x;
+        if (d == 1) {
+            const double x0 = s.p, x1 = x;
+            const double e0 = ((x0 - 3.0) * (x0 - 3.0) + (x1 - 5.0) * (x1 - 5.0)) - 9.0;
+            const double e1 = ((x0 - 1.0) * (x0 - 1.0) + (x1 - 0.0) * (x1 - 0.0)) - 16.0;
+            const double e2 = ((x0 - 6.0) * (x0 - 6.0) + (x1 - 2.0) * (x1 - 2.0)) - 4.0;
+            s.a = ((0.0 + e0 * e0) + e1 * e1) + e2 * e2;
+        }
+    }
+    __device__ __forceinline__ static double end(const ObjAcc &s, int) { return sqrt(s.a); }
+};
+
+// benchmarks/multi.rs:106-115,137: out_i = sum_{j>=i} x_j^2 (a fresh forward sum per i), cost = ||out||.
+// O(n^2) by construction in the reference; kept so, for bit parity of each partial sum.
+template <> struct Objective<EQS_OBJ_HEAVY> {
+    static constexpr bool streaming = false;
+    __device__ __forceinline__ static double eval(const double *x, int n, int64_t stride)
+    {
+        double acc = 0.0;
+        for (int i = 0; i < n; ++i) {
+            double o = 0.0;
+            for (int j = i; j < n; ++j) {
+                const double xj = x[(int64_t)j * stride];
+                o += xj * xj;
+            }
+            acc += o * o;
+        }
+        return sqrt(acc);
+    }
+};
+
+} // namespace eqs
+
+#include "user_objective.cuh"
+
+namespace eqs {
+template <> struct Objective<EQS_OBJ_USER> : public UserObjective {};
+
+// evaluate any functor on a strided column (used by eqs_objective_eval, f(x0), and strided functors)
+template <class Obj> __device__ __forceinline__ double objective_strided(const double *x, int n, int64_t stride)
+{
+    if constexpr (Obj::streaming) {
+        ObjAcc s;
+        Obj::begin(s, n);
+        for (int d = 0; d < n; ++d) Obj::feed(s, x[(int64_t)d * stride], d);
+        return Obj::end(s, n);
+    } else {
+        return Obj::eval(x, n, stride);
+    }
+}
+
+// host-side dispatch over the objective ID: f.template operator()<Objective<ID>>()
+template <class F> inline bool dispatch_objective(int id, F &&f)
+{
+    switch (id) {
+    case EQS_OBJ_SPHERE: f.template operator()<Objective<EQS_OBJ_SPHERE>>(); return true;
+    case EQS_OBJ_ROSENBROCK: f.template operator()<Objective<EQS_OBJ_ROSENBROCK>>(); return true;
+    case EQS_OBJ_RASTRIGIN: f.template operator()<Objective<EQS_OBJ_RASTRIGIN>>(); return true;
+    case EQS_OBJ_ACKLEY: f.template operator()<Objective<EQS_OBJ_ACKLEY>>(); return true;
+    case EQS_OBJ_THREE_CIRCLES: f.template operator()<Objective<EQS_OBJ_THREE_CIRCLES>>(); return true;
+    case EQS_OBJ_HEAVY: f.template operator()<Objective<EQS_OBJ_HEAVY>>(); return true;
+    case EQS_OBJ_USER: f.template operator()<Objective<EQS_OBJ_USER>>(); return true;
+    default: return false;
+    }
+}
+} // namespace eqs

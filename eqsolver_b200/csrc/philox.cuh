@@ -1,0 +1,78 @@
+// philox.cuh -- counter-based Philox4x32-10 in registers + the draw-index contract.
+//
+// Replaces the reference's `rand::rng()` + `Uniform`/`Normal` samplers
+// (particle_swarm.rs:367,373,407-408; cross_entropy.rs:270), which are unseedable.  One Philox block per
+// (particle, dimension) yields exactly the two uniforms (rp, rg) the reference draws per dimension.
+//
+//   key = (seed lo32, seed hi32)
+//   ctr = (gidx lo32, gidx hi32, stream << 28 | j, iteration)       j = dimension (PSO) or dim pair (CE)
+//   u   = ((w_hi mod 2^21) * 2^32 + w_lo) * 2^-53   in [0,1)        (w_lo, w_hi) = words (0,1) or (2,3)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace eqs {
+
+enum : uint32_t { STREAM_PSO_INIT = 0u, STREAM_PSO_STEP = 1u, STREAM_CE = 2u };
+
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+
+struct PhiloxKey {
+    uint32_t k0, k1;
+};
+
+__host__ __device__ inline PhiloxKey philox_key(uint64_t seed)
+{
+    return PhiloxKey{(uint32_t)seed, (uint32_t)(seed >> 32)};
+}
+
+// 10 rounds; the per-round keys depend only on the (uniform) key, so ptxas folds the bumps into immediates
+// of a uniform register: 2 IMAD.WIDE.U32 + 2 LOP3 per round.
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, PhiloxKey key)
+{
+    uint32_t k0 = key.k0, k1 = key.k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += PHILOX_W0;
+        k1 += PHILOX_W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ uint4 philox_draw(PhiloxKey key, uint32_t stream, uint32_t t, int64_t gidx, uint32_t j)
+{
+    return philox4x32_10((uint32_t)(uint64_t)gidx, (uint32_t)((uint64_t)gidx >> 32), (stream << 28) | j, t, key);
+}
+
+// exact u53 -> f64 without I2F: 2^84 + h*2^32 and 2^52 + lo are built by bit pasting, the two
+// subtractions/additions below are exact, so this equals (double)k * 2^-53 bit for bit.
+__device__ __forceinline__ double u01(uint32_t w_lo, uint32_t w_hi)
+{
+    const double dh = __hiloint2double(0x45300000, (int)(w_hi & 0x1FFFFFu));
+    const double dl = __hiloint2double(0x43300000, (int)w_lo);
+    return __dmul_rn(__dadd_rn(__dadd_rn(dh, -(0x1.0p84 + 0x1.0p52)), dl), 0x1.0p-53);
+}
+
+// Box-Muller on one block per dimension PAIR: z0 = r cos(2 pi u2), z1 = r sin(2 pi u2), r = sqrt(-2 ln(1-u1)).
+// Stands in for rand_distr's StandardNormal (cross_entropy.rs:270).
+__device__ __forceinline__ void normal_pair(uint4 w, double &z0, double &z1)
+{
+    const double u1 = u01(w.x, w.y);
+    const double u2 = u01(w.z, w.w);
+    const double r = sqrt(-2.0 * log(1.0 - u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+} // namespace eqs

@@ -1,0 +1,1005 @@
+// pso.cu -- ParticleSwarm population step on sm_100a (f64, no tensor cores: nothing here is a contraction).
+//
+// Replaces the body of ParticleSwarm::solve, reference src/solvers/global_optimisers/particle_swarm.rs:356-431:
+//   pso_x0_kernel        :357-359   gbest = x0, ring = +inf
+//   pso_init_kernel      :361-389   sample U[lo,hi] / U[-|hi-lo|,|hi-lo|], evaluate, pbest = x   (K1)
+//   pso_ring_scan_kernel :376-380   the ordered gbest record-lows of the init loop -> ring pushes
+//   pso_step_kernel      :399-419   fused velocity/position update + objective + pbest compare     (K2)
+//                        + block/grid min-loc reduction (K3) + (single rank) the gbest update :420-425
+//   pso_spec/commit      :399-427   sequential-exact mode: speculate-and-repair
+//   pso_apply_*          :420-425, :395-397, :433-441  gbest update, ring push, stall test
+// The kernels are HBM-bound: 40n+16 algorithmic bytes per particle-evaluation.
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+
+#include "objectives.cuh"
+#include "pso.cuh"
+
+namespace eqs {
+
+namespace {
+
+constexpr long long kNoIndex = 0x7fffffffffffffffLL;
+__device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// ---- vector I/O over the particle axis -----------------------------------------------------------------
+template <int VEC> struct VecIO;
+template <> struct VecIO<1> {
+    __device__ __forceinline__ static void load(const double *p, double (&o)[1]) { o[0] = *p; }
+    __device__ __forceinline__ static void store(double *p, const double (&o)[1]) { *p = o[0]; }
+};
+template <> struct VecIO<2> {
+    __device__ __forceinline__ static void load(const double *p, double (&o)[2])
+    {
+        const double2 t = *reinterpret_cast<const double2 *>(p);
+        o[0] = t.x;
+        o[1] = t.y;
+    }
+    __device__ __forceinline__ static void store(double *p, const double (&o)[2])
+    {
+        *reinterpret_cast<double2 *>(p) = make_double2(o[0], o[1]);
+    }
+};
+
+// ---- draws: (rp, rg) of particle_swarm.rs:407-408 ------------------------------------------------------
+template <bool REPLAY>
+__device__ __forceinline__ void step_draw(const PsoDev &P, uint32_t t, long long gi, int d, double &rp, double &rg)
+{
+    if constexpr (REPLAY) {
+        const double *src = P.replay + ((((long long)t - P.replay_t0) * P.ntotal + gi) * P.n + d) * 2;
+        rp = src[0];
+        rg = src[1];
+    } else {
+        const uint4 w = philox_draw(P.key, STREAM_PSO_STEP, t, gi, (uint32_t)d);
+        rp = u01(w.x, w.y);
+        rg = u01(w.z, w.w);
+    }
+}
+
+// particle_swarm.rs:409-413 with rustc's evaluation order ((w v) + ((c1 rp)(pb - x))) + ((c2 rg)(G - x)); x += v
+__device__ __forceinline__ void pso_update(const PsoDev &P, double &x, double &v, double pb, double g, double rp, double rg)
+{
+    v = P.w * v + P.c1 * rp * (pb - x) + P.c2 * rg * (g - x);
+    x = x + v;
+}
+
+// stalled_too_long, particle_swarm.rs:433-441
+__device__ __forceinline__ int stall_test(const PsoCtrl *c, double tol)
+{
+    int stalled = 1;
+    for (int j = 0; j < EQS_STALL_WINDOW; ++j)
+        if (!(fabs(c->ring[j] - c->Gc) < tol)) stalled = 0;
+    return stalled;
+}
+
+__device__ __forceinline__ void ring_push(PsoCtrl *c, double v)
+{
+    c->ring[c->ring_i] = v;
+    c->ring_i = (c->ring_i + 1) % EQS_STALL_WINDOW;
+}
+
+// K rows (dimensions d..d+K-1) of VEC particles: loads first, then update + objective, then stores
+template <class Obj, bool REPLAY, int VEC, int K>
+__device__ __forceinline__ void pso_rows(const PsoDev &P, uint32_t t, long long i0, int d, const double *sG,
+                                         ObjAcc (&acc)[VEC], const double *xin, const double *vin, double *xout,
+                                         double *vout)
+{
+    double xs[K][VEC], vs[K][VEC], ps[K][VEC];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const long long row = (long long)(d + k) * P.ld + i0;
+        VecIO<VEC>::load(xin + row, xs[k]);
+        VecIO<VEC>::load(vin + row, vs[k]);
+        VecIO<VEC>::load(P.pb + row, ps[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double g = sG[d + k];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            double rp, rg;
+            step_draw<REPLAY>(P, t, P.first + i0 + e, d + k, rp, rg);
+            pso_update(P, xs[k][e], vs[k][e], ps[k][e], g, rp, rg);
+            if constexpr (Obj::streaming) Obj::feed(acc[e], xs[k][e], d + k);
+        }
+        const long long row = (long long)(d + k) * P.ld + i0;
+        VecIO<VEC>::store(xout + row, xs[k]);
+        VecIO<VEC>::store(vout + row, vs[k]);
+    }
+}
+
+// all dimensions of VEC particles; returns their new costs
+template <class Obj, bool REPLAY, int VEC>
+__device__ __forceinline__ void pso_move(const PsoDev &P, uint32_t t, long long i0, const double *sG,
+                                         const double *xin, const double *vin, double *xout, double *vout,
+                                         double (&cost)[VEC])
+{
+    const int n = P.n;
+    ObjAcc acc[VEC];
+    if constexpr (Obj::streaming) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) Obj::begin(acc[e], n);
+    }
+    constexpr int UD = 4;
+    int d = 0;
+    for (; d + UD <= n; d += UD) pso_rows<Obj, REPLAY, VEC, UD>(P, t, i0, d, sG, acc, xin, vin, xout, vout);
+    for (; d < n; ++d) pso_rows<Obj, REPLAY, VEC, 1>(P, t, i0, d, sG, acc, xin, vin, xout, vout);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        if constexpr (Obj::streaming) cost[e] = Obj::end(acc[e], n);
+        else cost[e] = Obj::eval(xout + i0 + e, n, P.ld);
+    }
+}
+
+// the last block to finish reduces the per-block partials; returns true in that block only (all threads)
+__device__ __forceinline__ bool grid_minloc_last_block(const PsoDev &P, MinLoc mine, MinLoc *s_red, MinLoc &winner)
+{
+    __shared__ int s_last;
+    __shared__ MinLoc s_win;
+    MinLoc b = block_minloc(mine, s_red);
+    if (threadIdx.x == 0) {
+        P.part_cost[blockIdx.x] = b.c;
+        P.part_idx[blockIdx.x] = b.i;
+        __threadfence();
+        const unsigned ticket = atomicAdd(&P.ctrl->block_counter, 1u);
+        s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    MinLoc m{dinf(), kNoIndex};
+    for (int j = threadIdx.x; j < (int)gridDim.x; j += blockDim.x)
+        m = minloc_better(m, MinLoc{__ldcg(P.part_cost + j), __ldcg(P.part_idx + j)});
+    m = block_minloc(m, s_red);
+    if (threadIdx.x == 0) {
+        s_win = m;
+        P.ctrl->block_counter = 0;
+    }
+    __syncthreads();
+    winner = s_win;
+    return true;
+}
+
+// this rank's exchange record: (cost, global index, position column of `src`)
+__device__ __forceinline__ void write_record(const PsoDev &P, double cost, long long gidx, const double *src)
+{
+    const bool none = gidx == kNoIndex || gidx < 0;
+    if (threadIdx.x == 0) {
+        P.send[REC_COST] = cost;
+        P.send[REC_IDX] = none ? -1.0 : (double)gidx;
+    }
+    for (int d = threadIdx.x; d < P.n; d += blockDim.x)
+        P.send[REC_X + d] = none ? 0.0 : __ldcg(src + (long long)d * P.ld + (gidx - P.first));
+}
+
+// lowest cost, then lowest global index, over the ranks' records; -1 when every record is empty
+__device__ __forceinline__ int best_record(const double *recs, int world, long long R, double &bc)
+{
+    int win = -1;
+    double bi = 0.0;
+    bc = dinf();
+    for (int r = 0; r < world; ++r) {
+        const double *rec = recs + r * R;
+        const double idx = rec[REC_IDX], c = rec[REC_COST];
+        if (idx < 0.0) continue;
+        if (win < 0 || c < bc || (c == bc && idx < bi)) {
+            win = r;
+            bc = c;
+            bi = idx;
+        }
+    }
+    return win;
+}
+
+// synchronous gbest update (one per pass): particle_swarm.rs:420-425 applied to the pass's arg-min
+__device__ __forceinline__ void pso_apply_step(const PsoDev &P, const double *recs, int world)
+{
+    __shared__ int s_winner;
+    const long long R = record_doubles(P.n);
+    if (threadIdx.x == 0) {
+        PsoCtrl *c = P.ctrl;
+        double bc;
+        const int win = best_record(recs, world, R, bc);
+        const bool improved = win >= 0 && bc < c->Gc;
+        if (improved) {
+            ring_push(c, c->Gc);
+            c->Gc = bc;
+            c->improvements += 1;
+        }
+        c->iter += 1;
+        c->stalled = stall_test(c, P.tol);
+        s_winner = improved ? win : -1;
+    }
+    __syncthreads();
+    if (s_winner >= 0)
+        for (int d = threadIdx.x; d < P.n; d += blockDim.x) P.G[d] = recs[s_winner * R + REC_X + d];
+}
+
+// ---- kernels -------------------------------------------------------------------------------------------
+
+// :357-359.  G already holds x0 (H2D copy).
+template <class Obj> __global__ void pso_x0_kernel(const PsoDev P)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    PsoCtrl *c = P.ctrl;
+    c->Gc = objective_strided<Obj>(P.G, P.n, 1);
+    for (int j = 0; j < EQS_STALL_WINDOW; ++j) c->ring[j] = dinf();
+    c->ring_i = 0;
+    c->iter = 0;
+    c->improvements = 0;
+    c->spec_first = -1;
+    c->stalled = 0;
+    c->pass_done = 0;
+    c->block_counter = 0;
+    c->nan_seen = 0;
+}
+
+// :361-389 without the (order-dependent) gbest bookkeeping, which pso_ring_scan_kernel reconstructs
+template <class Obj, bool REPLAY> __global__ void __launch_bounds__(PSO_BLOCK) pso_init_kernel(const PsoDev P)
+{
+    __shared__ MinLoc s_red[32];
+    const int n = P.n;
+    const long long ngroups = (P.nloc + PSO_GROUP - 1) / PSO_GROUP;
+    MinLoc best{dinf(), kNoIndex};
+    for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const long long li = g * PSO_GROUP + threadIdx.x;
+        double c = dinf();
+        if (li < P.nloc) {
+            const long long gi = P.first + li;
+            ObjAcc acc;
+            if constexpr (Obj::streaming) Obj::begin(acc, n);
+            for (int d = 0; d < n; ++d) {
+                double pu, vu;
+                if constexpr (REPLAY) {
+                    pu = P.replay[gi * 2 * n + d];
+                    vu = P.replay[gi * 2 * n + n + d];
+                } else {
+                    const uint4 w = philox_draw(P.key, STREAM_PSO_INIT, 0u, gi, (uint32_t)d);
+                    pu = u01(w.x, w.y);
+                    vu = u01(w.z, w.w);
+                }
+                const double lo = P.lower[d], hi = P.upper[d];
+                const double x = pu * (hi - lo) + lo;              // Uniform::new_inclusive(lo, hi), :124-129
+                const double dist = fabs(hi - lo);                 // :135
+                const double v = vu * (dist + dist) + (-dist);     // Uniform::new_inclusive(-dist, dist)
+                const long long row = (long long)d * P.ld + li;
+                P.x[row] = x;
+                P.v[row] = v;
+                P.pb[row] = x;                                     // best_position = position, :385
+                if constexpr (Obj::streaming) Obj::feed(acc, x, d);
+            }
+            double cost;
+            if constexpr (Obj::streaming) cost = Obj::end(acc, n);
+            else cost = Obj::eval(P.x + li, n, P.ld);
+            P.pbc[li] = cost;
+            P.cost[li] = cost;
+            c = sanitize_cost(cost);
+            if (c < best.c) {
+                best.c = c;
+                best.i = gi;
+            }
+        }
+        const MinLoc gm = block_minloc(MinLoc{c, li}, s_red);
+        if (threadIdx.x == 0) P.group_min[g] = gm.c;
+    }
+    MinLoc win;
+    if (grid_minloc_last_block(P, best, s_red, win)) write_record(P, win.c, win.i, P.x);
+}
+
+// The reference updates gbest INSIDE the init loop (:376-380), pushing the old gbest cost on the stall ring at
+// every record low, in particle order.  Which positions are record lows is an exclusive prefix-min problem:
+// particle i pushes e_i = min(seed, c_0..c_{i-1}) iff c_i < e_i.  One CTA walks the per-tile minima (1024 tiles
+// per scan), then only the tiles that contain a record low (O(log N) of them for random costs).  Output: number
+// of pushes and the last <= 50 pushed values in order, appended to this rank's record.
+__global__ void __launch_bounds__(1024) pso_ring_scan_kernel(const PsoDev P)
+{
+    __shared__ double s_scan_d[33];
+    __shared__ int s_scan_i[33];
+    __shared__ long long s_list[1024];
+    __shared__ double s_seedlist[1024];
+    __shared__ double s_ring[EQS_STALL_WINDOW];
+    __shared__ double s_seed;
+    const int tid = threadIdx.x;
+    const long long R = record_doubles(P.n);
+    if (tid == 0) {
+        double seed = P.ctrl->Gc; // f(x0), :358
+        for (int r = 0; r < P.rank; ++r) { // particles of lower ranks come first in the reference's order
+            const double *rec = P.recv + r * R;
+            if (rec[REC_IDX] >= 0.0 && rec[REC_COST] < seed) seed = rec[REC_COST];
+        }
+        s_seed = seed;
+    }
+    if (tid < EQS_STALL_WINDOW) s_ring[tid] = dinf();
+    __syncthreads();
+    double running = s_seed;
+    long long count = 0;
+    const long long ngroups = (P.nloc + PSO_GROUP - 1) / PSO_GROUP;
+    for (long long g0 = 0; g0 < ngroups; g0 += 1024) {
+        const double gm = (g0 + tid < ngroups) ? P.group_min[g0 + tid] : dinf();
+        double chunk_min;
+        double ex = block_exclusive_scan(gm, dinf(), OpMin(), s_scan_d, chunk_min);
+        ex = ex < running ? ex : running;
+        const int flagged = gm < ex;
+        int nflag;
+        const int pos = block_exclusive_scan(flagged, 0, OpAddI(), s_scan_i, nflag);
+        if (flagged) {
+            s_list[pos] = g0 + tid;
+            s_seedlist[pos] = ex;
+        }
+        __syncthreads();
+        for (int q = 0; q < nflag; ++q) {
+            const long long li = s_list[q] * PSO_GROUP + tid;
+            const double gseed = s_seedlist[q];
+            const double c = (tid < PSO_GROUP && li < P.nloc) ? sanitize_cost(P.cost[li]) : dinf();
+            double dummy;
+            double e = block_exclusive_scan(c, dinf(), OpMin(), s_scan_d, dummy);
+            e = e < gseed ? e : gseed;
+            const int rec = c < e;
+            int tot;
+            const long long rk = count + block_exclusive_scan(rec, 0, OpAddI(), s_scan_i, tot);
+            if (rec && rk >= count + tot - EQS_STALL_WINDOW) s_ring[rk % EQS_STALL_WINDOW] = e;
+            count += tot;
+            __syncthreads();
+        }
+        running = chunk_min < running ? chunk_min : running;
+    }
+    if (tid < EQS_STALL_WINDOW) {
+        const long long kept = count < EQS_STALL_WINDOW ? count : EQS_STALL_WINDOW;
+        P.send[REC_RING + tid] = tid < kept ? s_ring[(count - kept + tid) % EQS_STALL_WINDOW] : dinf();
+    }
+    if (tid == 0) P.send[REC_PUSHES] = (double)count;
+}
+
+// merge the ranks' init records: gbest (strict <, lowest index) and the ring in global particle order
+__global__ void pso_init_apply_kernel(const PsoDev P)
+{
+    __shared__ int s_winner;
+    const long long R = record_doubles(P.n);
+    if (threadIdx.x == 0) {
+        PsoCtrl *c = P.ctrl;
+        double bc;
+        const int win = best_record(P.recv, P.world, R, bc);
+        const bool improved = win >= 0 && bc < c->Gc;
+        if (improved) c->Gc = bc;
+        long long g = 0;
+        for (int r = 0; r < P.world; ++r) {
+            const double *rec = P.recv + r * R;
+            const long long K = (long long)rec[REC_PUSHES];
+            const long long kept = K < EQS_STALL_WINDOW ? K : EQS_STALL_WINDOW;
+            g += K - kept;
+            for (long long j = 0; j < kept; ++j, ++g) c->ring[g % EQS_STALL_WINDOW] = rec[REC_RING + j];
+        }
+        c->ring_i = g % EQS_STALL_WINDOW;
+        c->improvements = g;
+        c->stalled = stall_test(c, P.tol);
+        s_winner = improved ? win : -1;
+    }
+    __syncthreads();
+    if (s_winner >= 0)
+        for (int d = threadIdx.x; d < P.n; d += blockDim.x) P.G[d] = P.recv[s_winner * R + REC_X + d];
+}
+
+// K2 + K3: the synchronous population step.  One thread owns VEC adjacent particles and walks the dimensions;
+// every global access is a lane-contiguous 8*VEC-byte word.  Philox draws, the update and the objective all
+// stay in registers; HBM sees x, v, pbest once in and x, v once out.
+template <class Obj, bool REPLAY, int VEC>
+__global__ void __launch_bounds__(PSO_BLOCK) pso_step_kernel(const PsoDev P, int inline_apply)
+{
+    extern __shared__ double sG[];
+    __shared__ MinLoc s_red[32];
+    PsoCtrl *ctrl = P.ctrl;
+    if (ctrl->stalled) return; // :395-397 -- passes after the stall test fires are no-ops
+    const uint32_t t = (uint32_t)ctrl->iter;
+    const int n = P.n;
+    for (int d = threadIdx.x; d < n; d += blockDim.x) sG[d] = P.G[d];
+    __syncthreads();
+
+    MinLoc best{dinf(), kNoIndex};
+    const long long nunits = (P.nloc + VEC - 1) / VEC;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < nunits;
+         u += (long long)gridDim.x * blockDim.x) {
+        const long long i0 = u * VEC;
+        double cost[VEC];
+        pso_move<Obj, REPLAY, VEC>(P, t, i0, sG, P.x, P.v, P.x, P.v, cost);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const long long li = i0 + e;
+            if (li < P.nloc) {
+                const double c = cost[e];
+                if (c < P.pbc[li]) { // :417-419
+                    P.pbc[li] = c;
+                    for (int d = 0; d < n; ++d) {
+                        const long long row = (long long)d * P.ld + li;
+                        P.pb[row] = P.x[row];
+                    }
+                }
+                const double cs = sanitize_cost(c);
+                if (cs < best.c) {
+                    best.c = cs;
+                    best.i = P.first + li;
+                }
+            }
+        }
+    }
+    MinLoc win;
+    if (grid_minloc_last_block(P, best, s_red, win)) {
+        write_record(P, win.c, win.i, P.x);
+        if (inline_apply) {
+            __syncthreads();
+            pso_apply_step(P, P.send, 1);
+        }
+    }
+}
+
+__global__ void pso_step_apply_kernel(const PsoDev P) { pso_apply_step(P, P.recv, P.world); }
+
+// ---- sequential-exact mode (the reference's semantics, F6) ---------------------------------------------
+// speculate: move every particle with global index >= start against the CURRENT gbest into (x2, v2, cost)
+// without committing, and find the FIRST particle whose cost beats gbest.
+template <class Obj, bool REPLAY>
+__global__ void __launch_bounds__(PSO_BLOCK) pso_spec_kernel(const PsoDev P, long long start_g)
+{
+    extern __shared__ double sG[];
+    __shared__ MinLoc s_red[32];
+    PsoCtrl *ctrl = P.ctrl;
+    if (ctrl->stalled) return;
+    const uint32_t t = (uint32_t)ctrl->iter;
+    const double Gc = ctrl->Gc;
+    for (int d = threadIdx.x; d < P.n; d += blockDim.x) sG[d] = P.G[d];
+    __syncthreads();
+    MinLoc first{0.0, kNoIndex}; // min over index only: all costs equal => lowest index wins
+    for (long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x; li < P.nloc;
+         li += (long long)gridDim.x * blockDim.x) {
+        const long long gi = P.first + li;
+        if (gi < start_g) continue;
+        double cost[1];
+        pso_move<Obj, REPLAY, 1>(P, t, li, sG, P.x, P.v, P.x2, P.v2, cost);
+        P.cost[li] = cost[0];
+        if (cost[0] < Gc && gi < first.i) first.i = gi; // :417,:420 (cost < Gc implies cost < pbest cost)
+    }
+    MinLoc win;
+    if (grid_minloc_last_block(P, first, s_red, win)) {
+        const bool none = win.i == kNoIndex;
+        write_record(P, none ? dinf() : __ldcg(P.cost + (win.i - P.first)), win.i, P.x2);
+    }
+}
+
+__global__ void pso_spec_apply_kernel(const PsoDev P)
+{
+    __shared__ int s_winner;
+    const long long R = record_doubles(P.n);
+    if (threadIdx.x == 0) {
+        PsoCtrl *c = P.ctrl;
+        int win = -1;
+        double bi = 0.0;
+        for (int r = 0; r < P.world; ++r) {
+            const double idx = P.recv[r * R + REC_IDX];
+            if (idx >= 0.0 && (win < 0 || idx < bi)) {
+                win = r;
+                bi = idx;
+            }
+        }
+        if (win >= 0) { // :420-425
+            ring_push(c, c->Gc);
+            c->Gc = P.recv[win * R + REC_COST];
+            c->improvements += 1;
+            c->spec_first = (long long)bi;
+        } else {
+            c->spec_first = -1;
+        }
+        const int done = (win < 0) || ((long long)bi == P.ntotal - 1);
+        c->pass_done = done;
+        if (done) {
+            c->iter += 1;
+            c->stalled = stall_test(c, P.tol);
+        }
+        s_winner = win;
+    }
+    __syncthreads();
+    if (s_winner >= 0)
+        for (int d = threadIdx.x; d < P.n; d += blockDim.x) P.G[d] = P.recv[s_winner * R + REC_X + d];
+}
+
+// commit the speculated state of global indices [start_g, end_g]: x, v <- x2, v2 and the pbest update :417-419
+__global__ void __launch_bounds__(PSO_BLOCK) pso_commit_kernel(const PsoDev P, long long start_g, long long end_g)
+{
+    for (long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x; li < P.nloc;
+         li += (long long)gridDim.x * blockDim.x) {
+        const long long gi = P.first + li;
+        if (gi < start_g || gi > end_g) continue;
+        const double c = P.cost[li];
+        const bool imp = c < P.pbc[li];
+        if (imp) P.pbc[li] = c;
+        for (int d = 0; d < P.n; ++d) {
+            const long long row = (long long)d * P.ld + li;
+            const double xv = P.x2[row];
+            P.x[row] = xv;
+            P.v[row] = P.v2[row];
+            if (imp) P.pb[row] = xv;
+        }
+    }
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+
+template <class K> int persistent_grid(Ctx *ctx, K kernel, int block, size_t smem, long long units_per_block_iter,
+                                       long long units, int &grid)
+{
+    int nb = 0;
+    if (smem > 48 * 1024) EQS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EQS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, block, smem));
+    if (nb < 1) return ctx->fail(EQS_ERR_EXTERNAL, "kernel does not fit on an SM (smem %zu)", smem);
+    const long long need = std::max(1LL, (units + units_per_block_iter - 1) / units_per_block_iter);
+    grid = (int)std::min<long long>(std::min<long long>((long long)nb * ctx->sm_count, need), 64LL * ctx->sm_count);
+    return EQS_OK;
+}
+
+} // namespace
+
+// ---- host driver ---------------------------------------------------------------------------------------
+
+PsoSolver::~PsoSolver()
+{
+    if (ctx_ && ctx_->device >= 0) cudaSetDevice(ctx_->device);
+    if (arena_) cudaFree(arena_);
+    if (replay_buf_) cudaFree(replay_buf_);
+    if (h_ctrl_) cudaFreeHost(h_ctrl_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+}
+
+int validate_pso_params(const eqs_pso_params *p, std::string *why)
+{
+    auto bad = [&](int st, const char *m) {
+        if (why) *why = m;
+        return st;
+    };
+    if (!p) return bad(EQS_ERR_INCORRECT_INPUT, "null parameters");
+    if (p->n <= 0) return bad(EQS_ERR_INCORRECT_INPUT, "dimension n must be positive");
+    if (p->n >= (1 << 28)) return bad(EQS_ERR_INCORRECT_INPUT, "dimension n must be below 2^28");
+    if (p->particle_count < 0 || p->iter_max < 0) return bad(EQS_ERR_INCORRECT_INPUT, "negative count");
+    if (p->objective_id < 0 || p->objective_id >= EQS_OBJ_COUNT) return bad(EQS_ERR_INCORRECT_INPUT, "unknown objective id");
+    if (p->objective_id == EQS_OBJ_THREE_CIRCLES && p->n != 2) return bad(EQS_ERR_INCORRECT_INPUT, "three-circles objective needs n = 2");
+    if (p->mode != EQS_PSO_SEQUENTIAL_EXACT && p->mode != EQS_PSO_SYNCHRONOUS) return bad(EQS_ERR_INCORRECT_INPUT, "unknown mode");
+    if (!p->lower || !p->upper) return bad(EQS_ERR_INCORRECT_INPUT, "null bounds");
+    // Uniform::new_inclusive(low, high): rand's error strings, surfaced as SolverError::ExternalError (:129,:139)
+    for (int d = 0; d < p->n; ++d) {
+        const double lo = p->lower[d], hi = p->upper[d];
+        if (!(lo <= hi)) return bad(EQS_ERR_EXTERNAL, "low > high (or equal if exclusive) in uniform distribution");
+        if (!std::isfinite(lo) || !std::isfinite(hi) || !std::isfinite(hi - lo))
+            return bad(EQS_ERR_EXTERNAL, "Non-finite range in uniform distribution");
+    }
+    return EQS_OK;
+}
+
+int PsoSolver::create(const eqs_pso_params *p)
+{
+    std::string why;
+    const int st = validate_pso_params(p, &why);
+    if (st != EQS_OK) return ctx_->fail(st, "%s", why.c_str());
+    p_ = *p;
+    const int n = p->n;
+    lower_.assign(p->lower, p->lower + n);
+    upper_.assign(p->upper, p->upper + n);
+    p_.lower = lower_.data();
+    p_.upper = upper_.data();
+    int rank = ctx_->rank, world = ctx_->world;
+    if (p->exchange == EQS_EXCHANGE_MANUAL) {
+        rank = p->virtual_rank;
+        world = p->virtual_world;
+        if (world < 1 || rank < 0 || rank >= world) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "bad virtual rank/world");
+        if (p->mode == EQS_PSO_SEQUENTIAL_EXACT && world > 1)
+            return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "sequential-exact mode needs exchange = AUTO");
+    }
+    manual_ = p->exchange == EQS_EXCHANGE_MANUAL && world > 1;
+    EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
+    int64_t first = 0, nloc = 0;
+    eqs_shard_range(p->particle_count, world, rank, &first, &nloc);
+    PsoDev &D = d_;
+    D.n = n;
+    D.world = world;
+    D.rank = rank;
+    D.first = first;
+    D.nloc = nloc;
+    D.ntotal = p->particle_count;
+    D.ld = (long long)align_up((size_t)std::max<int64_t>(nloc, 1), 16);
+    D.w = p->w;
+    D.c1 = p->c1;
+    D.c2 = p->c2;
+    D.tol = p->tol;
+    D.key = philox_key(p->seed);
+    D.replay = nullptr;
+    D.replay_t0 = 0;
+    if ((size_t)n * sizeof(double) > 200 * 1024) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "n too large for the shared-memory gbest tile");
+
+    const bool seq = p->mode == EQS_PSO_SEQUENTIAL_EXACT;
+    const size_t mat = (size_t)n * D.ld * sizeof(double);
+    const size_t vec = (size_t)D.ld * sizeof(double);
+    const size_t R = (size_t)record_doubles(n) * sizeof(double);
+    const long long ngroups = std::max<long long>((nloc + PSO_GROUP - 1) / PSO_GROUP, 1);
+    const int max_grid = 64 * std::max(ctx_->sm_count, 1);
+    // one arena: plan the offsets, allocate once, then bind the pointers
+    size_t off = 0;
+    auto plan = [&](size_t bytes) {
+        const size_t o = off;
+        off += align_up(bytes, 256);
+        return o;
+    };
+    const size_t o_x = plan(mat), o_v = plan(mat), o_pb = plan(mat), o_pbc = plan(vec), o_cost = plan(vec);
+    const size_t o_x2 = seq ? plan(mat) : 0, o_v2 = seq ? plan(mat) : 0;
+    const size_t o_G = plan(n * sizeof(double)), o_lo = plan(n * sizeof(double)), o_hi = plan(n * sizeof(double));
+    const size_t o_ctrl = plan(sizeof(PsoCtrl));
+    const size_t o_pc = plan(max_grid * sizeof(double)), o_pi = plan(max_grid * sizeof(long long));
+    const size_t o_gm = plan(ngroups * sizeof(double));
+    const size_t o_send = plan(R);
+    const bool own_recv = !(world == 1 && !manual_);
+    const size_t o_recv = own_recv ? plan(R * world) : o_send;
+    EQS_CUDA(ctx_, cudaMalloc(&arena_, off));
+    char *base = (char *)arena_;
+    D.x = (double *)(base + o_x);
+    D.v = (double *)(base + o_v);
+    D.pb = (double *)(base + o_pb);
+    D.pbc = (double *)(base + o_pbc);
+    D.cost = (double *)(base + o_cost);
+    D.x2 = seq ? (double *)(base + o_x2) : nullptr;
+    D.v2 = seq ? (double *)(base + o_v2) : nullptr;
+    D.G = (double *)(base + o_G);
+    double *lo = (double *)(base + o_lo), *hi = (double *)(base + o_hi);
+    D.lower = lo;
+    D.upper = hi;
+    D.ctrl = (PsoCtrl *)(base + o_ctrl);
+    D.part_cost = (double *)(base + o_pc);
+    D.part_idx = (long long *)(base + o_pi);
+    D.group_min = (double *)(base + o_gm);
+    D.send = (double *)(base + o_send);
+    D.recv = (double *)(base + o_recv);
+    max_grid_ = max_grid;
+    EQS_CUDA(ctx_, cudaMemcpyAsync(lo, lower_.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx_->stream));
+    EQS_CUDA(ctx_, cudaMemcpyAsync(hi, upper_.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx_->stream));
+    EQS_CUDA(ctx_, cudaMemsetAsync(D.ctrl, 0, sizeof(PsoCtrl), ctx_->stream));
+    EQS_CUDA(ctx_, cudaMemsetAsync(D.send, 0, R, ctx_->stream));
+    EQS_CUDA(ctx_, cudaMallocHost(&h_ctrl_, sizeof(PsoCtrl)));
+    memset(h_ctrl_, 0, sizeof(PsoCtrl));
+    EQS_CUDA(ctx_, cudaEventCreate(&ev0_));
+    EQS_CUDA(ctx_, cudaEventCreate(&ev1_));
+    return EQS_OK;
+}
+
+int PsoSolver::upload_replay(const double *host, int64_t doubles)
+{
+    const size_t bytes = (size_t)doubles * sizeof(double);
+    if (bytes > replay_cap_) {
+        if (replay_buf_) EQS_CUDA(ctx_, cudaFree(replay_buf_));
+        replay_buf_ = nullptr;
+        EQS_CUDA(ctx_, cudaMalloc(&replay_buf_, bytes));
+        replay_cap_ = bytes;
+    }
+    EQS_CUDA(ctx_, cudaMemcpyAsync(replay_buf_, host, bytes, cudaMemcpyHostToDevice, ctx_->stream));
+    return EQS_OK;
+}
+
+int PsoSolver::exchange()
+{
+    if (manual_ || d_.world == 1) return EQS_OK;
+    return comm_allgather_f64(ctx_, d_.send, d_.recv, record_doubles(d_.n), ctx_->stream);
+}
+
+int PsoSolver::fetch_ctrl()
+{
+    EQS_CUDA(ctx_, cudaMemcpyAsync(h_ctrl_, d_.ctrl, sizeof(PsoCtrl), cudaMemcpyDeviceToHost, ctx_->stream));
+    EQS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+    return EQS_OK;
+}
+
+int PsoSolver::launch_init_eval()
+{
+    const bool replay = p_.replay_init != nullptr;
+    int rc = EQS_OK;
+    if (replay) {
+        EQS_TRY(upload_replay(p_.replay_init, p_.particle_count * 2 * (int64_t)p_.n));
+        d_.replay = replay_buf_;
+    } else {
+        d_.replay = nullptr;
+    }
+    const long long ngroups = (d_.nloc + PSO_GROUP - 1) / PSO_GROUP;
+    dispatch_objective(p_.objective_id, [&]<class Obj>() {
+        pso_x0_kernel<Obj><<<1, 32, 0, ctx_->stream>>>(d_);
+        launches_++;
+        auto run = [&](auto kernel) {
+            int grid = 1;
+            rc = persistent_grid(ctx_, kernel, PSO_BLOCK, 0, 1, ngroups, grid);
+            if (rc != EQS_OK) return;
+            kernel<<<grid, PSO_BLOCK, 0, ctx_->stream>>>(d_);
+            launches_++;
+        };
+        if (replay) run(pso_init_kernel<Obj, true>);
+        else run(pso_init_kernel<Obj, false>);
+    });
+    EQS_TRY(rc);
+    EQS_CUDA(ctx_, cudaGetLastError());
+    d_.replay = nullptr;
+    return EQS_OK;
+}
+
+int PsoSolver::launch_ring_scan()
+{
+    pso_ring_scan_kernel<<<1, 1024, 0, ctx_->stream>>>(d_);
+    launches_++;
+    EQS_CUDA(ctx_, cudaGetLastError());
+    return EQS_OK;
+}
+
+int PsoSolver::launch_init_apply()
+{
+    pso_init_apply_kernel<<<1, 128, 0, ctx_->stream>>>(d_);
+    launches_++;
+    EQS_CUDA(ctx_, cudaGetLastError());
+    return EQS_OK;
+}
+
+int PsoSolver::init_local(const double *x0, int phase)
+{
+    EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
+    if (phase == 0) {
+        EQS_CUDA(ctx_, cudaMemcpyAsync(d_.G, x0, d_.n * sizeof(double), cudaMemcpyHostToDevice, ctx_->stream));
+        return launch_init_eval();
+    }
+    return launch_ring_scan();
+}
+
+int PsoSolver::init_apply() { return launch_init_apply(); }
+
+int PsoSolver::init(const double *x0)
+{
+    if (manual_ && d_.world > 1) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "exchange = MANUAL: use the split-phase calls");
+    EQS_TRY(init_local(x0, 0));
+    EQS_TRY(exchange());
+    EQS_TRY(init_local(x0, 1));
+    EQS_TRY(exchange());
+    return init_apply();
+}
+
+int PsoSolver::launch_step()
+{
+    const bool replay = d_.replay != nullptr;
+    const int vec = replay ? 1 : env_int("EQS_PSO_VEC", 2);
+    const size_t smem = (size_t)d_.n * sizeof(double);
+    const int inline_apply = (d_.world == 1 && !manual_) ? 1 : 0;
+    int rc = EQS_OK;
+    dispatch_objective(p_.objective_id, [&]<class Obj>() {
+        auto run = [&](auto kernel, int v) {
+            if (grid_step_ == 0) {
+                rc = persistent_grid(ctx_, kernel, PSO_BLOCK, smem, (long long)PSO_BLOCK * v, d_.nloc, grid_step_);
+                if (rc != EQS_OK) return;
+            }
+            kernel<<<grid_step_, PSO_BLOCK, smem, ctx_->stream>>>(d_, inline_apply);
+            launches_++;
+        };
+        if (replay) run(pso_step_kernel<Obj, true, 1>, 1);
+        else if (vec == 1) run(pso_step_kernel<Obj, false, 1>, 1);
+        else run(pso_step_kernel<Obj, false, 2>, 2);
+    });
+    EQS_TRY(rc);
+    EQS_CUDA(ctx_, cudaGetLastError());
+    return EQS_OK;
+}
+
+int PsoSolver::launch_step_apply()
+{
+    if (d_.world == 1 && !manual_) return EQS_OK; // applied by the last block of the step kernel
+    pso_step_apply_kernel<<<1, 128, 0, ctx_->stream>>>(d_);
+    launches_++;
+    EQS_CUDA(ctx_, cudaGetLastError());
+    return EQS_OK;
+}
+
+int PsoSolver::sequential_pass()
+{
+    EQS_TRY(fetch_ctrl());
+    if (h_ctrl_->stalled) return EQS_OK;
+    const bool replay = d_.replay != nullptr;
+    const size_t smem = (size_t)d_.n * sizeof(double);
+    long long start = 0;
+    for (;;) {
+        int rc = EQS_OK;
+        dispatch_objective(p_.objective_id, [&]<class Obj>() {
+            auto run = [&](auto kernel) {
+                int grid = 1;
+                rc = persistent_grid(ctx_, kernel, PSO_BLOCK, smem, PSO_BLOCK, d_.nloc, grid);
+                if (rc != EQS_OK) return;
+                kernel<<<grid, PSO_BLOCK, smem, ctx_->stream>>>(d_, start);
+                launches_++;
+            };
+            if (replay) run(pso_spec_kernel<Obj, true>);
+            else run(pso_spec_kernel<Obj, false>);
+        });
+        EQS_TRY(rc);
+        EQS_CUDA(ctx_, cudaGetLastError());
+        EQS_TRY(exchange());
+        pso_spec_apply_kernel<<<1, 128, 0, ctx_->stream>>>(d_);
+        launches_++;
+        EQS_TRY(fetch_ctrl());
+        const long long istar = h_ctrl_->spec_first;
+        const long long end = istar >= 0 ? istar : d_.ntotal - 1;
+        int grid = 1;
+        EQS_TRY(persistent_grid(ctx_, pso_commit_kernel, PSO_BLOCK, 0, PSO_BLOCK, d_.nloc, grid));
+        pso_commit_kernel<<<grid, PSO_BLOCK, 0, ctx_->stream>>>(d_, start, end);
+        launches_++;
+        EQS_CUDA(ctx_, cudaGetLastError());
+        if (h_ctrl_->pass_done) break;
+        start = istar + 1;
+    }
+    return EQS_OK;
+}
+
+int PsoSolver::step_local(const double *replay_step)
+{
+    EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
+    if (p_.mode != EQS_PSO_SYNCHRONOUS) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "split-phase stepping is synchronous-mode only");
+    if (replay_step) {
+        EQS_TRY(fetch_ctrl());
+        EQS_TRY(upload_replay(replay_step, p_.particle_count * 2 * (int64_t)p_.n));
+        d_.replay = replay_buf_;
+        d_.replay_t0 = h_ctrl_->iter;
+    } else {
+        d_.replay = nullptr;
+    }
+    grid_step_ = 0;
+    return launch_step();
+}
+
+int PsoSolver::step_apply() { return launch_step_apply(); }
+
+int PsoSolver::step(int64_t iters, const double *replay_step)
+{
+    EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
+    if (manual_ && d_.world > 1) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "exchange = MANUAL: use the split-phase calls");
+    if (replay_step) {
+        EQS_TRY(fetch_ctrl());
+        EQS_TRY(upload_replay(replay_step, iters * p_.particle_count * 2 * (int64_t)p_.n));
+        d_.replay = replay_buf_;
+        d_.replay_t0 = h_ctrl_->iter;
+    } else {
+        d_.replay = nullptr;
+    }
+    grid_step_ = 0;
+    const int64_t l0 = launches_;
+    EQS_CUDA(ctx_, cudaEventRecord(ev0_, ctx_->stream));
+    for (int64_t it = 0; it < iters; ++it) {
+        if (p_.mode == EQS_PSO_SYNCHRONOUS) {
+            EQS_TRY(launch_step());
+            EQS_TRY(exchange());
+            EQS_TRY(launch_step_apply());
+        } else {
+            EQS_TRY(sequential_pass());
+        }
+    }
+    EQS_CUDA(ctx_, cudaEventRecord(ev1_, ctx_->stream));
+    last_launches_ = launches_ - l0;
+    return EQS_OK;
+}
+
+int PsoSolver::sync()
+{
+    EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
+    EQS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+    return EQS_OK;
+}
+
+int PsoSolver::read_gbest(double *g, double *cost, int64_t *iters, int32_t *stalled, int64_t *improvements)
+{
+    EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
+    if (g) EQS_CUDA(ctx_, cudaMemcpyAsync(g, d_.G, d_.n * sizeof(double), cudaMemcpyDeviceToHost, ctx_->stream));
+    EQS_TRY(fetch_ctrl());
+    if (cost) *cost = h_ctrl_->Gc;
+    if (iters) *iters = h_ctrl_->iter;
+    if (stalled) *stalled = h_ctrl_->stalled;
+    if (improvements) *improvements = h_ctrl_->improvements;
+    return EQS_OK;
+}
+
+int PsoSolver::read_state(double *x, double *v, double *pb, double *pbc)
+{
+    EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
+    const int n = d_.n;
+    const long long L = d_.nloc, ld = d_.ld;
+    std::vector<double> tmp((size_t)n * ld);
+    auto pull = [&](const double *dev, double *out) -> int {
+        if (!out) return EQS_OK;
+        EQS_CUDA(ctx_, cudaMemcpyAsync(tmp.data(), dev, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx_->stream));
+        EQS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+        for (long long i = 0; i < L; ++i)
+            for (int d = 0; d < n; ++d) out[i * n + d] = tmp[(size_t)d * ld + i]; // SoA -> the reference's particle-major
+        return EQS_OK;
+    };
+    EQS_TRY(pull(d_.x, x));
+    EQS_TRY(pull(d_.v, v));
+    EQS_TRY(pull(d_.pb, pb));
+    if (pbc) {
+        EQS_CUDA(ctx_, cudaMemcpyAsync(pbc, d_.pbc, L * sizeof(double), cudaMemcpyDeviceToHost, ctx_->stream));
+        EQS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+    }
+    return EQS_OK;
+}
+
+int PsoSolver::read_ring(double *ring, int64_t *ring_i)
+{
+    EQS_TRY(fetch_ctrl());
+    if (ring) memcpy(ring, h_ctrl_->ring, sizeof(h_ctrl_->ring));
+    if (ring_i) *ring_i = h_ctrl_->ring_i;
+    return EQS_OK;
+}
+
+int PsoSolver::get_record(double *rec)
+{
+    EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
+    EQS_CUDA(ctx_, cudaMemcpyAsync(rec, d_.send, record_doubles(d_.n) * sizeof(double), cudaMemcpyDeviceToHost, ctx_->stream));
+    EQS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+    return EQS_OK;
+}
+
+int PsoSolver::set_records(const double *recs)
+{
+    EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
+    EQS_CUDA(ctx_, cudaMemcpyAsync(d_.recv, recs, d_.world * record_doubles(d_.n) * sizeof(double), cudaMemcpyHostToDevice,
+                                   ctx_->stream));
+    EQS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+    return EQS_OK;
+}
+
+// ParticleSwarm::solve, particle_swarm.rs:356-431
+int PsoSolver::solve(const double *x0, double *out_x, eqs_report *rep)
+{
+    cudaEvent_t e0, e1, e2;
+    EQS_CUDA(ctx_, cudaEventCreate(&e0));
+    EQS_CUDA(ctx_, cudaEventCreate(&e1));
+    EQS_CUDA(ctx_, cudaEventCreate(&e2));
+    const int64_t l0 = launches_;
+    EQS_CUDA(ctx_, cudaEventRecord(e0, ctx_->stream));
+    int st = init(x0);
+    if (st == EQS_OK) st = cudaEventRecord(e1, ctx_->stream) == cudaSuccess ? EQS_OK : EQS_ERR_EXTERNAL;
+    // the stall test lives on the device; the host only looks every kBatch passes to stop launching no-ops
+    const int64_t kBatch = 64;
+    int64_t left = p_.iter_max;
+    while (st == EQS_OK && left > 0) {
+        const int64_t b = std::min(kBatch, left);
+        st = step(b, nullptr);
+        left -= b;
+        if (st == EQS_OK && left > 0) {
+            st = fetch_ctrl();
+            if (st == EQS_OK && h_ctrl_->stalled) break;
+        }
+    }
+    if (st == EQS_OK) {
+        cudaEventRecord(e2, ctx_->stream);
+        st = read_gbest(out_x, nullptr, nullptr, nullptr, nullptr); // Ok(global_best_position), :430
+    }
+    if (st == EQS_OK && rep) {
+        float ms_init = 0.f, ms_loop = 0.f;
+        cudaEventElapsedTime(&ms_init, e0, e1);
+        cudaEventElapsedTime(&ms_loop, e1, e2);
+        rep->iters_run = h_ctrl_->iter;
+        rep->evals = 1 + p_.particle_count * (1 + h_ctrl_->iter);
+        rep->best_cost = h_ctrl_->Gc;
+        rep->stalled = h_ctrl_->stalled;
+        rep->world = d_.world;
+        rep->kernel_launches = launches_ - l0;
+        rep->init_ms = ms_init;
+        rep->loop_ms = ms_loop;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    return st;
+}
+
+} // namespace eqs

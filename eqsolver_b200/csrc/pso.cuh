@@ -1,0 +1,99 @@
+// pso.cuh -- device-side state of one ParticleSwarm shard and the host driver class.
+//
+// Data layout in HBM: structure of arrays, dimension-major, particle-contiguous
+//   x, v, pbest : [n][ld] f64   (ld = local particle count rounded up to 16 => 128-byte rows)
+//   pbest_cost  : [ld]   f64
+// replacing the reference's array of structs `Vec<Particle>` (particle_swarm.rs:14-22, 361-389), so that
+// thread i of a warp reads lane-contiguous 8/16-byte words for every dimension d.
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace eqs {
+
+// device-resident control block: everything the outer loop (particle_swarm.rs:394-428) decides on
+struct PsoCtrl {
+    double Gc;                      // global_best_cost
+    double ring[EQS_STALL_WINDOW];  // CircularArray<T,50> previous_best (:24-46,359)
+    long long ring_i;
+    long long iter;                 // outer-loop passes that ran
+    long long improvements;         // gbest improvements so far
+    long long spec_first;           // sequential mode: first improving global index of the last round, -1 = none
+    int stalled;                    // result of stalled_too_long (:433-441) for the NEXT pass
+    int pass_done;                  // sequential mode: the speculate-and-repair pass is complete
+    unsigned int block_counter;     // last-block-done ticket
+    int nan_seen;
+};
+
+struct PsoDev {
+    double *x, *v, *pb, *pbc;       // population, SoA [n][ld]
+    double *cost;                   // [ld] costs of the last evaluation (init ring scan, sequential mode)
+    double *x2, *v2;                // sequential mode: speculative next state
+    double *G;                      // [n] global_best_position
+    PsoCtrl *ctrl;
+    double *part_cost;              // [grid] per-block partial min-loc
+    long long *part_idx;
+    double *group_min;              // [ceil(nloc/GROUP)] per-tile minimum of the init costs
+    double *send, *recv;            // exchange records: [R], [world][R]
+    const double *lower, *upper;    // [n]
+    const double *replay;           // device copy of the caller's draw stream, or nullptr
+    long long ld, nloc, first, ntotal;
+    long long replay_t0;            // iteration index of replay block 0
+    int n, world, rank;
+    double w, c1, c2, tol;
+    PhiloxKey key;
+};
+
+constexpr int PSO_BLOCK = 256;
+constexpr int PSO_GROUP = 256; // particles per init tile = granularity of the ring scan
+
+int validate_pso_params(const eqs_pso_params *p, std::string *why);
+
+class PsoSolver {
+public:
+    PsoSolver(Ctx *ctx) : ctx_(ctx) {}
+    ~PsoSolver();
+    int create(const eqs_pso_params *p);
+    int init(const double *x0);
+    int init_local(const double *x0, int phase);
+    int init_apply();
+    int step(int64_t iters, const double *replay_step);
+    int step_local(const double *replay_step);
+    int step_apply();
+    int sync();
+    int read_gbest(double *g, double *cost, int64_t *iters, int32_t *stalled, int64_t *improvements);
+    int read_state(double *x, double *v, double *pb, double *pbc);
+    int read_ring(double *ring, int64_t *ring_i);
+    int get_record(double *rec);
+    int set_records(const double *recs);
+    int solve(const double *x0, double *out_x, eqs_report *rep);
+
+    Ctx *ctx_;
+    eqs_pso_params p_{};
+    PsoDev d_{};
+    std::vector<double> lower_, upper_;
+    void *arena_ = nullptr;
+    double *replay_buf_ = nullptr;
+    size_t replay_cap_ = 0;
+    PsoCtrl *h_ctrl_ = nullptr; // pinned mirror
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    int grid_step_ = 0, grid_init_ = 0;
+    int64_t launches_ = 0;
+    int64_t last_launches_ = 0;
+    float last_ms_ = 0.f;
+    bool manual_ = false;
+    int max_grid_ = 0;
+
+private:
+    int upload_replay(const double *host, int64_t iters);
+    int exchange();
+    int launch_init_eval();
+    int launch_ring_scan();
+    int launch_init_apply();
+    int launch_step();
+    int launch_step_apply();
+    int sequential_pass();
+    int fetch_ctrl();
+};
+
+} // namespace eqs

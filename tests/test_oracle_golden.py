@@ -1,0 +1,146 @@
+"""CPU: the C oracle (oracle/eqs_oracle.c) against the committed golden fixtures (tests/golden/make_golden.py)."""
+import numpy as np
+
+from conftest import assert_bit_equal, from_bits, golden
+from oracle import oracle as O
+
+
+def test_objective_kats_bit_exact():
+    for e in golden("objective_kats.json"):
+        got = O.objective(e["objective"], e["x"])
+        assert_bit_equal([got], [from_bits(e["bits"])], e["note"])
+
+
+def test_survey_objective_anchors():
+    # SURVEY.md §4 item 3 (computed there with glibc libm): the reference's own inputs
+    assert O.objective(O.RASTRIGIN, [80., -81., 82., -83., 84., -85., 86., -87., 88., -89.]) == 71485.0
+    assert O.objective(O.RASTRIGIN, [0.4] * 30) == 547.5050983124845
+    assert O.objective(O.RASTRIGIN, [80.] * 16) == 102400.0
+    assert O.objective(O.ROSENBROCK, [-1.2, 1.0]) == 24.199999999999996
+    assert O.objective(O.ACKLEY, [0.0] * 256) == 4.440892098500626e-16
+    assert O.objective(O.ACKLEY, [1.0] * 256) == 3.6253849384403627
+    # summation order of nalgebra's norm is third-party (unverified): tolerance, not bits
+    assert abs(O.objective(O.HEAVY, [0.3] * 100) - 52.351074487540366) < 1e-13
+    # reference tests/multi.rs:70: the three-circles least-squares point; it must be a local minimum
+    sol = np.array([4.217265312839526, 2.317879970005811])
+    f0 = O.objective(O.THREE_CIRCLES, sol)
+    for dx in (1e-4, -1e-4):
+        assert O.objective(O.THREE_CIRCLES, sol + [dx, 0]) > f0
+        assert O.objective(O.THREE_CIRCLES, sol + [0, dx]) > f0
+
+
+def test_philox_random123_kats():
+    g = golden("philox_kats.json")
+    for v in g["random123"]:
+        assert O.philox4x32_10(v["ctr"], v["key"]) == v["out"]
+
+
+def test_philox_draw_contract():
+    M = 0xFFFFFFFF
+    for v in golden("philox_kats.json")["contract"]:
+        ctr = [v["gidx"] & M, (v["gidx"] >> 32) & M, ((v["stream"] << 28) | v["j"]) & M, v["t"] & M]
+        key = [v["seed"] & M, (v["seed"] >> 32) & M]
+        w = O.philox4x32_10(ctr, key)
+        assert w == v["words"]
+        assert_bit_equal([O.u01(w[0], w[1]), O.u01(w[2], w[3])], [from_bits(v["u_lo"]), from_bits(v["u_hi"])])
+    # the oracle's draw helpers follow the same contract
+    pos, vel = O.pso_init_draws(1729, 0, 1)
+    v0 = golden("philox_kats.json")["contract"][0]
+    assert_bit_equal([pos[0], vel[0]], [from_bits(v0["u_lo"]), from_bits(v0["u_hi"])])
+    rp, rg = O.pso_step_draws(1729, 7, 123456789, 32)
+    v1 = golden("philox_kats.json")["contract"][1]
+    assert_bit_equal([rp[31], rg[31]], [from_bits(v1["u_lo"]), from_bits(v1["u_hi"])])
+
+
+def test_normals_are_standard():
+    z = np.concatenate([O.ce_normals(5, 0, i, 64) for i in range(2000)])
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
+    assert abs(np.mean(z ** 3)) < 0.05 and abs(np.mean(z ** 4) - 3.0) < 0.1
+
+
+def test_pso_trajectories_bit_exact():
+    for g in golden("pso_golden.json"):
+        o = O.Pso(g["objective"], g["lower"], g["upper"], particle_count=g["N"], iter_max=g["iters"], mode=g["mode"],
+                  seed=g["seed"])
+        o.init(g["x0"])
+        tr = g["trace"]
+        assert_bit_equal(o.gbest(), [from_bits(b) for b in tr[0]["gbest"]], "gbest after init")
+        assert_bit_equal([o.gbest_cost()], [from_bits(tr[0]["gbest_cost"])])
+        assert o.ring()[1] == tr[0]["ring_i"]
+        for t in range(1, len(tr)):
+            assert o.step() == 0
+            assert_bit_equal(o.gbest(), [from_bits(b) for b in tr[t]["gbest"]], f"gbest after pass {t}")
+            assert_bit_equal([o.gbest_cost()], [from_bits(tr[t]["gbest_cost"])])
+            assert o.ring()[1] == tr[t]["ring_i"], f"ring index after pass {t}"
+        x, v, pb, pbc = o.state()
+        assert_bit_equal(x, [[from_bits(b) for b in row] for row in g["final_x"]], "positions")
+        assert_bit_equal(v, [[from_bits(b) for b in row] for row in g["final_v"]], "velocities")
+        assert_bit_equal(pbc, [from_bits(b) for b in g["final_pbest_cost"]], "pbest costs")
+        assert_bit_equal(o.ring()[0], [from_bits(b) for b in g["ring"]], "stall ring")
+
+
+def test_ce_trajectories_bit_exact():
+    for g in golden("ce_golden.json"):
+        z = np.array([[[from_bits(b) for b in row] for row in it] for it in g["normals"]])
+        o = O.Ce(g["objective"], g["x0"], sample_size=g["N"], elite_count=g["k"], iter_max=g["iter_max"],
+                 std_dev=g["sigma0"], replay_normals=z,
+                 mean_divisor=O.DIV_REFERENCE_TEN if g["divisor_ten"] else O.DIV_ELITE_COUNT)
+        for t, tr in enumerate(g["trace"]):
+            assert o.step() == 0
+            mu, sg = o.state()
+            assert_bit_equal(mu, [from_bits(b) for b in tr["mu"]], f"mu after pass {t}")
+            assert_bit_equal(sg, [from_bits(b) for b in tr["sigma"]], f"sigma after pass {t}")
+            assert list(o.elites()) == tr["elites"]
+        assert o.step() == 1  # iter reached iter_max (cross_entropy.rs:255)
+
+
+def test_pso_sharded_protocol_equals_unsharded():
+    """The exchange protocol on 3 virtual shards reproduces the unsharded synchronous oracle."""
+    n, N, iters, world = 5, 97, 8, 3
+    lo, hi, x0 = [-5.0] * n, [10.0] * n, [3.0] * n
+    ref = O.Pso(O.ROSENBROCK, lo, hi, particle_count=N, iter_max=iters, mode=O.SYNCHRONOUS, seed=3, tol=0.0)
+    ref.init(x0)
+    shards = []
+    for r in range(world):
+        base, rem = divmod(N, world)
+        first = r * base + min(r, rem)
+        shards.append(O.Pso(O.ROSENBROCK, lo, hi, particle_count=N, iter_max=iters, mode=O.SYNCHRONOUS, seed=3,
+                            tol=0.0, first_index=first, local_count=base + (1 if r < rem else 0)))
+    recs = np.stack([s.init_local(x0) for s in shards])
+    f0 = O.objective(O.ROSENBROCK, x0)
+    pushes, tails = [], []
+    for r, s in enumerate(shards):
+        seed_cost = min([f0] + [recs[q, 0] for q in range(r) if recs[q, 1] >= 0])
+        k, tail = s.init_ring_local(seed_cost)
+        pushes.append(k); tails.append(tail)
+    for s in shards:
+        s.init_apply(recs, pushes, np.stack(tails))
+        assert_bit_equal(s.gbest(), ref.gbest()); assert_bit_equal(s.ring()[0], ref.ring()[0])
+        assert s.ring()[1] == ref.ring()[1]
+    for _ in range(iters):
+        ref.step()
+        out = [s.step_local() for s in shards]
+        recs = np.stack([o[1] for o in out])
+        for s in shards:
+            s.step_apply(recs)
+            assert_bit_equal(s.gbest(), ref.gbest()); assert_bit_equal([s.gbest_cost()], [ref.gbest_cost()])
+    x = np.concatenate([s.state()[0] for s in shards])
+    assert_bit_equal(x, ref.state()[0])
+
+
+def test_pso_validate_like_new():
+    import pytest
+    with pytest.raises(ValueError):
+        O.Pso(O.SPHERE, [1.0, 0.0], [0.0, 1.0])      # lower > upper -> Uniform::new_inclusive error
+    with pytest.raises(ValueError):
+        O.Pso(O.SPHERE, [0.0], [float("inf")])
+
+
+def test_known_optima():
+    x = O.Pso(O.SPHERE, [-5] * 4, [5] * 4, particle_count=400, iter_max=200, seed=1, tol=0.0).solve([4.0] * 4)
+    assert O.objective(O.SPHERE, x) < 1e-12
+    x = O.Pso(O.THREE_CIRCLES, [1, 1], [7, 7], particle_count=200, iter_max=200, seed=2, tol=0.0).solve([4.5, 2.5])
+    assert np.allclose(x, [4.217265312839526, 2.317879970005811], atol=1e-5)
+    mu = O.Ce(O.SPHERE, [3.0] * 4, sample_size=400, elite_count=40, iter_max=80, std_dev=[2.0] * 4,
+              mean_divisor=O.DIV_ELITE_COUNT, seed=3).solve()
+    assert O.objective(O.SPHERE, mu) < 1e-8

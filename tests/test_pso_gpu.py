@@ -1,0 +1,284 @@
+"""GPU: the CUDA ParticleSwarm path (through the C ABI) against the CPU oracle on identical draws."""
+import numpy as np
+import pytest
+
+import eqsolver_b200 as E
+from conftest import assert_bit_equal, from_bits, golden
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+OBJ_POINTS = {
+    E.Objective.SPHERE: 7, E.Objective.ROSENBROCK: 9, E.Objective.RASTRIGIN: 10, E.Objective.ACKLEY: 12,
+    E.Objective.THREE_CIRCLES: 2, E.Objective.HEAVY: 11, E.Objective.USER: 6,
+}
+
+
+def test_objective_kats(ctx):
+    for e in golden("objective_kats.json"):
+        got = ctx.objective_eval(e["objective"], e["x"])[0]
+        want = from_bits(e["bits"])
+        if e["objective"] in (2, 3):  # cos/exp: libdevice vs glibc, <= a few ulp of the summands
+            assert abs(got - want) <= 1e-12 * max(1.0, abs(want)) + 1e-13, e["note"]
+        else:
+            assert_bit_equal([got], [want], e["note"])
+
+
+def test_objectives_random_points_vs_oracle(ctx):
+    rng = np.random.default_rng(0)
+    for obj, n in OBJ_POINTS.items():
+        x = rng.uniform(-3, 3, size=(257, n))
+        got = ctx.objective_eval(obj, x)
+        want = np.array([O.objective(int(obj), row) for row in x])
+        if obj in (E.Objective.RASTRIGIN, E.Objective.ACKLEY):
+            np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-12)
+        else:
+            assert_bit_equal(got, want, obj.name)
+
+
+def test_philox_kats_and_contract(ctx):
+    g = golden("philox_kats.json")
+    for v in g["random123"]:
+        assert list(ctx.philox_blocks([v["ctr"]], v["key"])[0]) == v["out"]
+    rng = np.random.default_rng(1)
+    ctr = rng.integers(0, 2 ** 32, size=(1000, 4), dtype=np.uint64).astype(np.uint32)
+    key = np.array([123456789, 987654321], dtype=np.uint32)
+    got = ctx.philox_blocks(ctr, key)
+    for i in range(0, 1000, 37):
+        assert list(got[i]) == O.philox4x32_10(ctr[i], key)
+
+
+def test_draws_match_oracle_bit_exact(ctx):
+    seed, n = 2 ** 40 + 1729, 9
+    pos, vel = ctx.draws(0, seed, 0, 2 ** 33, 50, n)
+    rp, rg = ctx.draws(1, seed, 17, 123, 50, n)
+    for i in (0, 1, 49):
+        p, v = O.pso_init_draws(seed, 2 ** 33 + i, n)
+        assert_bit_equal(pos[i], p); assert_bit_equal(vel[i], v)
+        a, b = O.pso_step_draws(seed, 17, 123 + i, n)
+        assert_bit_equal(rp[i], a); assert_bit_equal(rg[i], b)
+    (z,) = ctx.draws(2, seed, 3, 1000, 64, n)
+    want = np.stack([O.ce_normals(seed, 3, 1000 + i, n) for i in range(64)])
+    np.testing.assert_allclose(z, want, rtol=0, atol=4e-15)  # log/sincospi: libdevice vs glibc
+
+
+def make(objective, n, N, mode, seed, lo=-5.0, hi=10.0, tol=0.0, iter_max=50):
+    lower, upper = [lo] * n, [hi] * n
+    g = (E.ParticleSwarm.new(objective, lower, upper).with_particle_count(N).with_iter_max(iter_max).with_tol(tol)
+         .with_seed(seed).with_mode(mode))
+    o = O.Pso(int(objective), lower, upper, particle_count=N, iter_max=iter_max, tol=tol, mode=int(mode), seed=seed)
+    return g, o
+
+
+def compare_state(run, orc, exact, what):
+    gx, gv, gpb, gpbc = run.state()
+    ox, ov, opb, opbc = orc.state()
+    g, gc, it, stalled, _ = run.gbest()
+    if exact:
+        assert_bit_equal(gx, ox, what + " x"); assert_bit_equal(gv, ov, what + " v")
+        assert_bit_equal(gpb, opb, what + " pbest"); assert_bit_equal(gpbc, opbc, what + " pbest cost")
+        assert_bit_equal(g, orc.gbest(), what + " gbest"); assert_bit_equal([gc], [orc.gbest_cost()])
+        assert_bit_equal(run.ring()[0], orc.ring()[0], what + " ring")
+    else:  # north_star: positions and velocities within 1e-12 relative
+        np.testing.assert_allclose(gx, ox, rtol=1e-12, atol=1e-12, err_msg=what)
+        np.testing.assert_allclose(gv, ov, rtol=1e-12, atol=1e-12, err_msg=what)
+        np.testing.assert_allclose(gpbc, opbc, rtol=1e-12, atol=1e-12, err_msg=what)
+        np.testing.assert_allclose(g, orc.gbest(), rtol=1e-12, atol=1e-12, err_msg=what)
+    assert run.ring()[1] == orc.ring()[1], what + " ring index"
+    assert it == orc.iters()
+
+
+@pytest.mark.parametrize("mode", [E.PsoMode.SYNCHRONOUS, E.PsoMode.SEQUENTIAL_EXACT])
+def test_golden_trajectories(ctx, mode):
+    for g in golden("pso_golden.json"):
+        if g["mode"] != int(mode):
+            continue
+        ps = (E.ParticleSwarm.new(g["objective"], g["lower"], g["upper"]).with_particle_count(g["N"])
+              .with_iter_max(g["iters"]).with_seed(g["seed"]).with_mode(mode).with_context(ctx))
+        run = ps.start(g["x0"])
+        tr = g["trace"]
+        gb, gc, _, _, _ = run.gbest()
+        assert_bit_equal(gb, [from_bits(b) for b in tr[0]["gbest"]]); assert_bit_equal([gc], [from_bits(tr[0]["gbest_cost"])])
+        for t in range(1, len(tr)):
+            run.step(1)
+            gb, gc, it, _, _ = run.gbest()
+            assert it == t
+            assert_bit_equal(gb, [from_bits(b) for b in tr[t]["gbest"]], f"gbest after pass {t}")
+            assert_bit_equal([gc], [from_bits(tr[t]["gbest_cost"])])
+            assert run.ring()[1] == tr[t]["ring_i"]
+        x, v, pb, pbc = run.state()
+        assert_bit_equal(x, [[from_bits(b) for b in row] for row in g["final_x"]])
+        assert_bit_equal(v, [[from_bits(b) for b in row] for row in g["final_v"]])
+        assert_bit_equal(pbc, [from_bits(b) for b in g["final_pbest_cost"]])
+        assert_bit_equal(run.ring()[0], [from_bits(b) for b in g["ring"]])
+
+
+@pytest.mark.parametrize("objective,exact", [(E.Objective.SPHERE, True), (E.Objective.ROSENBROCK, True),
+                                             (E.Objective.USER, True), (E.Objective.HEAVY, True),
+                                             (E.Objective.RASTRIGIN, False), (E.Objective.ACKLEY, False)])
+@pytest.mark.parametrize("mode", [E.PsoMode.SYNCHRONOUS, E.PsoMode.SEQUENTIAL_EXACT])
+def test_philox_parity_per_iteration(ctx, objective, exact, mode):
+    """Both sides generate the SAME Philox draws; state compared after init and after every pass."""
+    n, N, iters = (7, 1500, 6) if mode == E.PsoMode.SEQUENTIAL_EXACT else (13, 4099, 10)
+    lo, hi = (-5.12, 5.12) if objective in (E.Objective.RASTRIGIN,) else (-5.0, 10.0)
+    g, o = make(objective, n, N, mode, seed=1729, lo=lo, hi=hi)
+    x0 = np.full(n, 3.0)
+    run = g.with_context(ctx).start(x0)
+    o.init(x0)
+    compare_state(run, o, exact, "init")
+    for t in range(iters):
+        run.step(1)
+        assert o.step() == 0
+        compare_state(run, o, exact, f"pass {t}")
+
+
+@pytest.mark.parametrize("mode", [E.PsoMode.SYNCHRONOUS, E.PsoMode.SEQUENTIAL_EXACT])
+def test_replay_mode_host_draws(ctx, mode):
+    """Replay: identical HOST-generated draws (numpy Philox4x64, unrelated to the device generator) fed to both."""
+    n, N, iters = 6, 777, 5
+    rng = np.random.Generator(np.random.Philox(1729))
+    r_init = rng.random((N, 2 * n))
+    r_step = rng.random((iters, N, n, 2))
+    lower, upper = [-5.0] * n, [10.0] * n
+    g = (E.ParticleSwarm.new(E.Objective.ROSENBROCK, lower, upper).with_particle_count(N).with_iter_max(iters)
+         .with_tol(0.0).with_mode(mode).with_replay_init(r_init).with_context(ctx))
+    o = O.Pso(O.ROSENBROCK, lower, upper, particle_count=N, iter_max=iters, tol=0.0, mode=int(mode),
+              replay_init=r_init, replay_step=r_step)
+    x0 = np.zeros(n)
+    run = g.start(x0)
+    o.init(x0)
+    compare_state(run, o, True, "init")
+    # two passes in one call, then one at a time
+    run.step(2, r_step[:2]); o.step(); o.step()
+    compare_state(run, o, True, "passes 0-1")
+    for t in range(2, iters):
+        run.step(1, r_step[t:t + 1]); o.step()
+        compare_state(run, o, True, f"pass {t}")
+
+
+def test_ragged_and_tiny_populations(ctx):
+    for N in (1, 2, 3, 31, 255, 256, 257, 513):
+        g, o = make(E.Objective.ROSENBROCK, 3, N, E.PsoMode.SYNCHRONOUS, seed=N)
+        x0 = np.array([1.5, -0.5, 2.0])
+        run = g.with_context(ctx).start(x0); o.init(x0)
+        run.step(3); [o.step() for _ in range(3)]
+        compare_state(run, o, True, f"N={N}")
+    # n = 1 (Rosenbrock degenerates to 0), n not a multiple of the unroll
+    for n in (1, 2, 5, 33):
+        g, o = make(E.Objective.SPHERE, n, 300, E.PsoMode.SYNCHRONOUS, seed=n)
+        x0 = np.full(n, 2.0)
+        run = g.with_context(ctx).start(x0); o.init(x0)
+        run.step(4); [o.step() for _ in range(4)]
+        compare_state(run, o, True, f"n={n}")
+
+
+def test_empty_population_and_zero_iterations(ctx):
+    ps = E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * 3, [1.0] * 3).with_particle_count(0).with_context(ctx)
+    x0 = np.array([0.25, 0.5, -0.75])
+    assert_bit_equal(ps.solve(x0), x0)  # no particle ever beats f(x0): gbest stays x0 (particle_swarm.rs:357)
+    ps = E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * 3, [1.0] * 3).with_iter_max(0).with_seed(5).with_context(ctx)
+    o = O.Pso(O.SPHERE, [-1.0] * 3, [1.0] * 3, iter_max=0, seed=5)
+    assert_bit_equal(ps.solve(x0), o.solve(x0))
+
+
+def test_stall_exit_matches_oracle(ctx):
+    """The stall test (particle_swarm.rs:395-397,433-441) fires on the same pass on both sides."""
+    n, N = 2, 64
+    for mode in (E.PsoMode.SEQUENTIAL_EXACT, E.PsoMode.SYNCHRONOUS):
+        g, o = make(E.Objective.SPHERE, n, N, mode, seed=9, lo=-1.0, hi=1.0, tol=1e-3, iter_max=400)
+        x0 = np.array([0.9, -0.9])
+        got = g.with_context(ctx).solve(x0)
+        want = o.solve(x0)
+        assert_bit_equal(got, want)
+        assert g.last_report.iters_run == o.iters()
+        assert o.iters() < 400, "the case must actually stall"
+        assert g.last_report.stalled == 1
+        assert g.last_report.evals == 1 + N * (1 + o.iters())
+
+
+def test_solve_known_optima(ctx):
+    # reference style: loose tolerance on the known answer (tests/integrators.rs:87-116)
+    x = (E.ParticleSwarm.new(E.Objective.RASTRIGIN, [-5.12] * 2, [5.12] * 2).with_particle_count(1000)
+         .with_iter_max(1000).with_tol(0.0).with_mode(E.PsoMode.SYNCHRONOUS).with_seed(1).with_context(ctx)
+         .solve([5.0, 5.0]))
+    assert np.abs(x).max() < 1e-6
+    x = (E.ParticleSwarm.new(E.Objective.THREE_CIRCLES, [1.0, 1.0], [7.0, 7.0]).with_particle_count(500)
+         .with_iter_max(300).with_tol(0.0).with_seed(2).with_context(ctx).solve([4.5, 2.5]))
+    assert np.allclose(x, [4.217265312839526, 2.317879970005811], atol=1e-6)  # tests/multi.rs:70
+    x = (E.ParticleSwarm.new(E.Objective.ROSENBROCK, [-5.0] * 4, [10.0] * 4).with_particle_count(20000)
+         .with_iter_max(600).with_tol(0.0).with_mode(E.PsoMode.SYNCHRONOUS).with_seed(3).with_context(ctx)
+         .solve([0.0] * 4))
+    assert np.allclose(x, 1.0, atol=1e-4)
+
+
+def test_virtual_ranks_match_single_rank(ctx):
+    """Multi-rank protocol on one GPU: 3 virtual ranks, records moved by the harness, equal one rank bit for bit."""
+    n, N, iters, world = 5, 1001, 6, 3
+    lower, upper, x0 = [-5.0] * n, [10.0] * n, np.full(n, 3.0)
+    base = lambda: (E.ParticleSwarm.new(E.Objective.ROSENBROCK, lower, upper).with_particle_count(N).with_tol(0.0)
+                    .with_seed(77).with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx))
+    single = base().start(x0)
+    ranks = [base().with_virtual_rank(r, world).start() for r in range(world)]
+    assert [r.first for r in ranks] == [0, 334, 668] and sum(r.local for r in ranks) == N
+
+    def gather():
+        recs = np.stack([r.get_record() for r in ranks])
+        for r in ranks:
+            r.set_records(recs)
+
+    for r in ranks:
+        r.init_local(x0, 0)
+    gather()
+    for r in ranks:
+        r.init_local(x0, 1)
+    gather()
+    for r in ranks:
+        r.init_apply()
+    for t in range(iters + 1):
+        sg, sc, sit, _, _ = single.gbest()
+        sring = single.ring()
+        for r in ranks:
+            g, c, it, _, _ = r.gbest()
+            assert_bit_equal(g, sg, f"gbest t={t}"); assert_bit_equal([c], [sc]); assert it == sit
+            assert_bit_equal(r.ring()[0], sring[0]); assert r.ring()[1] == sring[1]
+        if t == iters:
+            break
+        single.step(1)
+        for r in ranks:
+            r.step_local()
+        gather()
+        for r in ranks:
+            r.step_apply()
+    x = np.concatenate([r.state()[0] for r in ranks])
+    assert_bit_equal(x, single.state()[0])
+
+
+def test_full_size_c2_properties(ctx):
+    """BASELINE config 2 at full size (Rosenbrock n=32, 2^20 particles): size-independent properties."""
+    n, N = 32, 1 << 20
+    ps = (E.ParticleSwarm.new(E.Objective.ROSENBROCK, [-5.0] * n, [10.0] * n).with_particle_count(N).with_tol(0.0)
+          .with_seed(1729).with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx))
+    run = ps.start(np.zeros(n))
+    _, c_prev, _, _, _ = run.gbest()
+    pbc_prev = run.state()[3]
+    for _ in range(3):
+        run.step(1)
+        x, v, pb, pbc = run.state()
+        g, c, it, _, _ = run.gbest()
+        assert c <= c_prev and np.all(pbc <= pbc_prev)            # gbest / pbest costs never increase
+        assert c == pbc.min()                                      # gbest cost = min pbest cost (f(x0)=31 is beaten)
+        i = int(np.argmin(pbc))
+        assert_bit_equal(pb[i], g)                                 # gbest position = that particle's pbest
+        idx = np.random.default_rng(it).integers(0, N, 64)
+        for j in idx:                                              # pbest cost is f(pbest) -- checksum of the state
+            assert pbc[j] == O.objective(O.ROSENBROCK, pb[j])
+        c_prev, pbc_prev = c, pbc
+    # and a sampled replay against the oracle's arithmetic for pass 3: recompute 32 particles from the state
+    x0s, v0s, pb0s, _ = x, v, pb, pbc
+    g_before = g.copy()
+    run.step(1)
+    x1, v1, _, _ = run.state()
+    for j in np.random.default_rng(5).integers(0, N, 32):
+        rp, rg = O.pso_step_draws(1729, 3, int(j), n)
+        vv = 0.5 * v0s[j] + 1.0 * rp * (pb0s[j] - x0s[j]) + 1.0 * rg * (g_before - x0s[j])
+        assert_bit_equal(v1[j], vv); assert_bit_equal(x1[j], x0s[j] + vv)
