@@ -91,6 +91,10 @@ SYMBOLS = {
     "eqs_ce_read_elites": (C.c_int, [_vp, i64p, i64p]),
     "eqs_ce_read_costs": (C.c_int, [_vp, dp]),
     "eqs_ce_local_range": (C.c_int, [_vp, i64p, i64p]),
+    "eqs_ce_phase": (C.c_int, [_vp, C.c_int32, dp]),
+    "eqs_ce_exchange_words": (C.c_int64, [_vp, C.c_int32]),
+    "eqs_ce_get_exchange": (C.c_int, [_vp, C.c_int32, _vp]),
+    "eqs_ce_set_exchange": (C.c_int, [_vp, C.c_int32, _vp]),
 }
 
 _lib = None

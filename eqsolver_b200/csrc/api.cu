@@ -11,9 +11,6 @@
 
 using namespace eqs;
 
-struct eqs_ctx {
-    Ctx c;
-};
 struct eqs_pso {
     PsoSolver s;
     explicit eqs_pso(Ctx *c) : s(c) {}

@@ -1,17 +1,926 @@
-// ce.cu -- TEMPORARY stub while the CrossEntropy kernels are being written (replaced in the next commit).
+// ce.cu -- CrossEntropy population step on sm_100a (f64; FP64-pipe bound: the sample matrix never touches HBM).
+//
+// Replaces the body of CrossEntropy::solve, reference src/solvers/global_optimisers/cross_entropy.rs:245-306:
+//   ce_sample_kernel   :256-274  x = mu + sigma z (counter-based Philox + Box-Muller in registers), cost only    (K4)
+//   ce_hist / ce_pick  :276      the full sort is replaced by a 6-pass radix SELECT of the k-th cost key          (K5)
+//   ce_flag/scan/compact         elite set = keys below the k-th key + lowest-index ties, in sample order
+//   ce_elite_gen       :284,291  elites are REGENERATED from their counters into a k x n matrix
+//   ce_rowsum + apply  :281-297  two-pass mean / Bessel-corrected sigma per dimension, fixed summation order       (K6)
+//   ce_sigma_apply     :255,299-302  mu, sigma <- new; iter += 1; loop condition for the next pass
+// Each pass is a sequence of PHASES separated by at most one small exchange (histogram or n doubles), so the
+// same code runs on one GPU, over NCCL, or as virtual ranks driven by a test harness.
+#include <algorithm>
+#include <cmath>
+#include <new>
+
 #include "common.cuh"
-using namespace eqs;
-struct eqs_ctx { Ctx c; };
-extern "C" {
-int eqs_ce_validate(const eqs_ce_params *) { return EQS_ERR_EXTERNAL; }
-int eqs_ce_solve(eqs_ctx *, const eqs_ce_params *, const double *, double *, eqs_report *) { return EQS_ERR_EXTERNAL; }
-int eqs_ce_create(eqs_ctx *, const eqs_ce_params *, const double *, eqs_ce **) { return EQS_ERR_EXTERNAL; }
-int eqs_ce_destroy(eqs_ce *) { return EQS_OK; }
-int eqs_ce_step(eqs_ce *, int64_t, const double *) { return EQS_ERR_EXTERNAL; }
-int eqs_ce_sync(eqs_ce *) { return EQS_ERR_EXTERNAL; }
-int eqs_ce_last_step_ms(eqs_ce *, double *, int64_t *) { return EQS_ERR_EXTERNAL; }
-int eqs_ce_read_state(eqs_ce *, double *, double *, int64_t *, int32_t *) { return EQS_ERR_EXTERNAL; }
-int eqs_ce_read_elites(eqs_ce *, int64_t *, int64_t *) { return EQS_ERR_EXTERNAL; }
-int eqs_ce_read_costs(eqs_ce *, double *) { return EQS_ERR_EXTERNAL; }
-int eqs_ce_local_range(eqs_ce *, int64_t *, int64_t *) { return EQS_ERR_EXTERNAL; }
+#include "objectives.cuh"
+#include "philox.cuh"
+
+namespace eqs {
+
+namespace {
+
+constexpr int CE_BLOCK = 256;
+constexpr int CE_BINS = 2048;
+constexpr int CE_PASSES = 6;
+constexpr int CE_TILE = 1024;  // samples per block in flag / compact (256 threads x 4, blocked)
+constexpr int CE_CHUNK = 4096; // elites per block in the row sums
+constexpr int CE_PHASES = 9;
+
+__host__ __device__ inline int pass_shift(int pass) { return pass < 5 ? 53 - 11 * pass : 0; }
+__host__ __device__ inline int pass_width(int pass) { return pass < 5 ? 11 : 9; }
+
+struct CeCtrl {
+    unsigned long long prefix; // bits of the k-th key decided so far
+    long long k_rem;           // rank of the k-th key inside the current bucket (1-based)
+    long long tie_take;        // samples with key == k-th key this rank contributes (lowest indices first)
+    long long n_elite_local;
+    long long iter;            // the reference's `iter`, starts at 1 (:253)
+    double sigma_inf;          // max |sigma| (:255)
+    int active;                // loop condition :255 for the NEXT pass
+    int nan_cost;              // a NaN cost was seen: the reference panics in the sort (:276)
+    int bad_sigma;             // a non-finite sigma was produced: the reference panics in Normal::new (:259)
+};
+
+struct CeDev {
+    double *mu, *sigma, *mu_new; // [n]
+    double *cost;                // [ld]
+    double *xs;                  // [n][ld] only for strided objectives
+    unsigned long long *hsend, *hrecv; // [BINS], [world][BINS]
+    double *msend, *mrecv;       // [n], [world][n]
+    int *blk_less, *blk_tie;     // [ntiles]
+    long long *blk_tie_off, *blk_el_off;
+    long long *elite_idx;        // [kcap] local sample indices, ascending
+    double *Ex;                  // [n][kld] regenerated elites
+    double *part;                // [n][nchunks]
+    CeCtrl *ctrl;
+    const double *replay;
+    long long replay_t0;
+    long long ld, nloc, first, ntotal, k, kcap, kld, ntiles;
+    long long iter_max;
+    int nchunks;
+    int n, world, rank, divisor_mode;
+    double tol;
+    PhiloxKey key;
+};
+
+__device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// order-preserving f64 -> u64: a < b  <=>  key(a) < key(b); NaN sorts last
+__device__ __forceinline__ unsigned long long cost_key(double c)
+{
+    const long long b = __double_as_longlong(c);
+    const unsigned long long u = (unsigned long long)b;
+    return b < 0 ? ~u : (u | 0x8000000000000000ULL);
 }
+
+// the coordinates of sample gi in dimension order: x_d = mu_d + sigma_d z_d  (Normal::sample, :265-271)
+template <bool REPLAY, class F>
+__device__ __forceinline__ void ce_sample_coords(const CeDev &P, uint32_t t, long long gi, const double *smu,
+                                                 const double *ssig, F &&f)
+{
+    const int n = P.n;
+    if constexpr (REPLAY) {
+        const double *z = P.replay + (((long long)t - P.replay_t0) * P.ntotal + gi) * n;
+        for (int d = 0; d < n; ++d) f(smu[d] + ssig[d] * z[d], d);
+    } else {
+        for (int p = 0; 2 * p < n; ++p) {
+            double z0, z1;
+            normal_pair(philox_draw(P.key, STREAM_CE, t, gi, (uint32_t)p), z0, z1);
+            f(smu[2 * p] + ssig[2 * p] * z0, 2 * p);
+            if (2 * p + 1 < n) f(smu[2 * p + 1] + ssig[2 * p + 1] * z1, 2 * p + 1);
+        }
+    }
+}
+
+__device__ __forceinline__ void load_mu_sigma(const CeDev &P, double *smu, double *ssig)
+{
+    for (int d = threadIdx.x; d < P.n; d += blockDim.x) {
+        smu[d] = P.mu[d];
+        ssig[d] = P.sigma[d];
+    }
+    __syncthreads();
+}
+
+// K4: one thread per sample; nothing but the 8-byte cost goes to HBM
+template <class Obj, bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK) ce_sample_kernel(const CeDev P)
+{
+    extern __shared__ double s_ms[];
+    CeCtrl *c = P.ctrl;
+    if (!c->active) return;
+    const uint32_t t = (uint32_t)(c->iter - 1);
+    double *smu = s_ms, *ssig = s_ms + P.n;
+    load_mu_sigma(P, smu, ssig);
+    bool nan = false;
+    for (long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x; li < P.nloc;
+         li += (long long)gridDim.x * blockDim.x) {
+        const long long gi = P.first + li;
+        double cost;
+        if constexpr (Obj::streaming) {
+            ObjAcc acc;
+            Obj::begin(acc, P.n);
+            ce_sample_coords<REPLAY>(P, t, gi, smu, ssig, [&](double x, int d) { Obj::feed(acc, x, d); });
+            cost = Obj::end(acc, P.n);
+        } else {
+            ce_sample_coords<REPLAY>(P, t, gi, smu, ssig, [&](double x, int d) { P.xs[(long long)d * P.ld + li] = x; });
+            cost = Obj::eval(P.xs + li, P.n, P.ld);
+        }
+        P.cost[li] = cost + 0.0; // -0 -> +0 so that key order and `<` agree
+        if (cost != cost) nan = true;
+    }
+    if (nan) c->nan_cost = 1;
+}
+
+// K5: one radix pass -- histogram of the current digit over the keys that match the decided prefix
+__global__ void __launch_bounds__(CE_BLOCK) ce_hist_kernel(const CeDev P, int pass)
+{
+    __shared__ unsigned int sh[CE_BINS];
+    if (!P.ctrl->active) return;
+    for (int b = threadIdx.x; b < CE_BINS; b += blockDim.x) sh[b] = 0u;
+    __syncthreads();
+    const int shift = pass_shift(pass), width = pass_width(pass);
+    const unsigned long long mask = (1ULL << width) - 1ULL;
+    const unsigned long long prefix = P.ctrl->prefix;
+    const int hi = shift + width;
+    for (long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x; li < P.nloc;
+         li += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = cost_key(P.cost[li]);
+        const bool match = pass == 0 || (key >> hi) == (prefix >> hi);
+        if (match) atomicAdd(&sh[(key >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < CE_BINS; b += blockDim.x)
+        if (sh[b]) atomicAdd(&P.hsend[b], (unsigned long long)sh[b]);
+}
+
+// pick the bucket that holds the k-th key from the (all ranks') histograms; after the last pass split the ties
+__global__ void __launch_bounds__(1024) ce_pick_kernel(const CeDev P, int pass)
+{
+    __shared__ long long s_scan[33];
+    __shared__ int s_bin;
+    __shared__ long long s_excl;
+    CeCtrl *c = P.ctrl;
+    if (!c->active) return;
+    const int tid = threadIdx.x;
+    long long h0 = 0, h1 = 0;
+    for (int r = 0; r < P.world; ++r) {
+        h0 += (long long)P.hrecv[(long long)r * CE_BINS + 2 * tid];
+        h1 += (long long)P.hrecv[(long long)r * CE_BINS + 2 * tid + 1];
+    }
+    const long long k_rem = pass == 0 ? P.k : c->k_rem;
+    const unsigned long long prefix = pass == 0 ? 0ULL : c->prefix;
+    if (tid == 0) {
+        s_bin = 0;
+        s_excl = 0;
+    }
+    long long total;
+    const long long excl = block_exclusive_scan(h0 + h1, 0LL, OpAddLL(), s_scan, total);
+    if (excl < k_rem && k_rem <= excl + h0) {
+        s_bin = 2 * tid;
+        s_excl = excl;
+    } else if (excl + h0 < k_rem && k_rem <= excl + h0 + h1) {
+        s_bin = 2 * tid + 1;
+        s_excl = excl + h0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        c->prefix = prefix | ((unsigned long long)s_bin << pass_shift(pass));
+        const long long rem = k_rem - s_excl;
+        c->k_rem = rem;
+        if (pass == CE_PASSES - 1) { // rem = how many of the samples with key == k-th key are elite, lowest index first
+            long long before = 0;
+            for (int r = 0; r < P.rank; ++r) before += (long long)P.hrecv[(long long)r * CE_BINS + s_bin];
+            const long long mine = (long long)P.hrecv[(long long)P.rank * CE_BINS + s_bin];
+            long long take = rem - before;
+            take = take < 0 ? 0 : (take > mine ? mine : take);
+            c->tie_take = take;
+        }
+    }
+    __syncthreads();
+    for (int b = tid; b < CE_BINS; b += blockDim.x) P.hsend[b] = 0ULL; // ready for the next pass
+}
+
+__global__ void __launch_bounds__(CE_BLOCK) ce_flag_kernel(const CeDev P)
+{
+    __shared__ int s_a[33], s_b[33];
+    if (!P.ctrl->active) return;
+    const unsigned long long T = P.ctrl->prefix;
+    const long long base = (long long)blockIdx.x * CE_TILE + threadIdx.x * 4;
+    int less = 0, ties = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const long long li = base + q;
+        if (li < P.nloc) {
+            const unsigned long long key = cost_key(P.cost[li]);
+            less += key < T;
+            ties += key == T;
+        }
+    }
+    int tl, tt;
+    block_exclusive_scan(less, 0, OpAddI(), s_a, tl);
+    block_exclusive_scan(ties, 0, OpAddI(), s_b, tt);
+    if (threadIdx.x == 0) {
+        P.blk_less[blockIdx.x] = tl;
+        P.blk_tie[blockIdx.x] = tt;
+    }
+}
+
+__global__ void __launch_bounds__(1024) ce_scan_kernel(const CeDev P)
+{
+    __shared__ long long s_scan[33];
+    CeCtrl *c = P.ctrl;
+    if (!c->active) return;
+    const long long tie_take = c->tie_take;
+    long long run_tie = 0, run_el = 0;
+    for (long long t0 = 0; t0 < P.ntiles; t0 += blockDim.x) {
+        const long long t = t0 + threadIdx.x;
+        const long long lt = t < P.ntiles ? P.blk_less[t] : 0, tt = t < P.ntiles ? P.blk_tie[t] : 0;
+        long long tot_tie, tot_el;
+        const long long ex_tie = run_tie + block_exclusive_scan(tt, 0LL, OpAddLL(), s_scan, tot_tie);
+        long long tie_el = tie_take - ex_tie;
+        tie_el = tie_el < 0 ? 0 : (tie_el > tt ? tt : tie_el);
+        const long long ex_el = run_el + block_exclusive_scan(lt + tie_el, 0LL, OpAddLL(), s_scan, tot_el);
+        if (t < P.ntiles) {
+            P.blk_tie_off[t] = ex_tie;
+            P.blk_el_off[t] = ex_el;
+        }
+        run_tie += tot_tie;
+        run_el += tot_el;
+    }
+    if (threadIdx.x == 0) c->n_elite_local = run_el;
+}
+
+// elite local indices in ascending sample order (deterministic summation order downstream)
+__global__ void __launch_bounds__(CE_BLOCK) ce_compact_kernel(const CeDev P)
+{
+    __shared__ int s_a[33];
+    if (!P.ctrl->active) return;
+    const unsigned long long T = P.ctrl->prefix;
+    const long long tie_take = P.ctrl->tie_take;
+    const long long base = (long long)blockIdx.x * CE_TILE + threadIdx.x * 4;
+    bool less[4], tie[4];
+    int tc = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const long long li = base + q;
+        less[q] = tie[q] = false;
+        if (li < P.nloc) {
+            const unsigned long long key = cost_key(P.cost[li]);
+            less[q] = key < T;
+            tie[q] = key == T;
+        }
+        tc += tie[q];
+    }
+    int dummy;
+    long long tie_rank = P.blk_tie_off[blockIdx.x] + block_exclusive_scan(tc, 0, OpAddI(), s_a, dummy);
+    bool el[4];
+    int ec = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        el[q] = less[q] || (tie[q] && tie_rank < tie_take);
+        tie_rank += tie[q];
+        ec += el[q];
+    }
+    long long pos = P.blk_el_off[blockIdx.x] + block_exclusive_scan(ec, 0, OpAddI(), s_a, dummy);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (el[q]) P.elite_idx[pos++] = base + q;
+}
+
+// regenerate the elites from their counters into Ex[d][j] (the N x n sample matrix never existed)
+template <bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK) ce_elite_gen_kernel(const CeDev P)
+{
+    extern __shared__ double s_ms[];
+    CeCtrl *c = P.ctrl;
+    if (!c->active) return;
+    const uint32_t t = (uint32_t)(c->iter - 1);
+    double *smu = s_ms, *ssig = s_ms + P.n;
+    load_mu_sigma(P, smu, ssig);
+    const long long ne = c->n_elite_local;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < ne; j += (long long)gridDim.x * blockDim.x) {
+        const long long li = P.elite_idx[j];
+        ce_sample_coords<REPLAY>(P, t, P.first + li, smu, ssig, [&](double x, int d) { P.Ex[(long long)d * P.kld + j] = x; });
+    }
+}
+
+// K6: per-dimension partial sums over a chunk of elites; mode 0: sum x, mode 1: sum (x - mu_new)^2 (:283-293)
+__global__ void __launch_bounds__(CE_BLOCK) ce_rowsum_kernel(const CeDev P, int mode)
+{
+    __shared__ double s_w[32];
+    if (!P.ctrl->active) return;
+    const long long ne = P.ctrl->n_elite_local;
+    const int d = blockIdx.y;
+    const long long j0 = (long long)blockIdx.x * CE_CHUNK, j1 = j0 + CE_CHUNK < ne ? j0 + CE_CHUNK : ne;
+    const double m = mode ? P.mu_new[d] : 0.0;
+    double acc = 0.0;
+    for (long long j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+        const double v = P.Ex[(long long)d * P.kld + j];
+        if (mode) {
+            const double e = v - m;
+            acc += e * e;
+        } else {
+            acc += v;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < CE_BLOCK / 32; ++w) s += s_w[w];
+        P.part[(long long)d * P.nchunks + blockIdx.x] = s;
+    }
+}
+
+// this rank's per-dimension sum, chunks added in chunk order
+__global__ void ce_moment_local_kernel(const CeDev P)
+{
+    if (!P.ctrl->active) return;
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= P.n) return;
+    double s = 0.0;
+    for (int ch = 0; ch < P.nchunks; ++ch) s += P.part[(long long)d * P.nchunks + ch];
+    P.msend[d] = s;
+}
+
+// mu_new = (sum over ranks, in rank order) / 10 or k  (:287)
+__global__ void ce_mean_apply_kernel(const CeDev P)
+{
+    if (!P.ctrl->active) return;
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= P.n) return;
+    double s = 0.0;
+    for (int r = 0; r < P.world; ++r) s += P.mrecv[(long long)r * P.n + d];
+    P.mu_new[d] = s / (P.divisor_mode == EQS_CE_DIV_REFERENCE_TEN ? 10.0 : (double)P.k);
+}
+
+// sigma_new = sqrt(sum / (k-1)) (:295-296); mus, sigmas <- new; iter += 1 (:299-302); loop condition (:255)
+__global__ void __launch_bounds__(1024) ce_sigma_apply_kernel(const CeDev P)
+{
+    __shared__ double s_max[32];
+    __shared__ int s_bad[32];
+    CeCtrl *c = P.ctrl;
+    if (!c->active) return;
+    double mx = 0.0;
+    int bad = 0;
+    for (int d = threadIdx.x; d < P.n; d += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < P.world; ++r) s += P.mrecv[(long long)r * P.n + d];
+        const double sg = sqrt(s / (double)(P.k - 1));
+        const double m = P.mu_new[d];
+        P.sigma[d] = sg;
+        P.mu[d] = m;
+        const double a = fabs(sg);
+        if (a > mx) mx = a;
+        if (!isfinite(sg) || !isfinite(m)) bad = 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_down_sync(0xffffffffu, mx, o);
+        mx = w > mx ? w : mx;
+        bad |= __shfl_down_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_max[threadIdx.x >> 5] = mx;
+        s_bad[threadIdx.x >> 5] = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            mx = s_max[w] > mx ? s_max[w] : mx;
+            bad |= s_bad[w];
+        }
+        c->sigma_inf = mx;
+        c->iter += 1;
+        if (bad) c->bad_sigma = 1;
+        c->active = (mx > P.tol) && (c->iter < P.iter_max) && !c->nan_cost && !c->bad_sigma;
+    }
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+} // namespace
+
+int validate_ce_params(const eqs_ce_params *p, std::string *why)
+{
+    auto bad = [&](int st, const char *m) {
+        if (why) *why = m;
+        return st;
+    };
+    if (!p) return bad(EQS_ERR_INCORRECT_INPUT, "null parameters");
+    if (p->n <= 0 || p->n >= (1 << 28)) return bad(EQS_ERR_INCORRECT_INPUT, "dimension n out of range");
+    if (p->sample_size <= 0) return bad(EQS_ERR_INCORRECT_INPUT, "sample size must be positive");
+    // the reference does not validate k: k < 2 divides by zero (:295) and k > N silently averages N samples (:284)
+    if (p->elite_count < 2 || p->elite_count > p->sample_size)
+        return bad(EQS_ERR_INCORRECT_INPUT, "importance selection size must satisfy 2 <= k <= sample size");
+    if (p->iter_max < 0) return bad(EQS_ERR_INCORRECT_INPUT, "negative iteration count");
+    if (p->objective_id < 0 || p->objective_id >= EQS_OBJ_COUNT) return bad(EQS_ERR_INCORRECT_INPUT, "unknown objective id");
+    if (p->objective_id == EQS_OBJ_THREE_CIRCLES && p->n != 2) return bad(EQS_ERR_INCORRECT_INPUT, "three-circles objective needs n = 2");
+    if (p->mean_divisor != EQS_CE_DIV_REFERENCE_TEN && p->mean_divisor != EQS_CE_DIV_ELITE_COUNT)
+        return bad(EQS_ERR_INCORRECT_INPUT, "unknown mean divisor mode");
+    return EQS_OK;
+}
+
+class CeSolver {
+public:
+    explicit CeSolver(Ctx *ctx) : ctx_(ctx) {}
+    ~CeSolver()
+    {
+        if (ctx_ && ctx_->device >= 0) cudaSetDevice(ctx_->device);
+        if (arena_) cudaFree(arena_);
+        if (replay_buf_) cudaFree(replay_buf_);
+        if (h_ctrl_) cudaFreeHost(h_ctrl_);
+        if (ev0_) cudaEventDestroy(ev0_);
+        if (ev1_) cudaEventDestroy(ev1_);
+    }
+
+    int create(const eqs_ce_params *p, const double *x0)
+    {
+        std::string why;
+        const int st = validate_ce_params(p, &why);
+        if (st != EQS_OK) return ctx_->fail(st, "%s", why.c_str());
+        if (!x0) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "null x0");
+        p_ = *p;
+        const int n = p->n;
+        int rank = ctx_->rank, world = ctx_->world;
+        if (p->exchange == EQS_EXCHANGE_MANUAL) {
+            rank = p->virtual_rank;
+            world = p->virtual_world;
+            if (world < 1 || rank < 0 || rank >= world) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "bad virtual rank/world");
+        }
+        manual_ = p->exchange == EQS_EXCHANGE_MANUAL && world > 1;
+        EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
+        int64_t first = 0, nloc = 0;
+        eqs_shard_range(p->sample_size, world, rank, &first, &nloc);
+        CeDev &D = d_;
+        D.n = n;
+        D.world = world;
+        D.rank = rank;
+        D.first = first;
+        D.nloc = nloc;
+        D.ntotal = p->sample_size;
+        D.k = p->elite_count;
+        D.ld = (long long)align_up((size_t)std::max<int64_t>(nloc, 1), 16);
+        D.kcap = std::max<long long>(1, std::min<long long>(D.k, nloc));
+        D.kld = (long long)align_up((size_t)D.kcap, 16);
+        D.ntiles = (nloc + CE_TILE - 1) / CE_TILE;
+        D.nchunks = (int)((D.kcap + CE_CHUNK - 1) / CE_CHUNK);
+        D.iter_max = p->iter_max;
+        D.divisor_mode = p->mean_divisor;
+        D.tol = p->tol;
+        D.key = philox_key(p->seed);
+        D.replay = nullptr;
+        D.replay_t0 = 0;
+        if ((size_t)2 * n * sizeof(double) > 200 * 1024) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "n too large for the shared-memory mu/sigma tile");
+        bool strided = false;
+        dispatch_objective(p->objective_id, [&]<class Obj>() { strided = !Obj::streaming; });
+
+        std::vector<double> sig(n, 1.0); // :247-251
+        if (p->std_dev) sig.assign(p->std_dev, p->std_dev + n);
+        double smax = 0.0;
+        bad_sigma0_ = false;
+        for (double s : sig) {
+            if (!std::isfinite(s)) bad_sigma0_ = true;
+            smax = std::max(smax, std::fabs(s));
+        }
+
+        size_t off = 0;
+        auto plan = [&](size_t bytes) {
+            const size_t o = off;
+            off += align_up(std::max<size_t>(bytes, 8), 256);
+            return o;
+        };
+        const size_t o_mu = plan(n * 8), o_sig = plan(n * 8), o_mun = plan(n * 8);
+        const size_t o_cost = plan(D.ld * 8);
+        const size_t o_xs = strided ? plan((size_t)n * D.ld * 8) : 0;
+        const bool own_recv = !(world == 1 && !manual_);
+        const size_t o_hs = plan(CE_BINS * 8), o_hr = own_recv ? plan((size_t)world * CE_BINS * 8) : o_hs;
+        const size_t o_ms = plan(n * 8), o_mr = own_recv ? plan((size_t)world * n * 8) : o_ms;
+        const size_t nt = (size_t)std::max<long long>(D.ntiles, 1);
+        const size_t o_bl = plan(nt * 4), o_bt = plan(nt * 4), o_bto = plan(nt * 8), o_beo = plan(nt * 8);
+        const size_t o_ei = plan(D.kcap * 8);
+        const size_t o_ex = plan((size_t)n * D.kld * 8);
+        const size_t o_part = plan((size_t)n * D.nchunks * 8);
+        const size_t o_ctrl = plan(sizeof(CeCtrl));
+        EQS_CUDA(ctx_, cudaMalloc(&arena_, off));
+        char *base = (char *)arena_;
+        D.mu = (double *)(base + o_mu);
+        D.sigma = (double *)(base + o_sig);
+        D.mu_new = (double *)(base + o_mun);
+        D.cost = (double *)(base + o_cost);
+        D.xs = strided ? (double *)(base + o_xs) : nullptr;
+        D.hsend = (unsigned long long *)(base + o_hs);
+        D.hrecv = (unsigned long long *)(base + o_hr);
+        D.msend = (double *)(base + o_ms);
+        D.mrecv = (double *)(base + o_mr);
+        D.blk_less = (int *)(base + o_bl);
+        D.blk_tie = (int *)(base + o_bt);
+        D.blk_tie_off = (long long *)(base + o_bto);
+        D.blk_el_off = (long long *)(base + o_beo);
+        D.elite_idx = (long long *)(base + o_ei);
+        D.Ex = (double *)(base + o_ex);
+        D.part = (double *)(base + o_part);
+        D.ctrl = (CeCtrl *)(base + o_ctrl);
+        EQS_CUDA(ctx_, cudaMallocHost(&h_ctrl_, sizeof(CeCtrl)));
+        memset(h_ctrl_, 0, sizeof(CeCtrl));
+        h_ctrl_->iter = 1; // :253
+        h_ctrl_->sigma_inf = smax;
+        h_ctrl_->active = (smax > p->tol) && (1 < p->iter_max) && !bad_sigma0_;
+        cudaStream_t s = ctx_->stream;
+        EQS_CUDA(ctx_, cudaMemcpyAsync(D.mu, x0, n * 8, cudaMemcpyHostToDevice, s)); // mus = x0, :246
+        EQS_CUDA(ctx_, cudaMemcpyAsync(D.sigma, sig.data(), n * 8, cudaMemcpyHostToDevice, s));
+        EQS_CUDA(ctx_, cudaMemcpyAsync(D.ctrl, h_ctrl_, sizeof(CeCtrl), cudaMemcpyHostToDevice, s));
+        EQS_CUDA(ctx_, cudaMemsetAsync(D.hsend, 0, CE_BINS * 8, s));
+        EQS_CUDA(ctx_, cudaStreamSynchronize(s));
+        EQS_CUDA(ctx_, cudaEventCreate(&ev0_));
+        EQS_CUDA(ctx_, cudaEventCreate(&ev1_));
+        sample_grid_ = 0;
+        return EQS_OK;
+    }
+
+    int upload_replay(const double *host, int64_t doubles)
+    {
+        const size_t bytes = (size_t)doubles * sizeof(double);
+        if (bytes > replay_cap_) {
+            if (replay_buf_) EQS_CUDA(ctx_, cudaFree(replay_buf_));
+            replay_buf_ = nullptr;
+            EQS_CUDA(ctx_, cudaMalloc(&replay_buf_, bytes));
+            replay_cap_ = bytes;
+        }
+        EQS_CUDA(ctx_, cudaMemcpyAsync(replay_buf_, host, bytes, cudaMemcpyHostToDevice, ctx_->stream));
+        return EQS_OK;
+    }
+
+    int fetch_ctrl()
+    {
+        EQS_CUDA(ctx_, cudaMemcpyAsync(h_ctrl_, d_.ctrl, sizeof(CeCtrl), cudaMemcpyDeviceToHost, ctx_->stream));
+        EQS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+        return EQS_OK;
+    }
+
+    int grid_for(long long units) const
+    {
+        const long long need = std::max<long long>(1, (units + CE_BLOCK - 1) / CE_BLOCK);
+        return (int)std::min<long long>(need, (long long)ctx_->sm_count * 8);
+    }
+
+    // phase kinds of exchange: 0 none, 1 histogram (u64[BINS]), 2 moments (f64[n])
+    static int phase_exchange(int phase) { return phase <= 5 ? 1 : (phase <= 7 ? 2 : 0); }
+
+    int launch_phase(int phase)
+    {
+        cudaStream_t s = ctx_->stream;
+        const CeDev &D = d_;
+        const bool replay = D.replay != nullptr;
+        const size_t smem = (size_t)2 * D.n * sizeof(double);
+        auto hist = [&](int pass) {
+            ce_hist_kernel<<<grid_for(D.nloc), CE_BLOCK, 0, s>>>(D, pass);
+            launches_++;
+        };
+        auto pick = [&](int pass) {
+            ce_pick_kernel<<<1, 1024, 0, s>>>(D, pass);
+            launches_++;
+        };
+        const int dim_grid = (D.n + 127) / 128;
+        int rc = EQS_OK;
+        if (phase == 0) {
+            dispatch_objective(p_.objective_id, [&]<class Obj>() {
+                auto run = [&](auto kernel) {
+                    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (sample_grid_ == 0) {
+                        int nb = 0;
+                        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, CE_BLOCK, smem);
+                        if (nb < 1) {
+                            rc = ctx_->fail(EQS_ERR_EXTERNAL, "sample kernel does not fit on an SM");
+                            return;
+                        }
+                        const long long need = std::max<long long>(1, (D.nloc + CE_BLOCK - 1) / CE_BLOCK);
+                        sample_grid_ = (int)std::min<long long>(need, (long long)nb * ctx_->sm_count);
+                    }
+                    kernel<<<sample_grid_, CE_BLOCK, smem, s>>>(D);
+                    launches_++;
+                };
+                if (replay) run(ce_sample_kernel<Obj, true>);
+                else run(ce_sample_kernel<Obj, false>);
+            });
+            EQS_TRY(rc);
+            hist(0);
+        } else if (phase <= 5) {
+            pick(phase - 1);
+            hist(phase);
+        } else if (phase == 6) {
+            pick(CE_PASSES - 1);
+            if (D.ntiles > 0) {
+                ce_flag_kernel<<<(unsigned)D.ntiles, CE_BLOCK, 0, s>>>(D);
+                launches_++;
+            }
+            ce_scan_kernel<<<1, 1024, 0, s>>>(D);
+            launches_++;
+            if (D.ntiles > 0) {
+                ce_compact_kernel<<<(unsigned)D.ntiles, CE_BLOCK, 0, s>>>(D);
+                launches_++;
+            }
+            auto gen = [&](auto kernel) {
+                if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                kernel<<<grid_for(D.kcap), CE_BLOCK, smem, s>>>(D);
+                launches_++;
+            };
+            if (replay) gen(ce_elite_gen_kernel<true>);
+            else gen(ce_elite_gen_kernel<false>);
+            ce_rowsum_kernel<<<dim3(D.nchunks, D.n), CE_BLOCK, 0, s>>>(D, 0);
+            ce_moment_local_kernel<<<dim_grid, 128, 0, s>>>(D);
+            launches_ += 2;
+        } else if (phase == 7) {
+            ce_mean_apply_kernel<<<dim_grid, 128, 0, s>>>(D);
+            ce_rowsum_kernel<<<dim3(D.nchunks, D.n), CE_BLOCK, 0, s>>>(D, 1);
+            ce_moment_local_kernel<<<dim_grid, 128, 0, s>>>(D);
+            launches_ += 3;
+        } else if (phase == 8) {
+            ce_sigma_apply_kernel<<<1, 1024, 0, s>>>(D);
+            launches_++;
+        } else {
+            return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "phase must be 0..8");
+        }
+        EQS_CUDA(ctx_, cudaGetLastError());
+        return EQS_OK;
+    }
+
+    int exchange(int kind)
+    {
+        if (manual_ || d_.world == 1 || kind == 0) return EQS_OK;
+        if (kind == 1)
+            return comm_allgather_f64(ctx_, (const double *)d_.hsend, (double *)d_.hrecv, CE_BINS, ctx_->stream);
+        return comm_allgather_f64(ctx_, d_.msend, d_.mrecv, d_.n, ctx_->stream);
+    }
+
+    int prepare_replay(const double *replay, int64_t iters)
+    {
+        if (replay) {
+            EQS_TRY(fetch_ctrl());
+            EQS_TRY(upload_replay(replay, iters * p_.sample_size * (int64_t)p_.n));
+            d_.replay = replay_buf_;
+            d_.replay_t0 = h_ctrl_->iter - 1;
+        } else {
+            d_.replay = nullptr;
+        }
+        sample_grid_ = 0;
+        return EQS_OK;
+    }
+
+    int step(int64_t iters, const double *replay)
+    {
+        EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
+        if (manual_) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "exchange = MANUAL: drive the phases with eqs_ce_phase");
+        if (bad_sigma0_ && p_.iter_max > 1) return ctx_->fail(EQS_ERR_NAN, "non-finite standard deviation (the reference panics in Normal::new, cross_entropy.rs:259)");
+        EQS_TRY(prepare_replay(replay, iters));
+        const int64_t l0 = launches_;
+        EQS_CUDA(ctx_, cudaEventRecord(ev0_, ctx_->stream));
+        for (int64_t it = 0; it < iters; ++it)
+            for (int ph = 0; ph < CE_PHASES; ++ph) {
+                EQS_TRY(launch_phase(ph));
+                EQS_TRY(exchange(phase_exchange(ph)));
+            }
+        EQS_CUDA(ctx_, cudaEventRecord(ev1_, ctx_->stream));
+        last_launches_ = launches_ - l0;
+        return EQS_OK;
+    }
+
+    int check_flags()
+    {
+        if (h_ctrl_->nan_cost) return ctx_->fail(EQS_ERR_NAN, "a sample cost is NaN (the reference panics in sort_unstable_by, cross_entropy.rs:276)");
+        if (h_ctrl_->bad_sigma) return ctx_->fail(EQS_ERR_NAN, "a non-finite mean or standard deviation was produced (the reference panics in Normal::new, cross_entropy.rs:259)");
+        return EQS_OK;
+    }
+
+    int read_state(double *mu, double *sigma, int64_t *iters, int32_t *active)
+    {
+        EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
+        cudaStream_t s = ctx_->stream;
+        if (mu) EQS_CUDA(ctx_, cudaMemcpyAsync(mu, d_.mu, d_.n * 8, cudaMemcpyDeviceToHost, s));
+        if (sigma) EQS_CUDA(ctx_, cudaMemcpyAsync(sigma, d_.sigma, d_.n * 8, cudaMemcpyDeviceToHost, s));
+        EQS_TRY(fetch_ctrl());
+        if (iters) *iters = h_ctrl_->iter - 1;
+        if (active) *active = h_ctrl_->active;
+        return check_flags();
+    }
+
+    // CrossEntropy::solve, cross_entropy.rs:245-306
+    int solve(double *out_mu, eqs_report *rep)
+    {
+        cudaEvent_t e0, e1;
+        EQS_CUDA(ctx_, cudaEventCreate(&e0));
+        EQS_CUDA(ctx_, cudaEventCreate(&e1));
+        const int64_t l0 = launches_;
+        cudaEventRecord(e0, ctx_->stream);
+        int st = EQS_OK;
+        const int64_t kBatch = 16;
+        int64_t left = std::max<int64_t>(p_.iter_max - 1, 0); // iter starts at 1 (:253,:255)
+        while (st == EQS_OK && left > 0) {
+            const int64_t b = std::min(kBatch, left);
+            st = step(b, nullptr);
+            left -= b;
+            if (st == EQS_OK) st = fetch_ctrl();
+            if (st == EQS_OK) st = check_flags();
+            if (st == EQS_OK && !h_ctrl_->active) break;
+        }
+        if (st == EQS_OK) {
+            cudaEventRecord(e1, ctx_->stream);
+            st = read_state(out_mu, nullptr, nullptr, nullptr); // Ok(mus), :305
+        }
+        if (st == EQS_OK && rep) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            rep->iters_run = h_ctrl_->iter - 1;
+            rep->evals = p_.sample_size * (h_ctrl_->iter - 1);
+            rep->best_cost = h_ctrl_->sigma_inf;
+            rep->stalled = !(h_ctrl_->sigma_inf > p_.tol);
+            rep->world = d_.world;
+            rep->kernel_launches = launches_ - l0;
+            rep->init_ms = 0.0;
+            rep->loop_ms = ms;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return st;
+    }
+
+    Ctx *ctx_;
+    eqs_ce_params p_{};
+    CeDev d_{};
+    void *arena_ = nullptr;
+    double *replay_buf_ = nullptr;
+    size_t replay_cap_ = 0;
+    CeCtrl *h_ctrl_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    int sample_grid_ = 0;
+    int64_t launches_ = 0, last_launches_ = 0;
+    bool manual_ = false, bad_sigma0_ = false;
+};
+
+} // namespace eqs
+
+using namespace eqs;
+
+struct eqs_ce {
+    CeSolver s;
+    explicit eqs_ce(Ctx *c) : s(c) {}
+};
+
+#define H_OR_FAIL(h)                                                                                             \
+    if (!(h)) return EQS_ERR_INCORRECT_INPUT
+
+extern "C" {
+
+int eqs_ce_validate(const eqs_ce_params *p) { return validate_ce_params(p, nullptr); }
+
+int eqs_ce_create(eqs_ctx *ctx, const eqs_ce_params *p, const double *x0, eqs_ce **out)
+{
+    if (!ctx || !out) return EQS_ERR_INCORRECT_INPUT;
+    *out = nullptr;
+    eqs_ce *h = new (std::nothrow) eqs_ce(&ctx->c);
+    if (!h) return ctx->c.fail(EQS_ERR_EXTERNAL, "out of host memory");
+    const int st = h->s.create(p, x0);
+    if (st != EQS_OK) {
+        delete h;
+        return st;
+    }
+    *out = h;
+    return EQS_OK;
+}
+
+int eqs_ce_destroy(eqs_ce *h)
+{
+    delete h;
+    return EQS_OK;
+}
+
+int eqs_ce_step(eqs_ce *h, int64_t iters, const double *replay_normals)
+{
+    H_OR_FAIL(h);
+    if (iters < 0) return h->s.ctx_->fail(EQS_ERR_INCORRECT_INPUT, "negative iteration count");
+    return h->s.step(iters, replay_normals);
+}
+
+int eqs_ce_sync(eqs_ce *h)
+{
+    H_OR_FAIL(h);
+    Ctx *c = h->s.ctx_;
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    EQS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EQS_OK;
+}
+
+int eqs_ce_last_step_ms(eqs_ce *h, double *ms, int64_t *kernel_launches)
+{
+    H_OR_FAIL(h);
+    Ctx *c = h->s.ctx_;
+    EQS_CUDA(c, cudaEventSynchronize(h->s.ev1_));
+    float f = 0.f;
+    EQS_CUDA(c, cudaEventElapsedTime(&f, h->s.ev0_, h->s.ev1_));
+    if (ms) *ms = f;
+    if (kernel_launches) *kernel_launches = h->s.last_launches_;
+    return EQS_OK;
+}
+
+int eqs_ce_read_state(eqs_ce *h, double *mu, double *sigma, int64_t *iters_run, int32_t *active)
+{
+    H_OR_FAIL(h);
+    return h->s.read_state(mu, sigma, iters_run, active);
+}
+
+int eqs_ce_read_elites(eqs_ce *h, int64_t *idx, int64_t *count)
+{
+    H_OR_FAIL(h);
+    CeSolver &s = h->s;
+    Ctx *c = s.ctx_;
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    EQS_TRY(s.fetch_ctrl());
+    const long long ne = s.h_ctrl_->n_elite_local;
+    if (count) *count = ne;
+    if (idx && ne > 0) {
+        EQS_CUDA(c, cudaMemcpyAsync(idx, s.d_.elite_idx, ne * 8, cudaMemcpyDeviceToHost, c->stream));
+        EQS_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (long long j = 0; j < ne; ++j) idx[j] += s.d_.first; // local -> global
+    }
+    return EQS_OK;
+}
+
+int eqs_ce_read_costs(eqs_ce *h, double *costs)
+{
+    H_OR_FAIL(h);
+    CeSolver &s = h->s;
+    Ctx *c = s.ctx_;
+    if (!costs) return EQS_ERR_INCORRECT_INPUT;
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    if (s.d_.nloc > 0) EQS_CUDA(c, cudaMemcpyAsync(costs, s.d_.cost, s.d_.nloc * 8, cudaMemcpyDeviceToHost, c->stream));
+    EQS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EQS_OK;
+}
+
+int eqs_ce_local_range(eqs_ce *h, int64_t *first, int64_t *local)
+{
+    H_OR_FAIL(h);
+    if (first) *first = h->s.d_.first;
+    if (local) *local = h->s.d_.nloc;
+    return EQS_OK;
+}
+
+int eqs_ce_phase(eqs_ce *h, int32_t phase, const double *replay_normals)
+{
+    H_OR_FAIL(h);
+    CeSolver &s = h->s;
+    Ctx *c = s.ctx_;
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    if (phase == 0) EQS_TRY(s.prepare_replay(replay_normals, 1));
+    return s.launch_phase(phase);
+}
+
+int64_t eqs_ce_exchange_words(eqs_ce *h, int32_t phase)
+{
+    if (!h) return 0;
+    const int kind = CeSolver::phase_exchange(phase);
+    return kind == 1 ? CE_BINS : (kind == 2 ? h->s.d_.n : 0);
+}
+
+int eqs_ce_get_exchange(eqs_ce *h, int32_t phase, void *words)
+{
+    H_OR_FAIL(h);
+    CeSolver &s = h->s;
+    Ctx *c = s.ctx_;
+    const int kind = CeSolver::phase_exchange(phase);
+    if (kind == 0 || !words) return c->fail(EQS_ERR_INCORRECT_INPUT, "phase has no exchange");
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    const void *src = kind == 1 ? (const void *)s.d_.hsend : (const void *)s.d_.msend;
+    const size_t bytes = (kind == 1 ? (size_t)CE_BINS : (size_t)s.d_.n) * 8;
+    EQS_CUDA(c, cudaMemcpyAsync(words, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    EQS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EQS_OK;
+}
+
+int eqs_ce_set_exchange(eqs_ce *h, int32_t phase, const void *words)
+{
+    H_OR_FAIL(h);
+    CeSolver &s = h->s;
+    Ctx *c = s.ctx_;
+    const int kind = CeSolver::phase_exchange(phase);
+    if (kind == 0 || !words) return c->fail(EQS_ERR_INCORRECT_INPUT, "phase has no exchange");
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    void *dst = kind == 1 ? (void *)s.d_.hrecv : (void *)s.d_.mrecv;
+    const size_t bytes = (kind == 1 ? (size_t)CE_BINS : (size_t)s.d_.n) * 8 * s.d_.world;
+    EQS_CUDA(c, cudaMemcpyAsync(dst, words, bytes, cudaMemcpyHostToDevice, c->stream));
+    EQS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EQS_OK;
+}
+
+int eqs_ce_solve(eqs_ctx *ctx, const eqs_ce_params *p, const double *x0, double *out_mu, eqs_report *report)
+{
+    if (!ctx) return EQS_ERR_INCORRECT_INPUT;
+    if (!x0 || !out_mu) return ctx->c.fail(EQS_ERR_INCORRECT_INPUT, "null x0 / out_mu");
+    CeSolver s(&ctx->c);
+    EQS_TRY(s.create(p, x0));
+    return s.solve(out_mu, report);
+}
+
+} // extern "C"

@@ -41,6 +41,15 @@ struct Ctx {
     }
 };
 
+} // namespace eqs
+
+// the opaque context of the C ABI
+struct eqs_ctx {
+    eqs::Ctx c;
+};
+
+namespace eqs {
+
 #define EQS_CUDA(ctx, expr)                                                                                      \
     do {                                                                                                         \
         cudaError_t _e = (expr);                                                                                 \

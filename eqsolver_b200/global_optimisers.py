@@ -487,3 +487,22 @@ class CeRun:
         c = np.empty(self.local)
         self.ctx.check(_ffi.lib().eqs_ce_read_costs(self._h, _p(c)))
         return c
+
+    # split-phase protocol (virtual ranks): phases 0..8 of one pass
+    N_PHASES = 9
+
+    def phase(self, phase: int, replay_normals=None):
+        r = None if replay_normals is None else _arr(replay_normals, self.cfg.sample_size * self.n)
+        self.ctx.check(_ffi.lib().eqs_ce_phase(self._h, phase, _p(r)))
+
+    def exchange_words(self, phase: int) -> int:
+        return int(_ffi.lib().eqs_ce_exchange_words(self._h, phase))
+
+    def get_exchange(self, phase: int) -> np.ndarray:
+        w = np.empty(self.exchange_words(phase), dtype=np.uint64)
+        self.ctx.check(_ffi.lib().eqs_ce_get_exchange(self._h, phase, w.ctypes.data_as(C.c_void_p)))
+        return w
+
+    def set_exchange(self, phase: int, words):
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        self.ctx.check(_ffi.lib().eqs_ce_set_exchange(self._h, phase, w.ctypes.data_as(C.c_void_p)))

@@ -202,6 +202,15 @@ int eqs_ce_read_state(eqs_ce *h, double *mu, double *sigma, int64_t *iters_run, 
 int eqs_ce_read_elites(eqs_ce *h, int64_t *idx, int64_t *count);
 int eqs_ce_read_costs(eqs_ce *h, double *costs);
 int eqs_ce_local_range(eqs_ce *h, int64_t *first, int64_t *local);
+/* split-phase protocol (EQS_EXCHANGE_MANUAL; also how the NCCL path is sequenced).  One pass of the while
+ * body is phases 0..8; after phase p the caller gathers eqs_ce_exchange_words(h, p) 8-byte words from every
+ * rank (get) and hands all ranks' words back in rank order (set): phases 0-5 a radix-select histogram
+ * (u64[2048]), phases 6-7 the elite moment sums (f64[n]), phase 8 nothing.  replay_normals (phase 0 only):
+ * NULL or z [N][n] for this pass. */
+int eqs_ce_phase(eqs_ce *h, int32_t phase, const double *replay_normals);
+int64_t eqs_ce_exchange_words(eqs_ce *h, int32_t phase);
+int eqs_ce_get_exchange(eqs_ce *h, int32_t phase, void *words);
+int eqs_ce_set_exchange(eqs_ce *h, int32_t phase, const void *words /*[world][words]*/);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -258,7 +258,7 @@ def test_full_size_c2_properties(ctx):
     n, N = 32, 1 << 20
     ps = (E.ParticleSwarm.new(E.Objective.ROSENBROCK, [-5.0] * n, [10.0] * n).with_particle_count(N).with_tol(0.0)
           .with_seed(1729).with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx))
-    run = ps.start(np.zeros(n))
+    run = ps.start(np.full(n, 8.0))  # f(x0) ~ 9.7e6: the swarm beats it at once
     _, c_prev, _, _, _ = run.gbest()
     pbc_prev = run.state()[3]
     for _ in range(3):
@@ -266,7 +266,7 @@ def test_full_size_c2_properties(ctx):
         x, v, pb, pbc = run.state()
         g, c, it, _, _ = run.gbest()
         assert c <= c_prev and np.all(pbc <= pbc_prev)            # gbest / pbest costs never increase
-        assert c == pbc.min()                                      # gbest cost = min pbest cost (f(x0)=31 is beaten)
+        assert c == pbc.min()                                      # gbest cost = min pbest cost
         i = int(np.argmin(pbc))
         assert_bit_equal(pb[i], g)                                 # gbest position = that particle's pbest
         idx = np.random.default_rng(it).integers(0, N, 64)
