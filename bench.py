@@ -291,6 +291,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "particle-evals/s", "h2d_bytes_per_step": h2d / e2e_iters,
                 "d2h_bytes_per_step": d2h / e2e_iters, "h2d_bytes_per_solve": h2d, "d2h_bytes_per_solve": d2h,
                 "passes_per_solve": e2e_iters, "seconds_per_solve": e2e_s,
+                "device_init_ms": rep.init_ms, "device_loop_ms": rep.loop_ms,
+                "host_overhead_ms": 1e3 * e2e_s - rep.init_ms - rep.loop_ms,
                 "call": "ParticleSwarm.new(obj, lower, upper).with_particle_count(N).with_iter_max(K).solve(x0)"},
         "gpu_launches": launches_total,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -24,7 +24,7 @@ template <class Obj> __global__ void objective_eval_kernel(const double *x, int 
 {
     // x is particle-major [count][n] as the caller (and the reference's closure) sees it
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) out[i] = objective_strided<Obj>(x + i * n, n, 1);
+    if (i < count) out[i] = objective_on<Obj>(StridedView{x + i * n, 1}, n);
 }
 
 __global__ void philox_blocks_kernel(const uint32_t *ctr, PhiloxKey key, long long count, uint32_t *out)
@@ -203,7 +203,7 @@ int eqs_philox_blocks(eqs_ctx *ctx, const uint32_t *ctr, const uint32_t key[2], 
     EQS_CUDA(c, cudaMalloc(&dc, 16 * count));
     EQS_CUDA(c, cudaMalloc(&dout, 16 * count));
     EQS_CUDA(c, cudaMemcpyAsync(dc, ctr, 16 * count, cudaMemcpyHostToDevice, c->stream));
-    philox_blocks_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(dc, PhiloxKey{key[0], key[1]}, count, dout);
+    philox_blocks_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(dc, philox_key(key[0], key[1]), count, dout);
     cudaError_t e = cudaMemcpyAsync(out, dout, 16 * count, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(dc);

@@ -124,7 +124,7 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK) ce
             cost = Obj::end(acc, P.n);
         } else {
             ce_sample_coords<REPLAY>(P, t, gi, smu, ssig, [&](double x, int d) { P.xs[(long long)d * P.ld + li] = x; });
-            cost = Obj::eval(P.xs + li, P.n, P.ld);
+            cost = Obj::eval(StridedView{P.xs + li, P.ld}, P.n);
         }
         P.cost[li] = cost + 0.0; // -0 -> +0 so that key order and `<` agree
         if (cost != cost) nan = true;

@@ -4,8 +4,8 @@
 // (particle_swarm.rs:92,415; cross_entropy.rs:55,273), which cannot run on the device.
 //
 // A functor is either STREAMING -- begin / feed(x_d, d) for d = 0..n-1 in order / end -- so that the fused
-// step kernel evaluates it while the coordinates are still in registers, or STRIDED -- eval(x, n, stride)
-// reading the coordinates back from the structure-of-arrays column (stride = row pitch).  The operation
+// step kernel evaluates it while the coordinates are still in registers, or RANDOM-ACCESS -- eval(x, n) with
+// x[d] reading coordinate d of this particle back from memory through a view of the device layout.  The operation
 // order of every functor equals the oracle's (oracle/eqs_oracle.c: orc_objective); the library is compiled
 // with -fmad=false because rustc never contracts a*b+c.
 #pragma once
@@ -17,6 +17,18 @@ namespace eqs {
 
 struct ObjAcc {
     double a, b, p;
+};
+
+// views of one particle's coordinates in the device layouts
+struct StridedView { // coordinate d at base[d * stride]: contiguous vectors (stride 1), dimension-major columns
+    const double *base;
+    long long stride;
+    __device__ __forceinline__ double operator[](int d) const { return base[(long long)d * stride]; }
+};
+struct GroupedView { // ParticleSwarm population: [n/4][ld][4], base = buffer + 4 * particle, pitch = 4 * ld
+    const double *base;
+    long long pitch;
+    __device__ __forceinline__ double operator[](int d) const { return base[(long long)(d >> 2) * pitch + (d & 3)]; }
 };
 
 constexpr double kTwoPi = 2.0 * 3.14159265358979323846; // (2.0 * PI), exact doubling
@@ -92,13 +104,13 @@ template <> struct Objective<EQS_OBJ_THREE_CIRCLES> {
 // O(n^2) by construction in the reference; kept so, for bit parity of each partial sum.
 template <> struct Objective<EQS_OBJ_HEAVY> {
     static constexpr bool streaming = false;
-    __device__ __forceinline__ static double eval(const double *x, int n, int64_t stride)
+    template <class X> __device__ __forceinline__ static double eval(const X &x, int n)
     {
         double acc = 0.0;
         for (int i = 0; i < n; ++i) {
             double o = 0.0;
             for (int j = i; j < n; ++j) {
-                const double xj = x[(int64_t)j * stride];
+                const double xj = x[j];
                 o += xj * xj;
             }
             acc += o * o;
@@ -114,16 +126,16 @@ template <> struct Objective<EQS_OBJ_HEAVY> {
 namespace eqs {
 template <> struct Objective<EQS_OBJ_USER> : public UserObjective {};
 
-// evaluate any functor on a strided column (used by eqs_objective_eval, f(x0), and strided functors)
-template <class Obj> __device__ __forceinline__ double objective_strided(const double *x, int n, int64_t stride)
+// evaluate any functor through a view (eqs_objective_eval, f(x0), random-access functors)
+template <class Obj, class X> __device__ __forceinline__ double objective_on(const X &x, int n)
 {
     if constexpr (Obj::streaming) {
         ObjAcc s;
         Obj::begin(s, n);
-        for (int d = 0; d < n; ++d) Obj::feed(s, x[(int64_t)d * stride], d);
+        for (int d = 0; d < n; ++d) Obj::feed(s, x[d], d);
         return Obj::end(s, n);
     } else {
-        return Obj::eval(x, n, stride);
+        return Obj::eval(x, n);
     }
 }
 

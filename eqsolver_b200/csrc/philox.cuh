@@ -6,7 +6,7 @@
 //
 //   key = (seed lo32, seed hi32)
 //   ctr = (gidx lo32, gidx hi32, stream << 28 | j, iteration)       j = dimension (PSO) or dim pair (CE)
-//   u   = ((w_hi mod 2^21) * 2^32 + w_lo) * 2^-53   in [0,1)        (w_lo, w_hi) = words (0,1) or (2,3)
+//   u   = ((w_hi mod 2^20) * 2^32 + w_lo) * 2^-52   in [0,1)        (w_lo, w_hi) = words (0,1) or (2,3)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -18,22 +18,29 @@ enum : uint32_t { STREAM_PSO_INIT = 0u, STREAM_PSO_STEP = 1u, STREAM_CE = 2u };
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 
+// the ten round keys, expanded once on the host: as kernel parameters they are constant-bank operands of the
+// LOP3s, so a round is exactly 2 IMAD.WIDE.U32 + 2 LOP3 with no key arithmetic on the device
 struct PhiloxKey {
-    uint32_t k0, k1;
+    uint32_t k0[10], k1[10];
 };
 
-__host__ __device__ inline PhiloxKey philox_key(uint64_t seed)
+__host__ __device__ inline PhiloxKey philox_key(uint32_t lo, uint32_t hi)
 {
-    return PhiloxKey{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    PhiloxKey k;
+    for (int r = 0; r < 10; ++r) {
+        k.k0[r] = lo + (uint32_t)r * PHILOX_W0;
+        k.k1[r] = hi + (uint32_t)r * PHILOX_W1;
+    }
+    return k;
 }
 
-// 10 rounds; the per-round keys depend only on the (uniform) key, so ptxas folds the bumps into immediates
-// of a uniform register: 2 IMAD.WIDE.U32 + 2 LOP3 per round.
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, PhiloxKey key)
+__host__ __device__ inline PhiloxKey philox_key(uint64_t seed) { return philox_key((uint32_t)seed, (uint32_t)(seed >> 32)); }
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKey &key)
 {
-    uint32_t k0 = key.k0, k1 = key.k1;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
+        const uint32_t k0 = key.k0[r], k1 = key.k1[r];
         const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
         const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -42,24 +49,21 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
         c3 = (uint32_t)p0;
         c0 = n0;
         c2 = n2;
-        k0 += PHILOX_W0;
-        k1 += PHILOX_W1;
     }
     return make_uint4(c0, c1, c2, c3);
 }
 
-__device__ __forceinline__ uint4 philox_draw(PhiloxKey key, uint32_t stream, uint32_t t, int64_t gidx, uint32_t j)
+__device__ __forceinline__ uint4 philox_draw(const PhiloxKey &key, uint32_t stream, uint32_t t, int64_t gidx, uint32_t j)
 {
     return philox4x32_10((uint32_t)(uint64_t)gidx, (uint32_t)((uint64_t)gidx >> 32), (stream << 28) | j, t, key);
 }
 
-// exact u53 -> f64 without I2F: 2^84 + h*2^32 and 2^52 + lo are built by bit pasting, the two
-// subtractions/additions below are exact, so this equals (double)k * 2^-53 bit for bit.
+// 52 random mantissa bits pasted under exponent 0 give a double in [1,2); minus one is exact, so this equals
+// (double)k * 2^-52 bit for bit (k = (w_hi mod 2^20) * 2^32 + w_lo).  One LOP3 + one DADD; it is also how
+// rand's Uniform<f64> turns bits into a float (into_float_with_exponent(0) - 1.0).
 __device__ __forceinline__ double u01(uint32_t w_lo, uint32_t w_hi)
 {
-    const double dh = __hiloint2double(0x45300000, (int)(w_hi & 0x1FFFFFu));
-    const double dl = __hiloint2double(0x43300000, (int)w_lo);
-    return __dmul_rn(__dadd_rn(__dadd_rn(dh, -(0x1.0p84 + 0x1.0p52)), dl), 0x1.0p-53);
+    return __dadd_rn(__hiloint2double((int)((w_hi & 0xFFFFFu) | 0x3FF00000u), (int)w_lo), -1.0);
 }
 
 // Box-Muller on one block per dimension PAIR: z0 = r cos(2 pi u2), z1 = r sin(2 pi u2), r = sqrt(-2 ln(1-u1)).

@@ -8,12 +8,26 @@
 //                        + block/grid min-loc reduction (K3) + (single rank) the gbest update :420-425
 //   pso_spec/commit      :399-427   sequential-exact mode: speculate-and-repair
 //   pso_apply_*          :420-425, :395-397, :433-441  gbest update, ring push, stall test
-// The kernels are HBM-bound: 40n+16 algorithmic bytes per particle-evaluation.
+//
+// DATA LAYOUT.  The reference keeps an array of structs `Vec<Particle>` (:14-22).  Here every
+// per-particle vector field is one buffer [ceil(n/4)][ld][4] f64: four consecutive dimensions of ONE particle
+// form a 32-byte DRAM sector, particles are contiguous within a 4-dimension group.  A warp reads 1 KB of
+// consecutive bytes with one 256-bit access per lane (LDG.E.ENL2.256), and every per-particle decision (which
+// buffer to write, whether to read pbest at all) is sector-granular, so it never causes partial-sector traffic.
+//
+// ROLE-SWAPPING POSITION BUFFERS (synchronous mode).  Position and pbest position live in two buffers A (= P.x) and
+// B (= P.pb) with one flag byte per particle: bit 1 = "x lives in B", bit 0 = "stale": the last pass improved
+// pbest, so pbest position == position and only one buffer holds live data.  A stale particle writes its new
+// position into the OTHER buffer and flips the role bit: the old buffer now IS the pbest position.  `best_position
+// = position.clone()` (:417-419) therefore costs no memory traffic, and the pbest sector of a stale particle is not
+// even read: <= 40n bytes per particle-evaluation whatever the improvement rate (ncu showed 70 % of the particles of
+// config 2 improving per pass, +14 % DRAM bytes in a copy-on-improve scheme; profiles/).
 #include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "objectives.cuh"
 #include "pso.cuh"
@@ -25,26 +39,26 @@ namespace {
 constexpr long long kNoIndex = 0x7fffffffffffffffLL;
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
-// ---- vector I/O over the particle axis -----------------------------------------------------------------
-template <int VEC> struct VecIO;
-template <> struct VecIO<1> {
-    __device__ __forceinline__ static void load(const double *p, double (&o)[1]) { o[0] = *p; }
-    __device__ __forceinline__ static void store(double *p, const double (&o)[1]) { *p = o[0]; }
-};
-template <> struct VecIO<2> {
-    __device__ __forceinline__ static void load(const double *p, double (&o)[2])
-    {
-        const double2 t = *reinterpret_cast<const double2 *>(p);
-        o[0] = t.x;
-        o[1] = t.y;
-    }
-    __device__ __forceinline__ static void store(double *p, const double (&o)[2])
-    {
-        *reinterpret_cast<double2 *>(p) = make_double2(o[0], o[1]);
-    }
+// ---- 256-bit global accesses: one 32-byte sector = 4 dimensions of one particle ------------------------------
+struct D4 {
+    double e[4];
 };
 
-// ---- draws: (rp, rg) of particle_swarm.rs:407-408 ------------------------------------------------------
+__device__ __forceinline__ D4 ld256(const double *p)
+{
+    D4 r;
+    asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.e[0]), "=d"(r.e[1]), "=d"(r.e[2]), "=d"(r.e[3]) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void st256(double *p, const D4 &v)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.e[0]), "d"(v.e[1]), "d"(v.e[2]), "d"(v.e[3]));
+}
+
+__device__ __forceinline__ long long goff(const PsoDev &P, int q, long long li) { return ((long long)q * P.ld + li) * 4; }
+
+// ---- draws: (rp, rg) of particle_swarm.rs:407-408 ------------------------------------------------------------
 template <bool REPLAY>
 __device__ __forceinline__ void step_draw(const PsoDev &P, uint32_t t, long long gi, int d, double &rp, double &rg)
 {
@@ -81,56 +95,87 @@ __device__ __forceinline__ void ring_push(PsoCtrl *c, double v)
     c->ring_i = (c->ring_i + 1) % EQS_STALL_WINDOW;
 }
 
-// K rows (dimensions d..d+K-1) of VEC particles: loads first, then update + objective, then stores
-template <class Obj, bool REPLAY, int VEC, int K>
-__device__ __forceinline__ void pso_rows(const PsoDev &P, uint32_t t, long long i0, int d, const double *sG,
-                                         ObjAcc (&acc)[VEC], const double *xin, const double *vin, double *xout,
-                                         double *vout)
+// one 4-dimension group already in registers: draws, update, objective; `dims` = live dimensions in the group
+template <class Obj, bool REPLAY, bool FULL>
+__device__ __forceinline__ void pso_group_math(const PsoDev &P, uint32_t t, long long gi, int q, const double *sG, ObjAcc &acc,
+                                               D4 &x, D4 &v, const D4 &pb, int dims)
 {
-    double xs[K][VEC], vs[K][VEC], ps[K][VEC];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const long long row = (long long)(d + k) * P.ld + i0;
-        VecIO<VEC>::load(xin + row, xs[k]);
-        VecIO<VEC>::load(vin + row, vs[k]);
-        VecIO<VEC>::load(P.pb + row, ps[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const double g = sG[d + k];
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
+    for (int j = 0; j < 4; ++j) {
+        if (FULL || j < dims) {
+            const int d = 4 * q + j;
             double rp, rg;
-            step_draw<REPLAY>(P, t, P.first + i0 + e, d + k, rp, rg);
-            pso_update(P, xs[k][e], vs[k][e], ps[k][e], g, rp, rg);
-            if constexpr (Obj::streaming) Obj::feed(acc[e], xs[k][e], d + k);
+            step_draw<REPLAY>(P, t, gi, d, rp, rg);
+            pso_update(P, x.e[j], v.e[j], pb.e[j], sG[d], rp, rg);
+            if constexpr (Obj::streaming) Obj::feed(acc, x.e[j], d);
         }
-        const long long row = (long long)(d + k) * P.ld + i0;
-        VecIO<VEC>::store(xout + row, xs[k]);
-        VecIO<VEC>::store(vout + row, vs[k]);
     }
 }
 
-// all dimensions of VEC particles; returns their new costs
-template <class Obj, bool REPLAY, int VEC>
-__device__ __forceinline__ void pso_move(const PsoDev &P, uint32_t t, long long i0, const double *sG,
-                                         const double *xin, const double *vin, double *xout, double *vout,
-                                         double (&cost)[VEC])
+// K consecutive groups of one particle: all loads first (3K independent 32-byte requests), then math, then stores
+template <class Obj, bool REPLAY, int K>
+__device__ __forceinline__ void pso_groups(const PsoDev &P, uint32_t t, long long li, int q, const double *sG, ObjAcc &acc,
+                                           const double *xin, const double *vin, const double *pbin, double *xout,
+                                           double *vout, bool load_pb)
 {
-    const int n = P.n;
-    ObjAcc acc[VEC];
-    if constexpr (Obj::streaming) {
+    D4 xs[K], vs[K], ps[K];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) Obj::begin(acc[e], n);
+    for (int k = 0; k < K; ++k) {
+        const long long off = goff(P, q + k, li);
+        xs[k] = ld256(xin + off);
+        vs[k] = ld256(vin + off);
+        if (load_pb) ps[k] = ld256(pbin + off);
     }
-    constexpr int UD = 4;
-    int d = 0;
-    for (; d + UD <= n; d += UD) pso_rows<Obj, REPLAY, VEC, UD>(P, t, i0, d, sG, acc, xin, vin, xout, vout);
-    for (; d < n; ++d) pso_rows<Obj, REPLAY, VEC, 1>(P, t, i0, d, sG, acc, xin, vin, xout, vout);
+    if (!load_pb) {
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-        if constexpr (Obj::streaming) cost[e] = Obj::end(acc[e], n);
-        else cost[e] = Obj::eval(xout + i0 + e, n, P.ld);
+        for (int k = 0; k < K; ++k) ps[k] = xs[k];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        pso_group_math<Obj, REPLAY, true>(P, t, P.first + li, q + k, sG, acc, xs[k], vs[k], ps[k], 4);
+        const long long off = goff(P, q + k, li);
+        st256(xout + off, xs[k]);
+        st256(vout + off, vs[k]);
+    }
+}
+
+// all dimensions of one particle; returns its new cost
+template <class Obj, bool REPLAY>
+__device__ __forceinline__ double pso_move(const PsoDev &P, uint32_t t, long long li, const double *sG, const double *xin,
+                                           const double *vin, const double *pbin, double *xout, double *vout, bool load_pb)
+{
+    const int n = P.n, nfull = n >> 2, rem = n & 3;
+    ObjAcc acc;
+    if constexpr (Obj::streaming) Obj::begin(acc, n);
+    constexpr int UQ = 2;
+    int q = 0;
+    for (; q + UQ <= nfull; q += UQ) pso_groups<Obj, REPLAY, UQ>(P, t, li, q, sG, acc, xin, vin, pbin, xout, vout, load_pb);
+    for (; q < nfull; ++q) pso_groups<Obj, REPLAY, 1>(P, t, li, q, sG, acc, xin, vin, pbin, xout, vout, load_pb);
+    if (rem) { // ragged last group: the padding dimensions are carried through unchanged
+        const long long off = goff(P, q, li);
+        D4 x = ld256(xin + off), v = ld256(vin + off), pb = x;
+        if (load_pb) pb = ld256(pbin + off);
+        pso_group_math<Obj, REPLAY, false>(P, t, P.first + li, q, sG, acc, x, v, pb, rem);
+        st256(xout + off, x);
+        st256(vout + off, v);
+    }
+    if constexpr (Obj::streaming) return Obj::end(acc, n);
+    else return Obj::eval(GroupedView{xout + li * 4, P.ld * 4}, n);
+}
+
+// end of a particle's pass in synchronous mode: pbest cost + flag byte (:417-419), running arg-min
+__device__ __forceinline__ void pso_finish_particle(const PsoDev &P, long long li, double c, double pbc_old, unsigned flags,
+                                                    MinLoc &best)
+{
+    const bool stale = flags & 1u, role = (flags >> 1) & 1u;
+    const bool imp = c < pbc_old;
+    if (imp) P.pbc[li] = c;
+    const unsigned nf = (imp ? 1u : 0u) | ((role != stale) ? 2u : 0u); // a stale particle moved to the other buffer
+    if (nf != flags) P.pbflag[li] = (unsigned char)nf;
+    const double cs = sanitize_cost(c);
+    if (cs < best.c) {
+        best.c = cs;
+        best.i = P.first + li;
     }
 }
 
@@ -163,16 +208,19 @@ __device__ __forceinline__ bool grid_minloc_last_block(const PsoDev &P, MinLoc m
     return true;
 }
 
-// this rank's exchange record: (cost, global index, position column of `src`)
+// this rank's exchange record: (cost, global index, the particle's position).  src == nullptr: the buffer that
+// holds x is named by the particle's role bit.
 __device__ __forceinline__ void write_record(const PsoDev &P, double cost, long long gidx, const double *src)
 {
     const bool none = gidx == kNoIndex || gidx < 0;
+    const long long li = none ? 0 : gidx - P.first;
+    if (!src && !none) src = (__ldcg(P.pbflag + li) & 2u) ? P.pb : P.x;
     if (threadIdx.x == 0) {
         P.send[REC_COST] = cost;
         P.send[REC_IDX] = none ? -1.0 : (double)gidx;
     }
     for (int d = threadIdx.x; d < P.n; d += blockDim.x)
-        P.send[REC_X + d] = none ? 0.0 : __ldcg(src + (long long)d * P.ld + (gidx - P.first));
+        P.send[REC_X + d] = none ? 0.0 : __ldcg(src + goff(P, d >> 2, li) + (d & 3));
 }
 
 // lowest cost, then lowest global index, over the ranks' records; -1 when every record is empty
@@ -218,14 +266,21 @@ __device__ __forceinline__ void pso_apply_step(const PsoDev &P, const double *re
         for (int d = threadIdx.x; d < P.n; d += blockDim.x) P.G[d] = recs[s_winner * R + REC_X + d];
 }
 
-// ---- kernels -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_gbest(const PsoDev &P, double *sG)
+{
+    const int npad = (P.n + 3) & ~3;
+    for (int d = threadIdx.x; d < npad; d += blockDim.x) sG[d] = d < P.n ? P.G[d] : 0.0;
+    __syncthreads();
+}
+
+// ---- kernels -------------------------------------------------------------------------------------------------
 
 // :357-359.  G already holds x0 (H2D copy).
 template <class Obj> __global__ void pso_x0_kernel(const PsoDev P)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     PsoCtrl *c = P.ctrl;
-    c->Gc = objective_strided<Obj>(P.G, P.n, 1);
+    c->Gc = objective_on<Obj>(StridedView{P.G, 1}, P.n);
     for (int j = 0; j < EQS_STALL_WINDOW; ++j) c->ring[j] = dinf();
     c->ring_i = 0;
     c->iter = 0;
@@ -234,14 +289,13 @@ template <class Obj> __global__ void pso_x0_kernel(const PsoDev P)
     c->stalled = 0;
     c->pass_done = 0;
     c->block_counter = 0;
-    c->nan_seen = 0;
 }
 
 // :361-389 without the (order-dependent) gbest bookkeeping, which pso_ring_scan_kernel reconstructs
 template <class Obj, bool REPLAY> __global__ void __launch_bounds__(PSO_BLOCK) pso_init_kernel(const PsoDev P)
 {
     __shared__ MinLoc s_red[32];
-    const int n = P.n;
+    const int n = P.n, nq = (n + 3) >> 2;
     const long long ngroups = (P.nloc + PSO_GROUP - 1) / PSO_GROUP;
     MinLoc best{dinf(), kNoIndex};
     for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
@@ -251,31 +305,41 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(PSO_BLOCK) p
             const long long gi = P.first + li;
             ObjAcc acc;
             if constexpr (Obj::streaming) Obj::begin(acc, n);
-            for (int d = 0; d < n; ++d) {
-                double pu, vu;
-                if constexpr (REPLAY) {
-                    pu = P.replay[gi * 2 * n + d];
-                    vu = P.replay[gi * 2 * n + n + d];
-                } else {
-                    const uint4 w = philox_draw(P.key, STREAM_PSO_INIT, 0u, gi, (uint32_t)d);
-                    pu = u01(w.x, w.y);
-                    vu = u01(w.z, w.w);
+            for (int q = 0; q < nq; ++q) {
+                D4 x4, v4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int d = 4 * q + j;
+                    x4.e[j] = 0.0;
+                    v4.e[j] = 0.0;
+                    if (d < n) {
+                        double pu, vu;
+                        if constexpr (REPLAY) {
+                            pu = P.replay[gi * 2 * n + d];
+                            vu = P.replay[gi * 2 * n + n + d];
+                        } else {
+                            const uint4 w = philox_draw(P.key, STREAM_PSO_INIT, 0u, gi, (uint32_t)d);
+                            pu = u01(w.x, w.y);
+                            vu = u01(w.z, w.w);
+                        }
+                        const double lo = P.lower[d], hi = P.upper[d];
+                        x4.e[j] = pu * (hi - lo) + lo;              // Uniform::new_inclusive(lo, hi), :124-129
+                        const double dist = fabs(hi - lo);          // :135
+                        v4.e[j] = vu * (dist + dist) + (-dist);     // Uniform::new_inclusive(-dist, dist)
+                        if constexpr (Obj::streaming) Obj::feed(acc, x4.e[j], d);
+                    }
                 }
-                const double lo = P.lower[d], hi = P.upper[d];
-                const double x = pu * (hi - lo) + lo;              // Uniform::new_inclusive(lo, hi), :124-129
-                const double dist = fabs(hi - lo);                 // :135
-                const double v = vu * (dist + dist) + (-dist);     // Uniform::new_inclusive(-dist, dist)
-                const long long row = (long long)d * P.ld + li;
-                P.x[row] = x;
-                P.v[row] = v;
-                P.pb[row] = x;                                     // best_position = position, :385
-                if constexpr (Obj::streaming) Obj::feed(acc, x, d);
+                const long long off = goff(P, q, li);
+                st256(P.x + off, x4);
+                st256(P.v + off, v4);
+                if (!P.sync) st256(P.pb + off, x4);                 // best_position = position, :385 (sync: flag below)
             }
             double cost;
             if constexpr (Obj::streaming) cost = Obj::end(acc, n);
-            else cost = Obj::eval(P.x + li, n, P.ld);
+            else cost = Obj::eval(GroupedView{P.x + li * 4, P.ld * 4}, n);
             P.pbc[li] = cost;
             P.cost[li] = cost;
+            P.pbflag[li] = P.sync ? 1 : 0;                          // sync: stale = pbest position is the position
             c = sanitize_cost(cost);
             if (c < best.c) {
                 best.c = c;
@@ -382,10 +446,10 @@ __global__ void pso_init_apply_kernel(const PsoDev P)
         for (int d = threadIdx.x; d < P.n; d += blockDim.x) P.G[d] = P.recv[s_winner * R + REC_X + d];
 }
 
-// K2 + K3: the synchronous population step.  One thread owns VEC adjacent particles and walks the dimensions;
-// every global access is a lane-contiguous 8*VEC-byte word.  Philox draws, the update and the objective all
-// stay in registers; HBM sees x, v, pbest once in and x, v once out.
-template <class Obj, bool REPLAY, int VEC>
+// K2 + K3: the synchronous population step.  One thread owns one particle and walks its 4-dimension groups with
+// 256-bit accesses; Philox draws, update and objective stay in registers.  HBM sees x, v (and pbest unless stale)
+// once in and x, v once out.
+template <class Obj, bool REPLAY>
 __global__ void __launch_bounds__(PSO_BLOCK) pso_step_kernel(const PsoDev P, int inline_apply)
 {
     extern __shared__ double sG[];
@@ -393,40 +457,20 @@ __global__ void __launch_bounds__(PSO_BLOCK) pso_step_kernel(const PsoDev P, int
     PsoCtrl *ctrl = P.ctrl;
     if (ctrl->stalled) return; // :395-397 -- passes after the stall test fires are no-ops
     const uint32_t t = (uint32_t)ctrl->iter;
-    const int n = P.n;
-    for (int d = threadIdx.x; d < n; d += blockDim.x) sG[d] = P.G[d];
-    __syncthreads();
-
+    load_gbest(P, sG);
     MinLoc best{dinf(), kNoIndex};
-    const long long nunits = (P.nloc + VEC - 1) / VEC;
-    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < nunits;
-         u += (long long)gridDim.x * blockDim.x) {
-        const long long i0 = u * VEC;
-        double cost[VEC];
-        pso_move<Obj, REPLAY, VEC>(P, t, i0, sG, P.x, P.v, P.x, P.v, cost);
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            const long long li = i0 + e;
-            if (li < P.nloc) {
-                const double c = cost[e];
-                if (c < P.pbc[li]) { // :417-419
-                    P.pbc[li] = c;
-                    for (int d = 0; d < n; ++d) {
-                        const long long row = (long long)d * P.ld + li;
-                        P.pb[row] = P.x[row];
-                    }
-                }
-                const double cs = sanitize_cost(c);
-                if (cs < best.c) {
-                    best.c = cs;
-                    best.i = P.first + li;
-                }
-            }
-        }
+    for (long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x; li < P.nloc;
+         li += (long long)gridDim.x * blockDim.x) {
+        const unsigned f = P.pbflag[li];
+        const bool stale = f & 1u, role = f & 2u;
+        const double pbc_old = P.pbc[li]; // issued now, consumed after the last dimension
+        double *xb = role ? P.pb : P.x, *ob = role ? P.x : P.pb;
+        const double c = pso_move<Obj, REPLAY>(P, t, li, sG, xb, P.v, ob, stale ? ob : xb, P.v, !stale);
+        pso_finish_particle(P, li, c, pbc_old, f, best);
     }
     MinLoc win;
     if (grid_minloc_last_block(P, best, s_red, win)) {
-        write_record(P, win.c, win.i, P.x);
+        write_record(P, win.c, win.i, nullptr);
         if (inline_apply) {
             __syncthreads();
             pso_apply_step(P, P.send, 1);
@@ -436,7 +480,7 @@ __global__ void __launch_bounds__(PSO_BLOCK) pso_step_kernel(const PsoDev P, int
 
 __global__ void pso_step_apply_kernel(const PsoDev P) { pso_apply_step(P, P.recv, P.world); }
 
-// ---- sequential-exact mode (the reference's semantics, F6) ---------------------------------------------
+// ---- sequential-exact mode (the reference's semantics, F6) ---------------------------------------------------
 // speculate: move every particle with global index >= start against the CURRENT gbest into (x2, v2, cost)
 // without committing, and find the FIRST particle whose cost beats gbest.
 template <class Obj, bool REPLAY>
@@ -448,17 +492,15 @@ __global__ void __launch_bounds__(PSO_BLOCK) pso_spec_kernel(const PsoDev P, lon
     if (ctrl->stalled) return;
     const uint32_t t = (uint32_t)ctrl->iter;
     const double Gc = ctrl->Gc;
-    for (int d = threadIdx.x; d < P.n; d += blockDim.x) sG[d] = P.G[d];
-    __syncthreads();
+    load_gbest(P, sG);
     MinLoc first{0.0, kNoIndex}; // min over index only: all costs equal => lowest index wins
     for (long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x; li < P.nloc;
          li += (long long)gridDim.x * blockDim.x) {
         const long long gi = P.first + li;
         if (gi < start_g) continue;
-        double cost[1];
-        pso_move<Obj, REPLAY, 1>(P, t, li, sG, P.x, P.v, P.x2, P.v2, cost);
-        P.cost[li] = cost[0];
-        if (cost[0] < Gc && gi < first.i) first.i = gi; // :417,:420 (cost < Gc implies cost < pbest cost)
+        const double cost = pso_move<Obj, REPLAY>(P, t, li, sG, P.x, P.v, P.pb, P.x2, P.v2, true);
+        P.cost[li] = cost;
+        if (cost < Gc && gi < first.i) first.i = gi; // :417,:420 (cost < Gc implies cost < pbest cost)
     }
     MinLoc win;
     if (grid_minloc_last_block(P, first, s_red, win)) {
@@ -506,6 +548,7 @@ __global__ void pso_spec_apply_kernel(const PsoDev P)
 // commit the speculated state of global indices [start_g, end_g]: x, v <- x2, v2 and the pbest update :417-419
 __global__ void __launch_bounds__(PSO_BLOCK) pso_commit_kernel(const PsoDev P, long long start_g, long long end_g)
 {
+    const int nq = (P.n + 3) >> 2;
     for (long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x; li < P.nloc;
          li += (long long)gridDim.x * blockDim.x) {
         const long long gi = P.first + li;
@@ -513,23 +556,17 @@ __global__ void __launch_bounds__(PSO_BLOCK) pso_commit_kernel(const PsoDev P, l
         const double c = P.cost[li];
         const bool imp = c < P.pbc[li];
         if (imp) P.pbc[li] = c;
-        for (int d = 0; d < P.n; ++d) {
-            const long long row = (long long)d * P.ld + li;
-            const double xv = P.x2[row];
-            P.x[row] = xv;
-            P.v[row] = P.v2[row];
-            if (imp) P.pb[row] = xv;
+        for (int q = 0; q < nq; ++q) {
+            const long long off = goff(P, q, li);
+            const D4 xv = ld256(P.x2 + off);
+            st256(P.x + off, xv);
+            st256(P.v + off, ld256(P.v2 + off));
+            if (imp) st256(P.pb + off, xv);
         }
     }
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-int env_int(const char *name, int dflt)
-{
-    const char *s = getenv(name);
-    return s ? atoi(s) : dflt;
-}
 
 template <class K> int persistent_grid(Ctx *ctx, K kernel, int block, size_t smem, long long units_per_block_iter,
                                        long long units, int &grid)
@@ -545,7 +582,7 @@ template <class K> int persistent_grid(Ctx *ctx, K kernel, int block, size_t sme
 
 } // namespace
 
-// ---- host driver ---------------------------------------------------------------------------------------
+// ---- host driver ---------------------------------------------------------------------------------------------
 
 PsoSolver::~PsoSolver()
 {
@@ -611,18 +648,20 @@ int PsoSolver::create(const eqs_pso_params *p)
     D.first = first;
     D.nloc = nloc;
     D.ntotal = p->particle_count;
-    D.ld = (long long)align_up((size_t)std::max<int64_t>(nloc, 1), 16);
+    D.ld = (long long)align_up((size_t)std::max<int64_t>(nloc, 1), 32); // rows start on 1 KB boundaries
     D.w = p->w;
     D.c1 = p->c1;
     D.c2 = p->c2;
     D.tol = p->tol;
     D.key = philox_key(p->seed);
+    D.sync = p->mode == EQS_PSO_SYNCHRONOUS;
     D.replay = nullptr;
     D.replay_t0 = 0;
-    if ((size_t)n * sizeof(double) > 200 * 1024) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "n too large for the shared-memory gbest tile");
+    const int nq = (n + 3) / 4;
+    if ((size_t)nq * 4 * sizeof(double) > 100 * 1024) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "n too large for the shared-memory gbest tile");
 
     const bool seq = p->mode == EQS_PSO_SEQUENTIAL_EXACT;
-    const size_t mat = (size_t)n * D.ld * sizeof(double);
+    const size_t mat = (size_t)nq * 4 * D.ld * sizeof(double);
     const size_t vec = (size_t)D.ld * sizeof(double);
     const size_t R = (size_t)record_doubles(n) * sizeof(double);
     const long long ngroups = std::max<long long>((nloc + PSO_GROUP - 1) / PSO_GROUP, 1);
@@ -635,6 +674,7 @@ int PsoSolver::create(const eqs_pso_params *p)
         return o;
     };
     const size_t o_x = plan(mat), o_v = plan(mat), o_pb = plan(mat), o_pbc = plan(vec), o_cost = plan(vec);
+    const size_t o_flag = plan((size_t)D.ld);
     const size_t o_x2 = seq ? plan(mat) : 0, o_v2 = seq ? plan(mat) : 0;
     const size_t o_G = plan(n * sizeof(double)), o_lo = plan(n * sizeof(double)), o_hi = plan(n * sizeof(double));
     const size_t o_ctrl = plan(sizeof(PsoCtrl));
@@ -650,6 +690,7 @@ int PsoSolver::create(const eqs_pso_params *p)
     D.pb = (double *)(base + o_pb);
     D.pbc = (double *)(base + o_pbc);
     D.cost = (double *)(base + o_cost);
+    D.pbflag = (unsigned char *)(base + o_flag);
     D.x2 = seq ? (double *)(base + o_x2) : nullptr;
     D.v2 = seq ? (double *)(base + o_v2) : nullptr;
     D.G = (double *)(base + o_G);
@@ -760,7 +801,7 @@ int PsoSolver::init_apply() { return launch_init_apply(); }
 
 int PsoSolver::init(const double *x0)
 {
-    if (manual_ && d_.world > 1) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "exchange = MANUAL: use the split-phase calls");
+    if (manual_) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "exchange = MANUAL: use the split-phase calls");
     EQS_TRY(init_local(x0, 0));
     EQS_TRY(exchange());
     EQS_TRY(init_local(x0, 1));
@@ -771,22 +812,20 @@ int PsoSolver::init(const double *x0)
 int PsoSolver::launch_step()
 {
     const bool replay = d_.replay != nullptr;
-    const int vec = replay ? 1 : env_int("EQS_PSO_VEC", 2);
-    const size_t smem = (size_t)d_.n * sizeof(double);
     const int inline_apply = (d_.world == 1 && !manual_) ? 1 : 0;
     int rc = EQS_OK;
+    const size_t smem = (size_t)((d_.n + 3) / 4) * 4 * sizeof(double);
     dispatch_objective(p_.objective_id, [&]<class Obj>() {
-        auto run = [&](auto kernel, int v) {
+        auto run = [&](auto kernel) {
             if (grid_step_ == 0) {
-                rc = persistent_grid(ctx_, kernel, PSO_BLOCK, smem, (long long)PSO_BLOCK * v, d_.nloc, grid_step_);
+                rc = persistent_grid(ctx_, kernel, PSO_BLOCK, smem, PSO_BLOCK, d_.nloc, grid_step_);
                 if (rc != EQS_OK) return;
             }
             kernel<<<grid_step_, PSO_BLOCK, smem, ctx_->stream>>>(d_, inline_apply);
             launches_++;
         };
-        if (replay) run(pso_step_kernel<Obj, true, 1>, 1);
-        else if (vec == 1) run(pso_step_kernel<Obj, false, 1>, 1);
-        else run(pso_step_kernel<Obj, false, 2>, 2);
+        if (replay) run(pso_step_kernel<Obj, true>);
+        else run(pso_step_kernel<Obj, false>);
     });
     EQS_TRY(rc);
     EQS_CUDA(ctx_, cudaGetLastError());
@@ -807,7 +846,7 @@ int PsoSolver::sequential_pass()
     EQS_TRY(fetch_ctrl());
     if (h_ctrl_->stalled) return EQS_OK;
     const bool replay = d_.replay != nullptr;
-    const size_t smem = (size_t)d_.n * sizeof(double);
+    const size_t smem = (size_t)((d_.n + 3) / 4) * 4 * sizeof(double);
     long long start = 0;
     for (;;) {
         int rc = EQS_OK;
@@ -862,7 +901,7 @@ int PsoSolver::step_apply() { return launch_step_apply(); }
 int PsoSolver::step(int64_t iters, const double *replay_step)
 {
     EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
-    if (manual_ && d_.world > 1) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "exchange = MANUAL: use the split-phase calls");
+    if (manual_) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "exchange = MANUAL: use the split-phase calls");
     if (replay_step) {
         EQS_TRY(fetch_ctrl());
         EQS_TRY(upload_replay(replay_step, iters * p_.particle_count * 2 * (int64_t)p_.n));
@@ -910,24 +949,38 @@ int PsoSolver::read_gbest(double *g, double *cost, int64_t *iters, int32_t *stal
 int PsoSolver::read_state(double *x, double *v, double *pb, double *pbc)
 {
     EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
-    const int n = d_.n;
+    const int n = d_.n, nq = (n + 3) / 4;
     const long long L = d_.nloc, ld = d_.ld;
-    std::vector<double> tmp((size_t)n * ld);
-    auto pull = [&](const double *dev, double *out) -> int {
-        if (!out) return EQS_OK;
-        EQS_CUDA(ctx_, cudaMemcpyAsync(tmp.data(), dev, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx_->stream));
+    const size_t m = (size_t)nq * 4 * ld;
+    auto pull = [&](const void *dev, void *host, size_t bytes) -> int {
+        EQS_CUDA(ctx_, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx_->stream));
         EQS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
-        for (long long i = 0; i < L; ++i)
-            for (int d = 0; d < n; ++d) out[i * n + d] = tmp[(size_t)d * ld + i]; // SoA -> the reference's particle-major
         return EQS_OK;
     };
-    EQS_TRY(pull(d_.x, x));
-    EQS_TRY(pull(d_.v, v));
-    EQS_TRY(pull(d_.pb, pb));
-    if (pbc) {
-        EQS_CUDA(ctx_, cudaMemcpyAsync(pbc, d_.pbc, L * sizeof(double), cudaMemcpyDeviceToHost, ctx_->stream));
-        EQS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+    auto at = [&](const std::vector<double> &buf, long long i, int d) { return buf[((size_t)(d >> 2) * ld + i) * 4 + (d & 3)]; };
+    // device layout -> the reference's particle-major Vec<Particle>, resolving the role / stale bits of synchronous mode
+    std::vector<unsigned char> flag((size_t)std::max<long long>(L, 1), 0);
+    if (d_.sync && L > 0) EQS_TRY(pull(d_.pbflag, flag.data(), (size_t)L));
+    if (x || pb) {
+        std::vector<double> A(m), B(m);
+        EQS_TRY(pull(d_.x, A.data(), m * sizeof(double)));
+        EQS_TRY(pull(d_.pb, B.data(), m * sizeof(double)));
+        for (long long i = 0; i < L; ++i) {
+            const bool stale = flag[i] & 1, role = flag[i] & 2;
+            const std::vector<double> &X = role ? B : A, &O = role ? A : B;
+            for (int d = 0; d < n; ++d) {
+                if (x) x[i * n + d] = at(X, i, d);
+                if (pb) pb[i * n + d] = stale ? at(X, i, d) : at(O, i, d);
+            }
+        }
     }
+    if (v) {
+        std::vector<double> V(m);
+        EQS_TRY(pull(d_.v, V.data(), m * sizeof(double)));
+        for (long long i = 0; i < L; ++i)
+            for (int d = 0; d < n; ++d) v[i * n + d] = at(V, i, d);
+    }
+    if (pbc && L > 0) EQS_TRY(pull(d_.pbc, pbc, (size_t)L * sizeof(double)));
     return EQS_OK;
 }
 

@@ -26,8 +26,9 @@ struct PsoCtrl {
 };
 
 struct PsoDev {
-    double *x, *v, *pb, *pbc;       // population, SoA [n][ld]
+    double *x, *v, *pb, *pbc;       // population, SoA [n][ld]; synchronous mode: x = buffer A, pb = buffer B (pso.cu)
     double *cost;                   // [ld] costs of the last evaluation (init ring scan, sequential mode)
+    unsigned char *pbflag;          // [ld] synchronous mode: bit 0 = stale (pbest == position), bit 1 = x lives in B
     double *x2, *v2;                // sequential mode: speculative next state
     double *G;                      // [n] global_best_position
     PsoCtrl *ctrl;
@@ -40,6 +41,7 @@ struct PsoDev {
     long long ld, nloc, first, ntotal;
     long long replay_t0;            // iteration index of replay block 0
     int n, world, rank;
+    int sync;                       // synchronous mode: role-swapping buffers, flags in pbflag
     double w, c1, c2, tol;
     PhiloxKey key;
 };

@@ -117,8 +117,10 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 
 double orc_u01(uint32_t w_lo, uint32_t w_hi)
 {
-    uint64_t k = ((uint64_t)(w_hi & 0x1FFFFFu) << 32) | (uint64_t)w_lo; /* 53 bits */
-    return (double)k * 0x1.0p-53;
+    /* 52 random mantissa bits under exponent 0, minus one: what rand's Uniform<f64> does
+     * (into_float_with_exponent(0) - 1.0), so u = k * 2^-52 with k = (w_hi mod 2^20) * 2^32 + w_lo */
+    uint64_t k = ((uint64_t)(w_hi & 0xFFFFFu) << 32) | (uint64_t)w_lo; /* 52 bits */
+    return (double)k * 0x1.0p-52;
 }
 
 /* Draw-index contract: key = (seed lo, seed hi);

@@ -58,7 +58,7 @@ enum { ORC_CE_DIV_REFERENCE_TEN = 0, ORC_CE_DIV_ELITE_COUNT = 1 };
 /* ---- building blocks ---------------------------------------------------------------------- */
 double orc_objective(int id, const double *x, int n);
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-/* u = ((w_hi mod 2^21) * 2^32 + w_lo) * 2^-53, the draw contract of DESIGN.md */
+/* u = ((w_hi mod 2^20) * 2^32 + w_lo) * 2^-52 in [0,1), the draw contract of DESIGN.md */
 double orc_u01(uint32_t w_lo, uint32_t w_hi);
 /* fill helpers used by tests to cross-check the device generator */
 void orc_pso_init_draws(uint64_t seed, int64_t gidx, int n, double *pos_u, double *vel_u);

@@ -109,7 +109,7 @@ def philox4x32_10(ctr, key):
 
 
 def u01(w_lo, w_hi):
-    return float(((w_hi & 0x1FFFFF) << 32) | w_lo) * 2.0 ** -53
+    return float(((w_hi & 0xFFFFF) << 32) | w_lo) * 2.0 ** -52
 
 
 def draw(seed, stream, t, gidx, j):
