@@ -65,7 +65,7 @@ class ClockSampler:
     """nvidia-smi sampled every 100 ms while the timed region runs."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_power_cap,clocks.mem,temperature.gpu")
 
     def __init__(self, device: int):
         self.rows = []
@@ -92,7 +92,7 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self, t0: float, t1: float, window: str):
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, pw, mem, temp = [], [], set(), [], [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, line in self.rows:
             if ts < t0 or ts > t1 + 0.15:
@@ -107,10 +107,16 @@ class ClockSampler:
             for name, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+            try:
+                pw.append(float(parts[2])); mem.append(float(parts[7])); temp.append(float(parts[8]))
+            except (ValueError, IndexError):
+                pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": window}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm), "window": window}
+                "samples": len(sm), "window": window,
+                "power_w": float(np.median(pw)) if pw else None, "mem_mhz": float(np.median(mem)) if mem else None,
+                "temp_c": float(np.median(temp)) if temp else None}
 
 
 def cpu_baseline_port(workload: str, budget_s: float):

@@ -58,6 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         os.makedirs(shadow, exist_ok=True)
         shutil.copyfile(user, os.path.join(shadow, "user_objective.cuh"))
         flags += ["-I", shadow]
+    flags += os.environ.get("EQS_NVCC_DEFINES", "").split()  # e.g. "-DEQS_PSO_UQ=3" for tuning sweeps
     if verbose:
         flags += ["-Xptxas", "-v"]
 

@@ -36,6 +36,14 @@ namespace eqs {
 
 namespace {
 
+// tuning knobs of the step kernel (measured on B200, profiles/r01_sweep.md): groups per load batch, min CTAs per SM
+#ifndef EQS_PSO_UQ
+#define EQS_PSO_UQ 2
+#endif
+#ifndef EQS_PSO_MINB
+#define EQS_PSO_MINB 2
+#endif
+
 constexpr long long kNoIndex = 0x7fffffffffffffffLL;
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
@@ -147,7 +155,7 @@ __device__ __forceinline__ double pso_move(const PsoDev &P, uint32_t t, long lon
     const int n = P.n, nfull = n >> 2, rem = n & 3;
     ObjAcc acc;
     if constexpr (Obj::streaming) Obj::begin(acc, n);
-    constexpr int UQ = 2;
+    constexpr int UQ = EQS_PSO_UQ;
     int q = 0;
     for (; q + UQ <= nfull; q += UQ) pso_groups<Obj, REPLAY, UQ>(P, t, li, q, sG, acc, xin, vin, pbin, xout, vout, load_pb);
     for (; q < nfull; ++q) pso_groups<Obj, REPLAY, 1>(P, t, li, q, sG, acc, xin, vin, pbin, xout, vout, load_pb);
@@ -450,7 +458,7 @@ __global__ void pso_init_apply_kernel(const PsoDev P)
 // 256-bit accesses; Philox draws, update and objective stay in registers.  HBM sees x, v (and pbest unless stale)
 // once in and x, v once out.
 template <class Obj, bool REPLAY>
-__global__ void __launch_bounds__(PSO_BLOCK) pso_step_kernel(const PsoDev P, int inline_apply)
+__global__ void __launch_bounds__(PSO_BLOCK, EQS_PSO_MINB) pso_step_kernel(const PsoDev P, int inline_apply)
 {
     extern __shared__ double sG[];
     __shared__ MinLoc s_red[32];
