@@ -237,14 +237,14 @@ def main():
     t1 = time.monotonic()
     ms, launches = run.last_step_ms()
     window = "timed region"
-    if sampler is not None and (t1 - t0) < 0.6:
+    # collective decision (the extra passes contain the per-pass exchange): every rank must take the same branch
+    if max_over_ranks(1.0 if (t1 - t0) < 0.6 else 0.0) > 0.5:
         # the region is shorter than a few nvidia-smi periods: keep the same kernel running (untimed) for the sampler
-        t_end = time.monotonic() + 1.2
-        while time.monotonic() < t_end:
-            run.step(200)
-            run.sync()
+        extra = int(max_over_ranks(max(1.0, 1.2 / max(ms * 1e-3 / args.steps, 1e-6))))
+        run.step(extra)
+        run.sync()
         t1 = time.monotonic()
-        window = "timed region + 1.2 s of the same step kernel (region too short to sample)"
+        window = "timed region + ~1.2 s of the same step kernel (region too short to sample)"
     if world > 1:
         dist.barrier()
     clocks = None

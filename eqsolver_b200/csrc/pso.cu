@@ -486,7 +486,11 @@ __global__ void __launch_bounds__(PSO_BLOCK, EQS_PSO_MINB) pso_step_kernel(const
     }
 }
 
-__global__ void pso_step_apply_kernel(const PsoDev P) { pso_apply_step(P, P.recv, P.world); }
+__global__ void pso_step_apply_kernel(const PsoDev P)
+{
+    if (P.ctrl->stalled) return; // the step kernel of a stalled pass did nothing: neither may this (:395-397)
+    pso_apply_step(P, P.recv, P.world);
+}
 
 // ---- sequential-exact mode (the reference's semantics, F6) ---------------------------------------------------
 // speculate: move every particle with global index >= start against the CURRENT gbest into (x2, v2, cost)

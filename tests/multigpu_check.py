@@ -1,0 +1,130 @@
+#!/usr/bin/env python3
+"""Multi-GPU parity check, one process per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multigpu_check.py
+
+Every rank holds a contiguous block of the population; per pass the ranks exchange one record over NCCL
+(csrc/comm.cu).  The sharded GPU run must equal the UNSHARDED oracle: bit for bit for ParticleSwarm (min-loc with
+lowest-index ties is order-free), to 1e-12 for CrossEntropy (moment sums are taken per rank, then in rank order).
+Also run by tests/test_multigpu.py when the box has >= 2 GPUs.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import eqsolver_b200 as E
+    from eqsolver_b200 import distributed as ED
+    from oracle import oracle as O
+
+    rank, world, local = ED.env_rank_world()
+    torch.cuda.set_device(local)
+    dist.init_process_group(backend="cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local))
+    ctx = ED.init_context(local)
+    assert ctx.rank_world == (rank, world)
+
+    def same_everywhere(a, what):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        t = torch.from_numpy(a.copy()).cuda()
+        gathered = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        for r, g in enumerate(gathered):
+            assert np.array_equal(g.cpu().numpy().view(np.uint64), a.view(np.uint64)), f"{what}: rank {r} differs"
+
+    # ---- ParticleSwarm, synchronous: sharded GPU == unsharded oracle, bit for bit --------------------------------
+    for (obj, n, N, iters) in [(E.Objective.ROSENBROCK, 9, 10007, 12), (E.Objective.SPHERE, 4, 3 * world + 1, 5),
+                               (E.Objective.USER, 6, 4099, 6)]:
+        lower, upper, x0 = [-5.0] * n, [10.0] * n, np.full(n, 3.0)
+        ps = (E.ParticleSwarm.new(obj, lower, upper).with_particle_count(N).with_tol(0.0).with_seed(1729)
+              .with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx))
+        run = ps.start(x0)
+        o = O.Pso(int(obj), lower, upper, particle_count=N, tol=0.0, mode=O.SYNCHRONOUS, seed=1729)
+        o.init(x0)
+        first, local_n = E.shard_range(N, world, rank)
+        assert (run.first, run.local) == (first, local_n)
+        for t in range(iters + 1):
+            g, c, it, stalled, _ = run.gbest()
+            assert np.array_equal(g.view(np.uint64), o.gbest().view(np.uint64)), f"PSO {obj.name} gbest pass {t}"
+            assert c == o.gbest_cost() and it == o.iters()
+            assert np.array_equal(run.ring()[0].view(np.uint64), o.ring()[0].view(np.uint64)) and run.ring()[1] == o.ring()[1]
+            x, v, pb, pbc = run.state()
+            ox, ov, opb, opbc = o.state()
+            sl = slice(first, first + local_n)
+            for a, b, nm in ((x, ox[sl], "x"), (v, ov[sl], "v"), (pb, opb[sl], "pbest"), (pbc, opbc[sl], "pbest cost")):
+                assert np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(b).view(np.uint64)), \
+                    f"PSO {obj.name} {nm} pass {t} rank {rank}"
+            same_everywhere(g, "gbest")
+            if t < iters:
+                run.step(1)
+                o.step()
+        run.close()
+
+    # ---- ParticleSwarm, sequential-exact across ranks (speculate-and-repair with a global first-index exchange) ---
+    n, N, iters = 5, 2003, 4
+    lower, upper, x0 = [-5.0] * n, [10.0] * n, np.full(n, 3.0)
+    ps = (E.ParticleSwarm.new(E.Objective.ROSENBROCK, lower, upper).with_particle_count(N).with_tol(0.0).with_seed(7)
+          .with_mode(E.PsoMode.SEQUENTIAL_EXACT).with_context(ctx))
+    run = ps.start(x0)
+    o = O.Pso(O.ROSENBROCK, lower, upper, particle_count=N, tol=0.0, mode=O.SEQUENTIAL, seed=7)
+    o.init(x0)
+    for t in range(iters):
+        run.step(1)
+        o.step()
+        g, c, it, _, _ = run.gbest()
+        assert np.array_equal(g.view(np.uint64), o.gbest().view(np.uint64)) and c == o.gbest_cost(), f"seq pass {t}"
+        assert np.array_equal(run.ring()[0].view(np.uint64), o.ring()[0].view(np.uint64))
+    run.close()
+
+    # ---- whole solve through the builder, stall exit on every rank at the same pass -------------------------------
+    ps = (E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * 2, [1.0] * 2).with_particle_count(64 * world).with_tol(1e-3)
+          .with_iter_max(400).with_seed(9).with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx))
+    got = ps.solve([0.9, -0.9])
+    oo = O.Pso(O.SPHERE, [-1.0] * 2, [1.0] * 2, particle_count=64 * world, tol=1e-3, iter_max=400, mode=O.SYNCHRONOUS, seed=9)
+    want = oo.solve([0.9, -0.9])
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (got, want)
+    assert ps.last_report.iters_run == oo.iters(), (ps.last_report.iters_run, oo.iters())
+    assert ps.last_report.world == world and ps.last_report.stalled == (1 if oo.iters() < 400 else 0)
+
+    # ---- CrossEntropy: distributed radix select + elite moments ---------------------------------------------------
+    n, N, k, iters = 7, 20011, 199, 5
+    x0, s0 = np.full(n, 3.0), np.full(n, 2.0)
+    ce = (E.CrossEntropy.new(E.Objective.ROSENBROCK).with_sample_size(N).with_importance_selection_size(k)
+          .with_iter_max(iters + 1).with_std_dev(s0).with_mean_divisor(E.MeanDivisor.ELITE_COUNT).with_seed(11)
+          .with_tol(0.0).with_context(ctx))
+    crun = ce.start(x0)
+    oc = O.Ce(O.ROSENBROCK, x0, sample_size=N, elite_count=k, iter_max=iters + 1, std_dev=s0,
+              mean_divisor=O.DIV_ELITE_COUNT, seed=11, tol=0.0)
+    for t in range(iters):
+        crun.step(1)
+        assert oc.step() == 0
+        mu, sg, it, act = crun.state()
+        omu, osg = oc.state()
+        np.testing.assert_allclose(mu, omu, rtol=1e-12, atol=5e-12, err_msg=f"CE mu pass {t}")
+        np.testing.assert_allclose(sg, osg, rtol=1e-12, atol=5e-12, err_msg=f"CE sigma pass {t}")
+        same_everywhere(mu, "CE mu")
+        el = crun.elites()
+        t_el = torch.zeros(k, dtype=torch.int64, device="cuda") - 1
+        t_el[:el.size] = torch.from_numpy(el).cuda()
+        gathered = [torch.empty_like(t_el) for _ in range(world)]
+        dist.all_gather(gathered, t_el)
+        allel = np.concatenate([g.cpu().numpy() for g in gathered])
+        allel = np.sort(allel[allel >= 0])
+        assert allel.tolist() == np.sort(oc.elites()).tolist(), f"CE elite set pass {t}"
+    crun.close()
+
+    dist.barrier()
+    if rank == 0:
+        print(f"multigpu_check OK on {world} GPUs")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -282,3 +282,37 @@ def test_full_size_c2_properties(ctx):
         rp, rg = O.pso_step_draws(1729, 3, int(j), n)
         vv = 0.5 * v0s[j] + 1.0 * rp * (pb0s[j] - x0s[j]) + 1.0 * rg * (g_before - x0s[j])
         assert_bit_equal(v1[j], vv); assert_bit_equal(x1[j], x0s[j] + vv)
+
+
+def test_virtual_ranks_stall_exit_matches_oracle(ctx):
+    """Multi-rank stall: once the stall test fires, further passes (step + exchange + apply) change nothing."""
+    n, N, world = 2, 128, 2
+    lower, upper, x0 = [-1.0] * n, [1.0] * n, np.array([0.9, -0.9])
+    base = lambda: (E.ParticleSwarm.new(E.Objective.SPHERE, lower, upper).with_particle_count(N).with_tol(1e-3)
+                    .with_iter_max(400).with_seed(9).with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx))
+    o = O.Pso(O.SPHERE, lower, upper, particle_count=N, tol=1e-3, iter_max=400, mode=O.SYNCHRONOUS, seed=9)
+    want = o.solve(x0)
+    assert o.iters() < 400, "the case must stall"
+    ranks = [base().with_virtual_rank(r, world).start() for r in range(world)]
+
+    def gather():
+        recs = np.stack([r.get_record() for r in ranks])
+        for r in ranks:
+            r.set_records(recs)
+
+    for ph in (0, 1):
+        for r in ranks:
+            r.init_local(x0, ph)
+        gather()
+    for r in ranks:
+        r.init_apply()
+    for _ in range(o.iters() + 25):  # 25 passes beyond the stall
+        for r in ranks:
+            r.step_local()
+        gather()
+        for r in ranks:
+            r.step_apply()
+    for r in ranks:
+        g, c, it, stalled, _ = r.gbest()
+        assert it == o.iters() and stalled
+        assert_bit_equal(g, want)
