@@ -1,0 +1,199 @@
+// eqsolver_b200.hpp -- header-only C++ mirror of eqsolver::global_optimisers over the C ABI (eqsolver_b200.h).
+//
+// Same builder surface as the Rust reference (AzeezDa/eqsolver v0.4.1):
+//   ParticleSwarm::create(objective, lower, upper)   ~ ParticleSwarm::new(f, lower, upper) -> SolverResult<Self>
+//                                                       (particle_swarm.rs:119-153)
+//   .with_*(..)                                      ~ :179-333 (setters returning &mut Self)
+//   .solve(x0) -> SolverResult<Vector>               ~ :356-431
+//   CrossEntropy(objective).with_*(..).solve(x0)     ~ cross_entropy.rs:75-85, 108-223, 245-306
+// The closure `f` is an Objective ID (device functors are compiled ahead of time).  Link with -leqsolver_b200.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <utility>
+#include <variant>
+#include <vector>
+
+#include "eqsolver_b200.h"
+
+namespace eqsolver {
+
+constexpr double DEFAULT_TOL = 1e-6;      // lib.rs:13
+constexpr int64_t DEFAULT_ITERMAX = 50;   // lib.rs:16
+
+enum class Objective : int32_t { Sphere = 0, Rosenbrock, Rastrigin, Ackley, ThreeCircles, Heavy, User };
+
+// SolverError, lib.rs:19-44
+struct SolverError {
+    enum Kind { MaxIterReached = 1, NotANumber, IncorrectInput, BadJacobian, TypeConversionError, ExternalError } kind;
+    std::string message;
+};
+
+template <class T> class SolverResult {
+public:
+    SolverResult(T v) : v_(std::move(v)) {}
+    SolverResult(SolverError e) : v_(std::move(e)) {}
+    bool is_ok() const { return v_.index() == 0; }
+    const T &unwrap() const { return std::get<0>(v_); }
+    const SolverError &unwrap_err() const { return std::get<1>(v_); }
+
+private:
+    std::variant<T, SolverError> v_;
+};
+
+using Vector = std::vector<double>;
+
+// one GPU: stream, device arena, communicator
+class Context {
+public:
+    static SolverResult<std::shared_ptr<Context>> create(int device = 0)
+    {
+        eqs_ctx *raw = nullptr;
+        const int st = eqs_ctx_create(device, &raw);
+        if (st != EQS_OK) return SolverError{static_cast<SolverError::Kind>(st), eqs_last_error(nullptr)};
+        return std::shared_ptr<Context>(new Context(raw));
+    }
+    ~Context() { eqs_ctx_destroy(raw_); }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    eqs_ctx *raw() const { return raw_; }
+    SolverError error(int st) const { return SolverError{static_cast<SolverError::Kind>(st), eqs_last_error(raw_)}; }
+
+private:
+    explicit Context(eqs_ctx *raw) : raw_(raw) {}
+    eqs_ctx *raw_;
+};
+
+namespace global_optimisers {
+
+enum class PsoMode : int32_t { SequentialExact = EQS_PSO_SEQUENTIAL_EXACT, Synchronous = EQS_PSO_SYNCHRONOUS };
+enum class MeanDivisor : int32_t { ReferenceTen = EQS_CE_DIV_REFERENCE_TEN, EliteCount = EQS_CE_DIV_ELITE_COUNT };
+
+class ParticleSwarm {
+public:
+    // ParticleSwarm::new: Err(ExternalError) when a bounds pair is not lower <= upper (particle_swarm.rs:124-139)
+    static SolverResult<ParticleSwarm> create(Objective objective, Vector lower_bounds, Vector upper_bounds)
+    {
+        ParticleSwarm s(objective, std::move(lower_bounds), std::move(upper_bounds));
+        if (s.lower_.size() != s.upper_.size())
+            return SolverError{SolverError::IncorrectInput, "bounds differ in length"};
+        const eqs_pso_params p = s.params();
+        const int st = eqs_pso_validate(&p);
+        if (st == EQS_ERR_EXTERNAL)
+            return SolverError{SolverError::ExternalError, "low > high (or equal if exclusive) in uniform distribution"};
+        if (st != EQS_OK) return SolverError{static_cast<SolverError::Kind>(st), "dimension, objective or bounds rejected"};
+        return s;
+    }
+
+    ParticleSwarm &with_inertia_weight(double v) { w_ = v; return *this; }
+    ParticleSwarm &with_cognitive_coefficient(double v) { c1_ = v; return *this; }
+    ParticleSwarm &with_social_coefficient(double v) { c2_ = v; return *this; }
+    ParticleSwarm &with_tol(double v) { tol_ = v; return *this; }
+    ParticleSwarm &with_particle_count(int64_t v) { particle_count_ = v; return *this; }
+    ParticleSwarm &with_iter_max(int64_t v) { iter_max_ = v; return *this; }
+    ParticleSwarm &with_seed(uint64_t v) { seed_ = v; return *this; }
+    ParticleSwarm &with_mode(PsoMode m) { mode_ = m; return *this; }
+    ParticleSwarm &with_context(std::shared_ptr<Context> c) { ctx_ = std::move(c); return *this; }
+
+    // solve(x0), particle_swarm.rs:356-431: the global best position
+    SolverResult<Vector> solve(const Vector &x0, eqs_report *report = nullptr) const
+    {
+        if (x0.size() != lower_.size()) return SolverError{SolverError::IncorrectInput, "x0 and bounds differ in length"};
+        std::shared_ptr<Context> ctx = ctx_;
+        if (!ctx) {
+            auto made = Context::create(0);
+            if (!made.is_ok()) return made.unwrap_err();
+            ctx = made.unwrap();
+        }
+        Vector out(x0.size());
+        const eqs_pso_params p = params();
+        const int st = eqs_pso_solve(ctx->raw(), &p, x0.data(), out.data(), report);
+        if (st != EQS_OK) return ctx->error(st);
+        return out;
+    }
+
+private:
+    ParticleSwarm(Objective o, Vector lo, Vector hi) : objective_(o), lower_(std::move(lo)), upper_(std::move(hi)) {}
+    eqs_pso_params params() const
+    {
+        eqs_pso_params p{};
+        p.n = static_cast<int32_t>(lower_.size());
+        p.objective_id = static_cast<int32_t>(objective_);
+        p.mode = static_cast<int32_t>(mode_);
+        p.exchange = EQS_EXCHANGE_AUTO;
+        p.particle_count = particle_count_;
+        p.iter_max = iter_max_;
+        p.tol = tol_;
+        p.w = w_;
+        p.c1 = c1_;
+        p.c2 = c2_;
+        p.lower = lower_.data();
+        p.upper = upper_.data();
+        p.seed = seed_;
+        p.virtual_world = 1;
+        return p;
+    }
+    Objective objective_;
+    Vector lower_, upper_;
+    double w_ = 0.5, c1_ = 1.0, c2_ = 1.0, tol_ = DEFAULT_TOL; // particle_swarm.rs:8-10
+    int64_t iter_max_ = DEFAULT_ITERMAX, particle_count_ = 100; // :11
+    uint64_t seed_ = 0;
+    PsoMode mode_ = PsoMode::SequentialExact;
+    std::shared_ptr<Context> ctx_;
+};
+
+class CrossEntropy {
+public:
+    explicit CrossEntropy(Objective objective) : objective_(objective) {} // CrossEntropy::new, cross_entropy.rs:75-85
+
+    CrossEntropy &with_tol(double v) { tol_ = v; return *this; }
+    CrossEntropy &with_iter_max(int64_t v) { iter_max_ = v; return *this; }
+    CrossEntropy &with_sample_size(int64_t v) { sample_size_ = v; return *this; }
+    CrossEntropy &with_importance_selection_size(int64_t v) { elite_ = v; return *this; }
+    CrossEntropy &with_std_dev(Vector v) { std_dev_ = std::move(v); return *this; }
+    CrossEntropy &with_seed(uint64_t v) { seed_ = v; return *this; }
+    CrossEntropy &with_mean_divisor(MeanDivisor m) { divisor_ = m; return *this; }
+    CrossEntropy &with_context(std::shared_ptr<Context> c) { ctx_ = std::move(c); return *this; }
+
+    // solve(x0), cross_entropy.rs:245-306: the final mean; the reference's panics become NotANumber
+    SolverResult<Vector> solve(const Vector &x0, eqs_report *report = nullptr) const
+    {
+        if (!std_dev_.empty() && std_dev_.size() != x0.size())
+            return SolverError{SolverError::IncorrectInput, "std_dev and x0 differ in length"};
+        std::shared_ptr<Context> ctx = ctx_;
+        if (!ctx) {
+            auto made = Context::create(0);
+            if (!made.is_ok()) return made.unwrap_err();
+            ctx = made.unwrap();
+        }
+        eqs_ce_params p{};
+        p.n = static_cast<int32_t>(x0.size());
+        p.objective_id = static_cast<int32_t>(objective_);
+        p.mean_divisor = static_cast<int32_t>(divisor_);
+        p.exchange = EQS_EXCHANGE_AUTO;
+        p.sample_size = sample_size_;
+        p.elite_count = elite_;
+        p.iter_max = iter_max_;
+        p.tol = tol_;
+        p.std_dev = std_dev_.empty() ? nullptr : std_dev_.data();
+        p.seed = seed_;
+        p.virtual_world = 1;
+        Vector out(x0.size());
+        const int st = eqs_ce_solve(ctx->raw(), &p, x0.data(), out.data(), report);
+        if (st != EQS_OK) return ctx->error(st);
+        return out;
+    }
+
+private:
+    Objective objective_;
+    Vector std_dev_;
+    double tol_ = DEFAULT_TOL;
+    int64_t iter_max_ = DEFAULT_ITERMAX, sample_size_ = 100, elite_ = 10; // cross_entropy.rs:8-9
+    uint64_t seed_ = 0;
+    MeanDivisor divisor_ = MeanDivisor::ReferenceTen;
+    std::shared_ptr<Context> ctx_;
+};
+
+} // namespace global_optimisers
+} // namespace eqsolver

@@ -1,0 +1,77 @@
+// C++ twin of the reference's doctests / examples for this path, through include/eqsolver_b200.hpp.
+//   test_builder host   : host-only behaviour (no GPU needed)
+//   test_builder gpu    : solves on cuda:0 (examples/global_optimisation.rs, global_optimiser_as_solver.rs style)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "eqsolver_b200.hpp"
+
+using namespace eqsolver;
+using namespace eqsolver::global_optimisers;
+
+#define CHECK(cond)                                                                                              \
+    do {                                                                                                         \
+        if (!(cond)) {                                                                                           \
+            std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond);                                          \
+            return 1;                                                                                            \
+        }                                                                                                        \
+    } while (0)
+
+static int host_tests()
+{
+    // ParticleSwarm::new -> Err(ExternalError) for lower > upper (particle_swarm.rs:124-139)
+    auto bad = ParticleSwarm::create(Objective::Rastrigin, {1.0, 0.0}, {0.0, 1.0});
+    CHECK(!bad.is_ok() && bad.unwrap_err().kind == SolverError::ExternalError);
+    auto bad2 = ParticleSwarm::create(Objective::ThreeCircles, {0.0, 0.0, 0.0}, {1.0, 1.0, 1.0});
+    CHECK(!bad2.is_ok() && bad2.unwrap_err().kind == SolverError::IncorrectInput);
+    auto ok = ParticleSwarm::create(Objective::Rastrigin, Vector(4, -100.0), Vector(4, 100.0));
+    CHECK(ok.is_ok());
+    CHECK(eqs_abi_version() == EQS_ABI_VERSION);
+    int64_t first = -1, local = -1;
+    CHECK(eqs_shard_range(10, 3, 2, &first, &local) == EQS_OK && first == 7 && local == 3);
+    std::printf("host tests ok\n");
+    return 0;
+}
+
+static int gpu_tests()
+{
+    auto made = Context::create(0);
+    CHECK(made.is_ok());
+    auto ctx = made.unwrap();
+    // doctest of particle_swarm.rs:337-355: 4-D Rastrigin, guess 80, bounds +-100 -- runs and returns Ok
+    {
+        auto ps = ParticleSwarm::create(Objective::Rastrigin, Vector(4, -100.0), Vector(4, 100.0)).unwrap();
+        auto r = ps.with_context(ctx).solve(Vector(4, 80.0));
+        CHECK(r.is_ok() && r.unwrap().size() == 4);
+    }
+    // examples/global_optimiser_as_solver.rs:44-49 with the optimum of tests/multi.rs:70
+    {
+        auto ps = ParticleSwarm::create(Objective::ThreeCircles, {1.0, 1.0}, {7.0, 7.0}).unwrap();
+        eqs_report rep{};
+        auto r = ps.with_context(ctx).with_particle_count(500).with_iter_max(300).with_tol(0.0).with_seed(2).solve({4.5, 2.5}, &rep);
+        CHECK(r.is_ok());
+        CHECK(std::fabs(r.unwrap()[0] - 4.217265312839526) < 1e-6 && std::fabs(r.unwrap()[1] - 2.317879970005811) < 1e-6);
+        CHECK(rep.iters_run == 300 && rep.evals == 1 + 500 * 301);
+    }
+    // CrossEntropy on the same problem
+    {
+        auto r = CrossEntropy(Objective::ThreeCircles).with_context(ctx).with_sample_size(2000).with_importance_selection_size(50)
+                     .with_iter_max(100).with_mean_divisor(MeanDivisor::EliteCount).with_seed(2).solve({4.5, 2.5});
+        CHECK(r.is_ok());
+        CHECK(std::fabs(r.unwrap()[0] - 4.217265312839526) < 1e-5 && std::fabs(r.unwrap()[1] - 2.317879970005811) < 1e-5);
+    }
+    // where the reference panics: non-finite standard deviation -> NotANumber
+    {
+        auto r = CrossEntropy(Objective::Sphere).with_context(ctx).with_std_dev({1.0, INFINITY}).solve({0.0, 0.0});
+        CHECK(!r.is_ok() && r.unwrap_err().kind == SolverError::NotANumber);
+    }
+    std::printf("gpu tests ok\n");
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc > 1 && !std::strcmp(argv[1], "gpu")) return gpu_tests();
+    return host_tests();
+}

@@ -1,0 +1,118 @@
+"""CPU, world_size 2 over gloo: the N>1 host logic -- rendezvous / unique-id shipping (eqsolver_b200/distributed.py),
+shard ranges, and the exchange PROTOCOL of DESIGN.md §5 run on the sharded oracle with the records moved by
+torch.distributed.  The CUDA kernels implement the same protocol (tests/test_pso_gpu.py virtual ranks,
+tests/multigpu_check.py over NCCL)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+WORLD = 2
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, results):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+    import eqsolver_b200 as E
+    from eqsolver_b200 import distributed as ED
+    from oracle import oracle as O
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert ED.env_rank_world() == (rank, world, rank)
+        # 1. the 128-byte communicator id travels from rank 0 to everyone
+        uid = ED.exchange_unique_id(rank, make_id=lambda: bytes(range(128)))
+        assert uid == bytes(range(128))
+
+        def allgather(vec):
+            t = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64).copy())
+            out = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(out, t)
+            return np.stack([o.numpy() for o in out])
+
+        # 2. ParticleSwarm (synchronous) sharded over the ranks == unsharded, bit for bit, ring included
+        n, N, iters = 5, 203, 7
+        lo, hi, x0 = [-5.0] * n, [10.0] * n, [3.0] * n
+        first, local = E.shard_range(N, world, rank)
+        ref = O.Pso(O.ROSENBROCK, lo, hi, particle_count=N, mode=O.SYNCHRONOUS, seed=3, tol=0.0)
+        ref.init(x0)
+        sh = O.Pso(O.ROSENBROCK, lo, hi, particle_count=N, mode=O.SYNCHRONOUS, seed=3, tol=0.0, first_index=first,
+                   local_count=local)
+        recs = allgather(sh.init_local(x0))                       # exchange 1: arg-min records
+        f0 = O.objective(O.ROSENBROCK, x0)
+        seed_cost = min([f0] + [recs[q, 0] for q in range(rank) if recs[q, 1] >= 0])
+        pushes, tail = sh.init_ring_local(seed_cost)
+        ring_recs = allgather(np.concatenate([[pushes], tail]))   # exchange 2: ordered ring pushes
+        sh.init_apply(recs, ring_recs[:, 0].astype(np.int64), ring_recs[:, 1:])
+        for t in range(iters + 1):
+            assert np.array_equal(sh.gbest().view(np.uint64), ref.gbest().view(np.uint64)), f"gbest pass {t}"
+            assert np.array_equal(sh.ring()[0].view(np.uint64), ref.ring()[0].view(np.uint64)) and sh.ring()[1] == ref.ring()[1]
+            assert np.array_equal(sh.state()[0].view(np.uint64), ref.state()[0][first:first + local].view(np.uint64))
+            if t < iters:
+                stalled, rec = sh.step_local()
+                sh.step_apply(allgather(rec))
+                ref.step()
+
+        # 3. CrossEntropy: global k-th cost + lowest-index ties, moment sums per rank then in rank order
+        n, N, k = 4, 301, 23
+        x0c, s0 = np.full(n, 3.0), np.full(n, 2.0)
+        first, local = E.shard_range(N, world, rank)
+        refc = O.Ce(O.ROSENBROCK, x0c, sample_size=N, elite_count=k, iter_max=6, std_dev=s0,
+                    mean_divisor=O.DIV_ELITE_COUNT, seed=5, tol=0.0)
+        shc = O.Ce(O.ROSENBROCK, x0c, sample_size=N, elite_count=k, iter_max=6, std_dev=s0,
+                   mean_divisor=O.DIV_ELITE_COUNT, seed=5, tol=0.0, first_index=first, local_count=local)
+        maxloc = max(E.shard_range(N, world, r)[1] for r in range(world))
+        for t in range(4):
+            refc.step()
+            shc.sample_local()
+            c = np.full(maxloc, np.inf); c[:local] = shc.costs()
+            allc = allgather(c)
+            flat = np.concatenate([allc[r, :E.shard_range(N, world, r)[1]] for r in range(world)])
+            T = np.sort(flat)[k - 1]
+            quota = k - int((flat < T).sum())
+            ties_before = sum(int((allc[r, :E.shard_range(N, world, r)[1]] == T).sum()) for r in range(rank))
+            mine = int((shc.costs() == T).sum())
+            take = min(max(quota - ties_before, 0), mine)
+            sums = allgather(shc.elite_sum_local(T, take))
+            mu_new = np.zeros(n)
+            for r in range(world):
+                mu_new = mu_new + sums[r]
+            mu_new = mu_new / k
+            sq = allgather(shc.elite_sqsum_local(mu_new))
+            tot = np.zeros(n)
+            for r in range(world):
+                tot = tot + sq[r]
+            shc.apply(mu_new, np.sqrt(tot / (k - 1)))
+            mu, sg = shc.state(); rmu, rsg = refc.state()
+            np.testing.assert_allclose(mu, rmu, rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(sg, rsg, rtol=1e-12, atol=1e-12)
+        results[rank] = "ok"
+    except Exception as e:  # surface the failure to the parent
+        import traceback
+        results[rank] = "FAIL: " + "".join(traceback.format_exception(e))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    results = mgr.dict()
+    port = _free_port()
+    mp.spawn(_worker, args=(WORLD, port, results), nprocs=WORLD, join=True)
+    assert dict(results) == {0: "ok", 1: "ok"}, "\n".join(str(v) for v in results.values())
