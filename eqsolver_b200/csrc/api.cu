@@ -121,6 +121,8 @@ int eqs_ctx_destroy(eqs_ctx *ctx)
     if (!ctx) return EQS_OK;
     cudaSetDevice(ctx->c.device);
     comm_destroy(&ctx->c);
+    if (ctx->c.stream) cudaStreamSynchronize(ctx->c.stream);
+    ctx->c.drop_caches();
     if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;
     return EQS_OK;

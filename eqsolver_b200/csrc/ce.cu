@@ -429,9 +429,10 @@ public:
     ~CeSolver()
     {
         if (ctx_ && ctx_->device >= 0) cudaSetDevice(ctx_->device);
-        if (arena_) cudaFree(arena_);
+        if (arena_ || h_ctrl_) cudaStreamSynchronize(ctx_->stream);
+        ctx_->release_arena(arena_, arena_bytes_);
         if (replay_buf_) cudaFree(replay_buf_);
-        if (h_ctrl_) cudaFreeHost(h_ctrl_);
+        ctx_->release_pinned(h_ctrl_);
         if (ev0_) cudaEventDestroy(ev0_);
         if (ev1_) cudaEventDestroy(ev1_);
     }
@@ -504,7 +505,7 @@ public:
         const size_t o_ex = plan((size_t)n * D.kld * 8);
         const size_t o_part = plan((size_t)n * D.nchunks * 8);
         const size_t o_ctrl = plan(sizeof(CeCtrl));
-        EQS_CUDA(ctx_, cudaMalloc(&arena_, off));
+        EQS_CUDA(ctx_, ctx_->acquire_arena(off, &arena_, &arena_bytes_));
         char *base = (char *)arena_;
         D.mu = (double *)(base + o_mu);
         D.sigma = (double *)(base + o_sig);
@@ -523,7 +524,8 @@ public:
         D.Ex = (double *)(base + o_ex);
         D.part = (double *)(base + o_part);
         D.ctrl = (CeCtrl *)(base + o_ctrl);
-        EQS_CUDA(ctx_, cudaMallocHost(&h_ctrl_, sizeof(CeCtrl)));
+        static_assert(sizeof(CeCtrl) <= Ctx::kPinnedBytes, "pinned block too small");
+        EQS_CUDA(ctx_, ctx_->acquire_pinned((void **)&h_ctrl_));
         memset(h_ctrl_, 0, sizeof(CeCtrl));
         h_ctrl_->iter = 1; // :253
         h_ctrl_->sigma_inf = smax;
@@ -750,6 +752,7 @@ public:
     eqs_ce_params p_{};
     CeDev d_{};
     void *arena_ = nullptr;
+    size_t arena_bytes_ = 0;
     double *replay_buf_ = nullptr;
     size_t replay_cap_ = 0;
     CeCtrl *h_ctrl_ = nullptr;

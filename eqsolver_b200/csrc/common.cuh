@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -28,6 +29,64 @@ struct Ctx {
     Comm *comm = nullptr;
     int rank = 0, world = 1;
     mutable std::string error;
+
+    // Allocation caches.  The reference's benchmark shape (benchmarks/multi.rs:70-100) constructs a solver and runs a
+    // whole default solve (100 particles, 50 passes) per sample: cudaMalloc / cudaMallocHost / cudaFree would cost
+    // 100x the kernels.  One device arena and a few pinned control blocks are therefore kept per context.
+    void *cached_arena = nullptr;
+    size_t cached_arena_bytes = 0;
+    std::vector<void *> pinned_free; // blocks of kPinnedBytes
+    std::mutex cache_mutex;          // solvers sharing a context may be created / destroyed from different threads
+    static constexpr size_t kPinnedBytes = 1024;
+
+    cudaError_t acquire_arena(size_t bytes, void **out, size_t *got)
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        if (cached_arena && cached_arena_bytes >= bytes) {
+            *out = cached_arena;
+            *got = cached_arena_bytes;
+            cached_arena = nullptr;
+            cached_arena_bytes = 0;
+            return cudaSuccess;
+        }
+        *got = bytes;
+        return cudaMalloc(out, bytes);
+    }
+    void release_arena(void *p, size_t bytes)
+    {
+        if (!p) return;
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        if (bytes > cached_arena_bytes) {
+            if (cached_arena) cudaFree(cached_arena);
+            cached_arena = p;
+            cached_arena_bytes = bytes;
+        } else {
+            cudaFree(p);
+        }
+    }
+    cudaError_t acquire_pinned(void **out)
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        if (!pinned_free.empty()) {
+            *out = pinned_free.back();
+            pinned_free.pop_back();
+            return cudaSuccess;
+        }
+        return cudaMallocHost(out, kPinnedBytes);
+    }
+    void release_pinned(void *p)
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        if (p) pinned_free.push_back(p);
+    }
+    void drop_caches()
+    {
+        if (cached_arena) cudaFree(cached_arena);
+        cached_arena = nullptr;
+        cached_arena_bytes = 0;
+        for (void *p : pinned_free) cudaFreeHost(p);
+        pinned_free.clear();
+    }
 
     int fail(int status, const char *fmt, ...) const
     {

@@ -218,17 +218,21 @@ __device__ __forceinline__ bool grid_minloc_last_block(const PsoDev &P, MinLoc m
 
 // this rank's exchange record: (cost, global index, the particle's position).  src == nullptr: the buffer that
 // holds x is named by the particle's role bit.
+// CG: the data was written by OTHER CTAs of this grid -> read it from L2 (__ldcg); false inside the single-CTA kernel.
+template <bool CG = true>
 __device__ __forceinline__ void write_record(const PsoDev &P, double cost, long long gidx, const double *src)
 {
     const bool none = gidx == kNoIndex || gidx < 0;
     const long long li = none ? 0 : gidx - P.first;
-    if (!src && !none) src = (__ldcg(P.pbflag + li) & 2u) ? P.pb : P.x;
+    if (!src && !none) src = ((CG ? __ldcg(P.pbflag + li) : P.pbflag[li]) & 2u) ? P.pb : P.x;
     if (threadIdx.x == 0) {
         P.send[REC_COST] = cost;
         P.send[REC_IDX] = none ? -1.0 : (double)gidx;
     }
-    for (int d = threadIdx.x; d < P.n; d += blockDim.x)
-        P.send[REC_X + d] = none ? 0.0 : __ldcg(src + goff(P, d >> 2, li) + (d & 3));
+    for (int d = threadIdx.x; d < P.n; d += blockDim.x) {
+        const double *p = src + goff(P, d >> 2, li) + (d & 3);
+        P.send[REC_X + d] = none ? 0.0 : (CG ? __ldcg(p) : *p);
+    }
 }
 
 // lowest cost, then lowest global index, over the ranks' records; -1 when every record is empty
@@ -578,6 +582,104 @@ __global__ void __launch_bounds__(PSO_BLOCK) pso_commit_kernel(const PsoDev P, l
     }
 }
 
+// K8: small populations (nloc <= PSO_SMALL_MAX, one rank).  The reference's own shapes -- 100 particles x 50 passes
+// (benchmarks/multi.rs:70-84), 1000 x 1000 (BASELINE config 1) -- fit on ONE SM, and a pass is a few microseconds, so
+// kernel launches and host round trips are the whole cost.  One CTA therefore runs `iters` passes back to back: same
+// device functions, same buffers, __syncthreads instead of kernel boundaries.  Sequential-exact mode runs its
+// speculate-and-repair rounds (see pso_spec_kernel) inside the kernel too.
+template <class Obj, bool SEQ>
+__global__ void __launch_bounds__(PSO_SMALL_BLOCK) pso_small_kernel(const PsoDev P, long long iters)
+{
+    extern __shared__ double sG[];
+    __shared__ MinLoc s_red[32];
+    __shared__ MinLoc s_win;
+    __shared__ long long s_start;
+    PsoCtrl *c = P.ctrl;
+    const int tid = threadIdx.x;
+    for (long long pass = 0; pass < iters; ++pass) {
+        if (c->stalled) break; // :395-397 (uniform: written before the last barrier of the previous pass)
+        const uint32_t t = (uint32_t)c->iter;
+        load_gbest(P, sG);
+        if constexpr (!SEQ) {
+            MinLoc best{dinf(), kNoIndex};
+            for (long long li = tid; li < P.nloc; li += blockDim.x) {
+                const unsigned f = P.pbflag[li];
+                const bool stale = f & 1u, role = f & 2u;
+                const double pbc_old = P.pbc[li];
+                double *xb = role ? P.pb : P.x, *ob = role ? P.x : P.pb;
+                const double cost = pso_move<Obj, false>(P, t, li, sG, xb, P.v, ob, stale ? ob : xb, P.v, !stale);
+                pso_finish_particle(P, li, cost, pbc_old, f, best);
+            }
+            const MinLoc b = block_minloc(best, s_red);
+            if (tid == 0) s_win = b;
+            __threadfence_block();
+            __syncthreads();
+            write_record<false>(P, s_win.c, s_win.i, nullptr);
+            __threadfence_block();
+            __syncthreads();
+            pso_apply_step(P, P.send, 1);
+            __syncthreads();
+        } else {
+            const int nq = (P.n + 3) >> 2;
+            if (tid == 0) s_start = 0;
+            __syncthreads();
+            for (;;) {
+                const long long start = s_start;
+                const double Gc = c->Gc;
+                MinLoc first{0.0, kNoIndex};
+                for (long long li = tid; li < P.nloc; li += blockDim.x) {
+                    const long long gi = P.first + li;
+                    if (gi < start) continue;
+                    const double cost = pso_move<Obj, false>(P, t, li, sG, P.x, P.v, P.pb, P.x2, P.v2, true);
+                    P.cost[li] = cost;
+                    if (cost < Gc && gi < first.i) first.i = gi; // :417,:420
+                }
+                const MinLoc b = block_minloc(first, s_red);
+                if (tid == 0) s_win = b;
+                __threadfence_block();
+                __syncthreads();
+                const long long istar = s_win.i;
+                const bool found = istar != kNoIndex;
+                const long long end = found ? istar : P.ntotal - 1;
+                for (long long li = tid; li < P.nloc; li += blockDim.x) { // commit [start, end], :413-419
+                    const long long gi = P.first + li;
+                    if (gi < start || gi > end) continue;
+                    const double cost = P.cost[li];
+                    const bool imp = cost < P.pbc[li];
+                    if (imp) P.pbc[li] = cost;
+                    for (int q = 0; q < nq; ++q) {
+                        const long long off = goff(P, q, li);
+                        const D4 xv = ld256(P.x2 + off);
+                        st256(P.x + off, xv);
+                        st256(P.v + off, ld256(P.v2 + off));
+                        if (imp) st256(P.pb + off, xv);
+                    }
+                }
+                if (found) { // :420-425
+                    const long long wl = istar - P.first;
+                    for (int d = tid; d < P.n; d += blockDim.x) P.G[d] = P.x2[goff(P, d >> 2, wl) + (d & 3)];
+                    if (tid == 0) {
+                        ring_push(c, c->Gc);
+                        c->Gc = P.cost[wl];
+                        c->improvements += 1;
+                        s_start = istar + 1;
+                    }
+                }
+                const bool done = !found || istar == P.ntotal - 1;
+                __threadfence_block();
+                __syncthreads();
+                if (done) break;
+                load_gbest(P, sG);
+            }
+            if (tid == 0) {
+                c->iter += 1;
+                c->stalled = stall_test(c, P.tol);
+            }
+            __syncthreads();
+        }
+    }
+}
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 template <class K> int persistent_grid(Ctx *ctx, K kernel, int block, size_t smem, long long units_per_block_iter,
@@ -599,9 +701,10 @@ template <class K> int persistent_grid(Ctx *ctx, K kernel, int block, size_t sme
 PsoSolver::~PsoSolver()
 {
     if (ctx_ && ctx_->device >= 0) cudaSetDevice(ctx_->device);
-    if (arena_) cudaFree(arena_);
+    if (arena_ || h_ctrl_) cudaStreamSynchronize(ctx_->stream); // nothing of this solver may still be in flight
+    ctx_->release_arena(arena_, arena_bytes_);
     if (replay_buf_) cudaFree(replay_buf_);
-    if (h_ctrl_) cudaFreeHost(h_ctrl_);
+    ctx_->release_pinned(h_ctrl_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
 }
@@ -695,7 +798,7 @@ int PsoSolver::create(const eqs_pso_params *p)
     const size_t o_send = plan(R);
     const bool own_recv = !(world == 1 && !manual_);
     const size_t o_recv = own_recv ? plan(R * world) : o_send;
-    EQS_CUDA(ctx_, cudaMalloc(&arena_, off));
+    EQS_CUDA(ctx_, ctx_->acquire_arena(off, &arena_, &arena_bytes_));
     char *base = (char *)arena_;
     D.x = (double *)(base + o_x);
     D.v = (double *)(base + o_v);
@@ -720,7 +823,8 @@ int PsoSolver::create(const eqs_pso_params *p)
     EQS_CUDA(ctx_, cudaMemcpyAsync(hi, upper_.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx_->stream));
     EQS_CUDA(ctx_, cudaMemsetAsync(D.ctrl, 0, sizeof(PsoCtrl), ctx_->stream));
     EQS_CUDA(ctx_, cudaMemsetAsync(D.send, 0, R, ctx_->stream));
-    EQS_CUDA(ctx_, cudaMallocHost(&h_ctrl_, sizeof(PsoCtrl)));
+    static_assert(sizeof(PsoCtrl) <= Ctx::kPinnedBytes, "pinned block too small");
+    EQS_CUDA(ctx_, ctx_->acquire_pinned((void **)&h_ctrl_));
     memset(h_ctrl_, 0, sizeof(PsoCtrl));
     EQS_CUDA(ctx_, cudaEventCreate(&ev0_));
     EQS_CUDA(ctx_, cudaEventCreate(&ev1_));
@@ -925,7 +1029,30 @@ int PsoSolver::step(int64_t iters, const double *replay_step)
     grid_step_ = 0;
     const int64_t l0 = launches_;
     EQS_CUDA(ctx_, cudaEventRecord(ev0_, ctx_->stream));
-    for (int64_t it = 0; it < iters; ++it) {
+    const bool small = d_.world == 1 && !manual_ && !replay_step && d_.nloc >= 1 && d_.nloc <= PSO_SMALL_MAX &&
+                       !getenv("EQS_PSO_NO_SMALL");
+    if (small && iters > 0) {
+        // K8: the whole batch of passes in one single-CTA launch
+        const size_t smem = (size_t)((d_.n + 3) / 4) * 4 * sizeof(double);
+        const int block = (int)std::min<long long>(PSO_SMALL_BLOCK, (d_.nloc + 31) / 32 * 32);
+        const bool seq = p_.mode == EQS_PSO_SEQUENTIAL_EXACT;
+        int rc = EQS_OK;
+        dispatch_objective(p_.objective_id, [&]<class Obj>() {
+            auto run = [&](auto kernel) {
+                if (smem > 48 * 1024 &&
+                    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                    rc = ctx_->fail(EQS_ERR_EXTERNAL, "cannot reserve %zu bytes of shared memory", smem);
+                if (rc != EQS_OK) return;
+                kernel<<<1, block, smem, ctx_->stream>>>(d_, (long long)iters);
+                launches_++;
+            };
+            if (seq) run(pso_small_kernel<Obj, true>);
+            else run(pso_small_kernel<Obj, false>);
+        });
+        EQS_TRY(rc);
+        EQS_CUDA(ctx_, cudaGetLastError());
+    }
+    for (int64_t it = 0; it < (small ? 0 : iters); ++it) {
         if (p_.mode == EQS_PSO_SYNCHRONOUS) {
             EQS_TRY(launch_step());
             EQS_TRY(exchange());

@@ -48,6 +48,8 @@ struct PsoDev {
 
 constexpr int PSO_BLOCK = 256;
 constexpr int PSO_GROUP = 256; // particles per init tile = granularity of the ring scan
+constexpr int PSO_SMALL_BLOCK = 512; // K8: threads of the single-CTA whole-solve kernel
+constexpr int PSO_SMALL_MAX = 2048;  // K8: largest population it takes (4 particles per thread)
 
 int validate_pso_params(const eqs_pso_params *p, std::string *why);
 
@@ -75,6 +77,7 @@ public:
     PsoDev d_{};
     std::vector<double> lower_, upper_;
     void *arena_ = nullptr;
+    size_t arena_bytes_ = 0;
     double *replay_buf_ = nullptr;
     size_t replay_cap_ = 0;
     PsoCtrl *h_ctrl_ = nullptr; // pinned mirror

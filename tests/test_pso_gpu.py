@@ -316,3 +316,34 @@ def test_virtual_ranks_stall_exit_matches_oracle(ctx):
         g, c, it, stalled, _ = r.gbest()
         assert it == o.iters() and stalled
         assert_bit_equal(g, want)
+
+
+@pytest.mark.parametrize("mode", [E.PsoMode.SYNCHRONOUS, E.PsoMode.SEQUENTIAL_EXACT])
+def test_small_kernel_equals_multi_launch_path(ctx, mode, monkeypatch):
+    """K8 (one CTA, all passes in one launch) and the multi-launch path produce identical states."""
+    n, N, iters = 6, 700, 9
+    lower, upper, x0 = [-5.0] * n, [10.0] * n, np.full(n, 3.0)
+    mk = lambda: (E.ParticleSwarm.new(E.Objective.ROSENBROCK, lower, upper).with_particle_count(N).with_tol(0.0)
+                  .with_seed(21).with_mode(mode).with_context(ctx))
+    small = mk().start(x0)
+    small.step(iters)
+    monkeypatch.setenv("EQS_PSO_NO_SMALL", "1")
+    big = mk().start(x0)
+    big.step(iters)
+    monkeypatch.delenv("EQS_PSO_NO_SMALL")
+    for a, b in zip(small.state(), big.state()):
+        assert_bit_equal(a, b)
+    assert_bit_equal(small.gbest()[0], big.gbest()[0]); assert small.gbest()[1:4] == big.gbest()[1:4]
+    assert_bit_equal(small.ring()[0], big.ring()[0])
+    assert small.last_step_ms()[1] == 1 and big.last_step_ms()[1] >= iters   # launches
+
+
+def test_sequential_host_driven_path_large_population(ctx):
+    """Populations above the single-CTA limit run speculate-and-repair with host-driven rounds."""
+    n, N, iters = 5, 2600, 4
+    g, o = make(E.Objective.ROSENBROCK, n, N, E.PsoMode.SEQUENTIAL_EXACT, seed=33)
+    x0 = np.full(n, 3.0)
+    run = g.with_context(ctx).start(x0); o.init(x0)
+    for t in range(iters):
+        run.step(1); o.step()
+        compare_state(run, o, True, f"pass {t}")
