@@ -130,6 +130,17 @@ void comm_destroy(Ctx *ctx);
 int comm_allgather_f64(Ctx *ctx, const double *send, double *recv, int64_t count_per_rank, cudaStream_t s);
 int comm_allreduce_sum_u64(Ctx *ctx, unsigned long long *buf, int64_t count, cudaStream_t s);
 
+// ---- peer-memory mailboxes (NVLink / NVSwitch, CUDA IPC): the fused exchange of the ParticleSwarm step kernel ----
+// One mailbox per rank, mapped into every peer: [seq u64 | flags [2][world] u64 | records [2][world][MB_REC_CAP] f64].
+// A rank's last CTA stores its record into slot (exchange number & 1, my rank) of EVERY mailbox, release-stores the
+// exchange number into the matching flag, and acquire-waits until its own mailbox holds that number from every peer.
+constexpr size_t MB_SEQ = 0, MB_TIMEOUT = 8, MB_FLAG = 256, MB_REC = 4096;
+constexpr int MB_MAX_WORLD = 16;
+constexpr long long MB_REC_CAP = REC_X + 12800 + 2; // doubles per record slot (n <= 12800)
+constexpr size_t MB_BYTES = MB_REC + 2ull * MB_MAX_WORLD * MB_REC_CAP * sizeof(double);
+// returns false when the context has no peer mailboxes (single rank, IPC unavailable, or EQS_P2P=0)
+bool comm_p2p(Ctx *ctx, char **mailbox, char *const **d_peers);
+
 // ---- device helpers ------------------------------------------------------------------------------------
 __device__ __forceinline__ double sanitize_cost(double c) { return (c != c) ? __longlong_as_double(0x7ff0000000000000LL) : c; }
 

@@ -278,6 +278,57 @@ __device__ __forceinline__ void pso_apply_step(const PsoDev &P, const double *re
         for (int d = threadIdx.x; d < P.n; d += blockDim.x) P.G[d] = recs[s_winner * R + REC_X + d];
 }
 
+// ---- the exchange fused into the step kernel (one kernel per pass at any world size) ---------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Called by the LAST CTA of the step kernel once P.send holds this rank's record.  Stores the record into every
+// rank's mailbox over NVLink, publishes the exchange number, waits for every peer's number, then applies the same
+// gbest selection as pso_step_apply_kernel.  No deadlock: a CTA only waits for kernels running on OTHER GPUs.
+__device__ __forceinline__ void pso_p2p_exchange_apply(const PsoDev &P)
+{
+    const int tid = threadIdx.x;
+    const long long R = record_doubles(P.n);
+    unsigned long long *seq_p = reinterpret_cast<unsigned long long *>(P.mailbox + MB_SEQ);
+    const unsigned long long s = *seq_p + 1; // every rank runs the same sequence of exchanges
+    const int slot = (int)(s & 1ull);
+    __syncthreads(); // P.send complete, everyone has read seq
+    for (int r = 0; r < P.world; ++r) {
+        double *dst = reinterpret_cast<double *>(P.peers[r] + MB_REC) + ((size_t)slot * P.world + P.rank) * MB_REC_CAP;
+        for (long long i = tid; i < R; i += blockDim.x) dst[i] = P.send[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < P.world) {
+        unsigned long long *theirs = reinterpret_cast<unsigned long long *>(P.peers[tid] + MB_FLAG) + slot * P.world + P.rank;
+        st_release_sys(theirs, s);
+        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(P.mailbox + MB_FLAG) + slot * P.world + tid;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(mine) != s) {
+            if (clock64() - t0 > 6000000000LL) { // ~3 s: a peer died; fail instead of hanging the GPU
+                P.ctrl->p2p_timeout = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const double *src = reinterpret_cast<const double *>(P.mailbox + MB_REC) + (size_t)slot * P.world * MB_REC_CAP;
+    for (int r = 0; r < P.world; ++r)
+        for (long long i = tid; i < R; i += blockDim.x) P.recv[r * R + i] = __ldcv(src + r * MB_REC_CAP + i);
+    if (tid == 0) *seq_p = s;
+    __threadfence_block();
+    __syncthreads();
+    pso_apply_step(P, P.recv, P.world);
+}
+
 __device__ __forceinline__ void load_gbest(const PsoDev &P, double *sG)
 {
     const int npad = (P.n + 3) & ~3;
@@ -301,6 +352,7 @@ template <class Obj> __global__ void pso_x0_kernel(const PsoDev P)
     c->stalled = 0;
     c->pass_done = 0;
     c->block_counter = 0;
+    c->p2p_timeout = 0;
 }
 
 // :361-389 without the (order-dependent) gbest bookkeeping, which pso_ring_scan_kernel reconstructs
@@ -483,9 +535,11 @@ __global__ void __launch_bounds__(PSO_BLOCK, EQS_PSO_MINB) pso_step_kernel(const
     MinLoc win;
     if (grid_minloc_last_block(P, best, s_red, win)) {
         write_record(P, win.c, win.i, nullptr);
-        if (inline_apply) {
+        if (inline_apply == 1) {
             __syncthreads();
             pso_apply_step(P, P.send, 1);
+        } else if (inline_apply == 2) {
+            pso_p2p_exchange_apply(P);
         }
     }
 }
@@ -819,6 +873,18 @@ int PsoSolver::create(const eqs_pso_params *p)
     D.send = (double *)(base + o_send);
     D.recv = (double *)(base + o_recv);
     max_grid_ = max_grid;
+    D.mailbox = nullptr;
+    D.peers = nullptr;
+    fused_exchange_ = false;
+    if (!manual_ && world > 1 && D.sync && record_doubles(n) <= MB_REC_CAP) {
+        char *mb = nullptr;
+        char *const *peers = nullptr;
+        if (comm_p2p(ctx_, &mb, &peers)) {
+            D.mailbox = mb;
+            D.peers = peers;
+            fused_exchange_ = true;
+        }
+    }
     EQS_CUDA(ctx_, cudaMemcpyAsync(lo, lower_.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx_->stream));
     EQS_CUDA(ctx_, cudaMemcpyAsync(hi, upper_.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx_->stream));
     EQS_CUDA(ctx_, cudaMemsetAsync(D.ctrl, 0, sizeof(PsoCtrl), ctx_->stream));
@@ -847,6 +913,7 @@ int PsoSolver::upload_replay(const double *host, int64_t doubles)
 int PsoSolver::exchange()
 {
     if (manual_ || d_.world == 1) return EQS_OK;
+    if (fused_exchange_ && in_sync_step_) return EQS_OK; // done by the step kernel itself over peer memory
     return comm_allgather_f64(ctx_, d_.send, d_.recv, record_doubles(d_.n), ctx_->stream);
 }
 
@@ -854,6 +921,7 @@ int PsoSolver::fetch_ctrl()
 {
     EQS_CUDA(ctx_, cudaMemcpyAsync(h_ctrl_, d_.ctrl, sizeof(PsoCtrl), cudaMemcpyDeviceToHost, ctx_->stream));
     EQS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+    if (h_ctrl_->p2p_timeout) return ctx_->fail(EQS_ERR_EXTERNAL, "a peer rank did not reach the gbest exchange (peer-memory mailbox timed out)");
     return EQS_OK;
 }
 
@@ -928,7 +996,7 @@ int PsoSolver::init(const double *x0)
 int PsoSolver::launch_step()
 {
     const bool replay = d_.replay != nullptr;
-    const int inline_apply = (d_.world == 1 && !manual_) ? 1 : 0;
+    const int inline_apply = (d_.world == 1 && !manual_) ? 1 : (fused_exchange_ ? 2 : 0);
     int rc = EQS_OK;
     const size_t smem = (size_t)((d_.n + 3) / 4) * 4 * sizeof(double);
     dispatch_objective(p_.objective_id, [&]<class Obj>() {
@@ -950,7 +1018,7 @@ int PsoSolver::launch_step()
 
 int PsoSolver::launch_step_apply()
 {
-    if (d_.world == 1 && !manual_) return EQS_OK; // applied by the last block of the step kernel
+    if ((d_.world == 1 && !manual_) || fused_exchange_) return EQS_OK; // applied by the last block of the step kernel
     pso_step_apply_kernel<<<1, 128, 0, ctx_->stream>>>(d_);
     launches_++;
     EQS_CUDA(ctx_, cudaGetLastError());
@@ -1054,9 +1122,11 @@ int PsoSolver::step(int64_t iters, const double *replay_step)
     }
     for (int64_t it = 0; it < (small ? 0 : iters); ++it) {
         if (p_.mode == EQS_PSO_SYNCHRONOUS) {
+            in_sync_step_ = true;
             EQS_TRY(launch_step());
             EQS_TRY(exchange());
             EQS_TRY(launch_step_apply());
+            in_sync_step_ = false;
         } else {
             EQS_TRY(sequential_pass());
         }

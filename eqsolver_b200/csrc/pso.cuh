@@ -20,6 +20,7 @@ struct PsoCtrl {
     long long improvements;         // gbest improvements so far
     long long spec_first;           // sequential mode: first improving global index of the last round, -1 = none
     int stalled;                    // result of stalled_too_long (:433-441) for the NEXT pass
+    int p2p_timeout;                // a peer never showed up in the fused exchange
     int pass_done;                  // sequential mode: the speculate-and-repair pass is complete
     unsigned int block_counter;     // last-block-done ticket
     int nan_seen;
@@ -36,6 +37,8 @@ struct PsoDev {
     long long *part_idx;
     double *group_min;              // [ceil(nloc/GROUP)] per-tile minimum of the init costs
     double *send, *recv;            // exchange records: [R], [world][R]
+    char *mailbox;                  // peer-memory exchange (common.cuh): this rank's mailbox, or nullptr
+    char *const *peers;             // device table of every rank's mailbox as mapped on this GPU
     const double *lower, *upper;    // [n]
     const double *replay;           // device copy of the caller's draw stream, or nullptr
     long long ld, nloc, first, ntotal;
@@ -87,6 +90,8 @@ public:
     int64_t last_launches_ = 0;
     float last_ms_ = 0.f;
     bool manual_ = false;
+    bool fused_exchange_ = false; // synchronous step exchanges over peer memory inside the step kernel
+    bool in_sync_step_ = false;
     int max_grid_ = 0;
 
 private:
