@@ -60,6 +60,7 @@ SYMBOLS = {
     "eqs_objective_eval": (C.c_int, [_vp, C.c_int32, dp, C.c_int32, C.c_int64, dp]),
     "eqs_philox_blocks": (C.c_int, [_vp, _u32p, _u32p, C.c_int64, _u32p]),
     "eqs_draws": (C.c_int, [_vp, C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, dp, dp]),
+    "eqs_device_cos": (C.c_int, [_vp, dp, C.c_int64, dp]),
     "eqs_measure_fp64": (C.c_int, [_vp, dp]),
     "eqs_measure_copy": (C.c_int, [_vp, C.c_int64, dp]),
     "eqs_pso_validate": (C.c_int, [C.POINTER(PsoParams)]),

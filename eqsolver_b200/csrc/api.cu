@@ -38,6 +38,12 @@ __global__ void philox_blocks_kernel(const uint32_t *ctr, PhiloxKey key, long lo
     out[4 * i + 3] = r.w;
 }
 
+__global__ void cos_kernel(const double *x, long long count, double *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = eqs_cos(x[i]);
+}
+
 __global__ void draws_kernel(int kind, PhiloxKey key, uint32_t t, long long first, long long count, int n, double *a, double *b)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,6 +236,25 @@ int eqs_draws(eqs_ctx *ctx, int32_t kind, uint64_t seed, int64_t t, int64_t firs
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(da);
     cudaFree(db);
+    if (e != cudaSuccess) return c->fail(EQS_ERR_EXTERNAL, "CUDA error: %s", cudaGetErrorString(e));
+    return EQS_OK;
+}
+
+int eqs_device_cos(eqs_ctx *ctx, const double *x, int64_t count, double *out)
+{
+    if (!ctx || !x || !out || count < 0) return EQS_ERR_INCORRECT_INPUT;
+    Ctx *c = &ctx->c;
+    if (count == 0) return EQS_OK;
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    double *dx = nullptr, *dout = nullptr;
+    EQS_CUDA(c, cudaMalloc(&dx, sizeof(double) * count));
+    EQS_CUDA(c, cudaMalloc(&dout, sizeof(double) * count));
+    EQS_CUDA(c, cudaMemcpyAsync(dx, x, sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));
+    cos_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(dx, count, dout);
+    cudaError_t e = cudaMemcpyAsync(out, dout, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dx);
+    cudaFree(dout);
     if (e != cudaSuccess) return c->fail(EQS_ERR_EXTERNAL, "CUDA error: %s", cudaGetErrorString(e));
     return EQS_OK;
 }

@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/eqsolver_b200.h"
+#include "devmath.cuh"
 
 namespace eqs {
 
@@ -62,7 +63,7 @@ template <> struct Objective<EQS_OBJ_ROSENBROCK> {
 template <> struct Objective<EQS_OBJ_RASTRIGIN> {
     static constexpr bool streaming = true;
     __device__ __forceinline__ static void begin(ObjAcc &s, int n) { s.a = 10.0 * (double)n; }
-    __device__ __forceinline__ static void feed(ObjAcc &s, double x, int) { s.a += x * x - 10.0 * cos(kTwoPi * x); }
+    __device__ __forceinline__ static void feed(ObjAcc &s, double x, int) { s.a += x * x - 10.0 * eqs_cos(kTwoPi * x); }
     __device__ __forceinline__ static double end(const ObjAcc &s, int) { return s.a; }
 };
 
@@ -72,7 +73,7 @@ template <> struct Objective<EQS_OBJ_ACKLEY> {
     __device__ __forceinline__ static void feed(ObjAcc &s, double x, int)
     {
         s.a += x * x;
-        s.b += cos(kTwoPi * x);
+        s.b += eqs_cos(kTwoPi * x);
     }
     __device__ __forceinline__ static double end(const ObjAcc &s, int n)
     {

@@ -10,6 +10,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "devmath.cuh"
 
 namespace eqs {
 
@@ -72,9 +73,9 @@ __device__ __forceinline__ void normal_pair(uint4 w, double &z0, double &z1)
 {
     const double u1 = u01(w.x, w.y);
     const double u2 = u01(w.z, w.w);
-    const double r = sqrt(-2.0 * log(1.0 - u1));
+    const double r = sqrt(-2.0 * log_unit(1.0 - u1));
     double s, c;
-    sincospi(2.0 * u2, &s, &c);
+    sincospi_unit(2.0 * u2, s, c);
     z0 = r * c;
     z1 = r * s;
 }

@@ -169,6 +169,12 @@ class Context:
         self.check(_ffi.lib().eqs_draws(self._h, kind, C.c_uint64(seed), t, first, count, n, _p(a), _p(b)))
         return (a,) if kind == 2 else (a, b)
 
+    def device_cos(self, x) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        out = np.empty_like(x)
+        self.check(_ffi.lib().eqs_device_cos(self._h, _p(x), x.size, _p(out)))
+        return out
+
     def measure_fp64(self) -> float:
         v = C.c_double(0)
         self.check(_ffi.lib().eqs_measure_fp64(self._h, C.byref(v)))

@@ -148,6 +148,8 @@ int eqs_philox_blocks(eqs_ctx *ctx, const uint32_t *ctr /*[count][4]*/, const ui
  * 2: CE standard normals (a = z, b unused).  a, b: [count][n] for global indices first..first+count-1. */
 int eqs_draws(eqs_ctx *ctx, int32_t kind, uint64_t seed, int64_t t, int64_t first, int64_t count, int32_t n,
               double *a, double *b);
+/* the device cosine used by the Rastrigin / Ackley functors (accuracy tests): out[i] = cos(x[i]) */
+int eqs_device_cos(eqs_ctx *ctx, const double *x, int64_t count, double *out);
 /* measured machine ceilings for the roofline: DFMA issue rate (TFLOP/s) and copy bandwidth (GB/s) */
 int eqs_measure_fp64(eqs_ctx *ctx, double *tflops);
 int eqs_measure_copy(eqs_ctx *ctx, int64_t bytes, double *gbps);

@@ -111,6 +111,7 @@ extern "C" {
     pub fn eqs_philox_blocks(ctx: *mut eqs_ctx, ctr: *const u32, key: *const u32, count: i64, out: *mut u32) -> c_int;
     pub fn eqs_draws(ctx: *mut eqs_ctx, kind: i32, seed: u64, t: i64, first: i64, count: i64, n: i32,
                      a: *mut c_double, b: *mut c_double) -> c_int;
+    pub fn eqs_device_cos(ctx: *mut eqs_ctx, x: *const c_double, count: i64, out: *mut c_double) -> c_int;
     pub fn eqs_measure_fp64(ctx: *mut eqs_ctx, tflops: *mut c_double) -> c_int;
     pub fn eqs_measure_copy(ctx: *mut eqs_ctx, bytes: i64, gbps: *mut c_double) -> c_int;
 

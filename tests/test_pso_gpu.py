@@ -347,3 +347,20 @@ def test_sequential_host_driven_path_large_population(ctx):
     for t in range(iters):
         run.step(1); o.step()
         compare_state(run, o, True, f"pass {t}")
+
+
+def test_device_cos_accuracy(ctx):
+    """eqs_cos (objectives.cuh) against glibc: <= 2 ulp on the arguments the path produces, exact special cases."""
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([rng.uniform(-700, 700, 400000), rng.uniform(-8e5, 8e5, 200000), rng.uniform(-1e-3, 1e-3, 50000),
+                         2 * np.pi * rng.uniform(-5.12, 5.12, 200000), np.array([0.0, -0.0, np.pi / 2, np.pi, 1e6, -3e7, 1e15, 1e300])])
+    got = ctx.device_cos(xs)
+    want = np.cos(xs)
+    ulp = np.spacing(np.abs(want))
+    err = np.abs(got - want) / np.maximum(ulp, np.finfo(float).tiny)
+    # near the zeros of cos an ulp of the RESULT is tiny; bound the error by 2 ulp of the result or 1 ulp of 1.0
+    ok = (err <= 2.0) | (np.abs(got - want) <= 2.3e-16)
+    assert ok.all(), (xs[~ok][:5], got[~ok][:5], want[~ok][:5], err.max())
+    sp = ctx.device_cos(np.array([np.inf, -np.inf, np.nan]))
+    assert np.isnan(sp).all()
+    assert ctx.device_cos(np.array([0.0]))[0] == 1.0
