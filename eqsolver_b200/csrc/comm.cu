@@ -219,13 +219,4 @@ int comm_allgather_f64(Ctx *ctx, const double *send, double *recv, int64_t count
     return EQS_OK;
 }
 
-int comm_allreduce_sum_u64(Ctx *ctx, unsigned long long *buf, int64_t count, cudaStream_t s)
-{
-    if (!ctx->comm) return ctx->fail(EQS_ERR_EXTERNAL, "world > 1 but the context has no communicator");
-    NcclApi &a = nccl();
-    const ncclResult_t r = a.AllReduce(buf, buf, (size_t)count, ncclUint64, ncclSum, ctx->comm->comm, s);
-    if (r != 0) return ctx->fail(EQS_ERR_EXTERNAL, "ncclAllReduce: %s", a.GetErrorString(r));
-    return EQS_OK;
-}
-
 } // namespace eqs

@@ -128,7 +128,6 @@ int comm_unique_id(void *out128, std::string &err);
 int comm_init(Ctx *ctx, int rank, int world, const void *id128);
 void comm_destroy(Ctx *ctx);
 int comm_allgather_f64(Ctx *ctx, const double *send, double *recv, int64_t count_per_rank, cudaStream_t s);
-int comm_allreduce_sum_u64(Ctx *ctx, unsigned long long *buf, int64_t count, cudaStream_t s);
 
 // ---- peer-memory mailboxes (NVLink / NVSwitch, CUDA IPC): the fused exchange of the ParticleSwarm step kernel ----
 // One mailbox per rank, mapped into every peer: [seq u64 | flags [2][world] u64 | records [2][world][MB_REC_CAP] f64].
