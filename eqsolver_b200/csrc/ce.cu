@@ -27,6 +27,7 @@ constexpr int CE_PASSES = 6;
 constexpr int CE_TILE = 1024;  // samples per block in flag / compact (256 threads x 4, blocked)
 constexpr int CE_CHUNK = 4096; // elites per block in the row sums
 constexpr int CE_PHASES = 9;
+constexpr int CE_SMALL_MAX = 1024; // samples the single-CTA whole-solve kernel takes (one per thread)
 
 __host__ __device__ inline int pass_shift(int pass) { return pass < 5 ? 53 - 11 * pass : 0; }
 __host__ __device__ inline int pass_width(int pass) { return pass < 5 ? 11 : 9; }
@@ -399,6 +400,110 @@ __global__ void __launch_bounds__(1024) ce_sigma_apply_kernel(const CeDev P)
     }
 }
 
+// Small sample sizes (N <= CE_SMALL_MAX on one rank): the reference's default shape is 100 samples x 49 passes
+// (cross_entropy.rs:8-9, benchmarks/multi.rs:86-100), where a 23-launch pass is nothing but launch latency.  One CTA
+// runs `iters` passes: one thread per sample, costs ranked by counting in shared memory (rank = samples with a lower
+// cost, ties by lower index -- the order of a stable sort, :276), the k elites regenerated into shared memory IN RANK
+// ORDER, and mu / sigma summed by one thread per dimension in exactly the reference's order (:281-297), so with
+// replayed normals and a transcendental-free objective the result is bit-identical to the reference's arithmetic.
+template <class Obj, bool REPLAY> __global__ void __launch_bounds__(1024) ce_small_kernel(const CeDev P, long long iters)
+{
+    extern __shared__ double s_dyn[];
+    __shared__ int s_nan;
+    __shared__ double s_red[32];
+    __shared__ int s_bad[32];
+    CeCtrl *c = P.ctrl;
+    const int tid = threadIdx.x, n = P.n, N = (int)P.nloc, k = (int)P.k;
+    double *smu = s_dyn, *ssig = s_dyn + n, *scost = s_dyn + 2 * n, *sEx = s_dyn + 2 * n + N; // [n] [n] [N] [k][n]
+    for (long long pass = 0; pass < iters; ++pass) {
+        if (!c->active) break; // :255 (uniform: written before the last barrier of the previous pass)
+        const uint32_t t = (uint32_t)(c->iter - 1);
+        if (tid == 0) s_nan = 0;
+        load_mu_sigma(P, smu, ssig);
+        if (tid < N) { // :264-274
+            const long long gi = P.first + tid;
+            double cost;
+            if constexpr (Obj::streaming) {
+                ObjAcc acc;
+                Obj::begin(acc, n);
+                ce_sample_coords<REPLAY>(P, t, gi, smu, ssig, [&](double x, int d) { Obj::feed(acc, x, d); });
+                cost = Obj::end(acc, n);
+            } else {
+                ce_sample_coords<REPLAY>(P, t, gi, smu, ssig, [&](double x, int d) { P.xs[(long long)d * P.ld + tid] = x; });
+                cost = Obj::eval(StridedView{P.xs + tid, P.ld}, n);
+            }
+            cost = cost + 0.0;
+            scost[tid] = cost;
+            P.cost[tid] = cost;
+            if (cost != cost) s_nan = 1;
+        }
+        __syncthreads();
+        if (s_nan) { // the reference panics in the sort (:276)
+            if (tid == 0) {
+                c->nan_cost = 1;
+                c->active = 0;
+            }
+            break;
+        }
+        if (tid < N) { // rank by counting = position after a stable sort by cost
+            const double mine = scost[tid];
+            int rank = 0;
+            for (int j = 0; j < N; ++j) {
+                const double o = scost[j];
+                rank += (o < mine) || (o == mine && j < tid);
+            }
+            if (rank < k) {
+                P.elite_idx[rank] = tid;
+                double *row = sEx + (size_t)rank * n;
+                ce_sample_coords<REPLAY>(P, t, P.first + tid, smu, ssig, [&](double x, int d) { row[d] = x; });
+            }
+        }
+        __syncthreads();
+        double mx = 0.0;
+        int bad = 0;
+        for (int d = tid; d < n; d += blockDim.x) { // :281-297, elites in cost order like the reference
+            double mu = 0.0;
+            for (int j = 0; j < k; ++j) mu += sEx[(size_t)j * n + d];
+            mu /= (P.divisor_mode == EQS_CE_DIV_REFERENCE_TEN ? 10.0 : (double)k);
+            double sg = 0.0;
+            for (int j = 0; j < k; ++j) {
+                const double e = sEx[(size_t)j * n + d] - mu;
+                sg += e * e;
+            }
+            sg = sqrt(sg / (double)(k - 1));
+            P.mu[d] = mu;
+            P.sigma[d] = sg;
+            const double a = fabs(sg);
+            if (a > mx) mx = a;
+            if (!isfinite(sg) || !isfinite(mu)) bad = 1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double w = __shfl_down_sync(0xffffffffu, mx, o);
+            mx = w > mx ? w : mx;
+            bad |= __shfl_down_sync(0xffffffffu, bad, o);
+        }
+        if ((tid & 31) == 0) {
+            s_red[tid >> 5] = mx;
+            s_bad[tid >> 5] = bad;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+                mx = s_red[w] > mx ? s_red[w] : mx;
+                bad |= s_bad[w];
+            }
+            c->sigma_inf = mx;
+            c->n_elite_local = k;
+            c->iter += 1; // :302
+            if (bad) c->bad_sigma = 1;
+            c->active = (mx > P.tol) && (c->iter < P.iter_max) && !c->bad_sigma;
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
+}
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 } // namespace
@@ -679,7 +784,33 @@ public:
         EQS_TRY(prepare_replay(replay, iters));
         const int64_t l0 = launches_;
         EQS_CUDA(ctx_, cudaEventRecord(ev0_, ctx_->stream));
-        for (int64_t it = 0; it < iters; ++it)
+        // small sample sizes on one rank: all passes of the batch in ONE single-CTA launch (ce_small_kernel)
+        const size_t small_smem = ((size_t)2 * d_.n + d_.nloc + (size_t)d_.k * d_.n) * sizeof(double);
+        const bool small = d_.world == 1 && d_.nloc >= 2 && d_.nloc <= CE_SMALL_MAX && small_smem <= 160 * 1024 &&
+                           !getenv("EQS_CE_NO_SMALL");
+        if (small && iters > 0) {
+            const bool rp = d_.replay != nullptr;
+            const int block = (int)std::min<long long>(1024, (std::max<long long>(d_.nloc, std::min(d_.n, 256)) + 31) / 32 * 32);
+            int rc = EQS_OK;
+            dispatch_objective(p_.objective_id, [&]<class Obj>() {
+                auto run = [&](auto kernel) {
+                    if (small_smem > 48 * 1024 &&
+                        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem) != cudaSuccess)
+                        rc = ctx_->fail(EQS_ERR_EXTERNAL, "cannot reserve %zu bytes of shared memory", small_smem);
+                    if (rc != EQS_OK) return;
+                    kernel<<<1, block, small_smem, ctx_->stream>>>(d_, (long long)iters);
+                    launches_++;
+                };
+                if (rp) run(ce_small_kernel<Obj, true>);
+                else run(ce_small_kernel<Obj, false>);
+            });
+            EQS_TRY(rc);
+            EQS_CUDA(ctx_, cudaGetLastError());
+            small_path_ = true;
+        } else {
+            small_path_ = false;
+        }
+        for (int64_t it = 0; it < (small ? 0 : iters); ++it)
             for (int ph = 0; ph < CE_PHASES; ++ph) {
                 EQS_TRY(launch_phase(ph));
                 EQS_TRY(exchange(phase_exchange(ph)));
@@ -760,6 +891,7 @@ public:
     int sample_grid_ = 0;
     int64_t launches_ = 0, last_launches_ = 0;
     bool manual_ = false, bad_sigma0_ = false;
+    bool small_path_ = false; // the last step() ran ce_small_kernel (elite list is in cost order)
 };
 
 } // namespace eqs
@@ -846,6 +978,7 @@ int eqs_ce_read_elites(eqs_ce *h, int64_t *idx, int64_t *count)
         EQS_CUDA(c, cudaMemcpyAsync(idx, s.d_.elite_idx, ne * 8, cudaMemcpyDeviceToHost, c->stream));
         EQS_CUDA(c, cudaStreamSynchronize(c->stream));
         for (long long j = 0; j < ne; ++j) idx[j] += s.d_.first; // local -> global
+        if (s.small_path_) std::sort(idx, idx + ne);              // the contract is ascending sample order
     }
     return EQS_OK;
 }

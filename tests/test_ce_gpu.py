@@ -91,7 +91,13 @@ def test_ties_at_kth_cost_lowest_index_first(ctx):
     run = ce.start(np.zeros(n))
     run.step(1, z1)
     assert run.elites().tolist() == list(range(k))
-    assert np.all(run.state()[1] == 0.0)          # identical elites: sigma = 0 exactly
+    # identical elites: sigma is what the reference's sequential sums make of it (not exactly 0: 11 x / 11 != x)
+    o1 = O.Ce(O.SPHERE, np.zeros(n), sample_size=N, elite_count=k, iter_max=3, mean_divisor=O.DIV_ELITE_COUNT,
+              replay_normals=z1)
+    o1.step()
+    assert np.array_equal(run.state()[0].view(np.uint64), o1.state()[0].view(np.uint64))
+    assert np.array_equal(run.state()[1].view(np.uint64), o1.state()[1].view(np.uint64))
+    assert run.state()[1].max() < 1e-15
 
 
 def test_reference_default_solve(ctx):
@@ -212,3 +218,44 @@ def test_full_size_c3_properties(ctx):
     run.step(3)
     mu2, sg2, it2, _ = run.state()
     assert it2 == 4 and sg2.max() < sg.max() < 2.0                  # the distribution keeps contracting
+
+
+def test_small_kernel_replay_is_bit_exact(ctx):
+    """The single-CTA kernel sums the elites in cost order like the reference: with replayed normals and a
+    transcendental-free objective mu and sigma are bit-identical to the oracle (and to the golden fixtures)."""
+    from conftest import assert_bit_equal
+    for g in golden("ce_golden.json"):
+        z = np.array([[[from_bits(b) for b in row] for row in it] for it in g["normals"]])
+        ce = (E.CrossEntropy.new(g["objective"]).with_sample_size(g["N"]).with_importance_selection_size(g["k"])
+              .with_iter_max(g["iter_max"]).with_std_dev(g["sigma0"]).with_context(ctx)
+              .with_mean_divisor(E.MeanDivisor.REFERENCE_TEN if g["divisor_ten"] else E.MeanDivisor.ELITE_COUNT))
+        run = ce.start(g["x0"])
+        for t, tr in enumerate(g["trace"]):
+            run.step(1, z[t:t + 1])
+            mu, sg, it, _ = run.state()
+            assert_bit_equal(mu, [from_bits(b) for b in tr["mu"]], f"mu pass {t}")
+            assert_bit_equal(sg, [from_bits(b) for b in tr["sigma"]], f"sigma pass {t}")
+            assert run.last_step_ms()[1] == 1      # one launch
+
+
+@pytest.mark.parametrize("objective", [E.Objective.ROSENBROCK, E.Objective.RASTRIGIN, E.Objective.HEAVY])
+def test_small_kernel_equals_phase_pipeline(ctx, objective, monkeypatch):
+    n, N, k, iters = 9, 777, 31, 6
+    x0, s0 = np.full(n, 3.0), np.full(n, 2.0)
+    mk = lambda: (E.CrossEntropy.new(objective).with_sample_size(N).with_importance_selection_size(k)
+                  .with_iter_max(iters + 1).with_std_dev(s0).with_mean_divisor(E.MeanDivisor.ELITE_COUNT).with_seed(5)
+                  .with_tol(0.0).with_context(ctx))
+    small = mk().start(x0)
+    monkeypatch.setenv("EQS_CE_NO_SMALL", "1")
+    big = mk().start(x0)
+    for t in range(iters):
+        monkeypatch.delenv("EQS_CE_NO_SMALL", raising=False)
+        small.step(1)
+        monkeypatch.setenv("EQS_CE_NO_SMALL", "1")
+        big.step(1)
+        assert small.elites().tolist() == big.elites().tolist()
+        np.testing.assert_allclose(small.costs(), big.costs(), rtol=1e-10)
+        close(small.state()[0], big.state()[0], 5.0, f"mu pass {t}")
+        close(small.state()[1], big.state()[1], 5.0, f"sigma pass {t}")
+        assert small.state()[2:] == big.state()[2:]
+    assert small.last_step_ms()[1] == 1 and big.last_step_ms()[1] > 10
