@@ -349,6 +349,53 @@ def test_sequential_host_driven_path_large_population(ctx):
         compare_state(run, o, True, f"pass {t}")
 
 
+def test_degenerate_inputs_match_oracle(ctx):
+    # NaN start: f(x0) = NaN, no `cost < NaN` is ever true (:376, :420) -> gbest stays x0, the ring is never pushed
+    n, N = 3, 500
+    for mode in (E.PsoMode.SYNCHRONOUS, E.PsoMode.SEQUENTIAL_EXACT):
+        g, o = make(E.Objective.SPHERE, n, N, mode, seed=4)
+        x0 = np.array([np.nan, 1.0, 2.0])
+        run = g.with_context(ctx).start(x0); o.init(x0)
+        run.step(3); [o.step() for _ in range(3)]
+        gb, gc, it, _, _ = run.gbest()
+        assert np.isnan(gc) and np.isnan(o.gbest_cost()) and it == o.iters() == 3
+        assert np.array_equal(gb.view(np.uint64), o.gbest().view(np.uint64))
+        assert_bit_equal(run.state()[0], o.state()[0]); assert_bit_equal(run.ring()[0], o.ring()[0])
+    # lower == upper is legal for Uniform::new_inclusive: every particle starts on the same point with zero velocity
+    lower = upper = [1.5, -2.0]
+    ps = (E.ParticleSwarm.new(E.Objective.ROSENBROCK, lower, upper).with_particle_count(200).with_tol(0.0).with_seed(1)
+          .with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx))
+    o = O.Pso(O.ROSENBROCK, lower, upper, particle_count=200, tol=0.0, mode=O.SYNCHRONOUS, seed=1)
+    x0 = np.array([0.0, 0.0])
+    run = ps.start(x0); o.init(x0)
+    run.step(4); [o.step() for _ in range(4)]
+    compare_state(run, o, True, "degenerate bounds")
+    # zero coefficients: particles keep half their velocity each pass
+    ps = (E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * 2, [1.0] * 2).with_particle_count(100).with_tol(0.0)
+          .with_cognitive_coefficient(0.0).with_social_coefficient(0.0).with_inertia_weight(0.25).with_seed(2)
+          .with_mode(E.PsoMode.SEQUENTIAL_EXACT).with_context(ctx))
+    o = O.Pso(O.SPHERE, [-1.0] * 2, [1.0] * 2, particle_count=100, tol=0.0, c1=0.0, c2=0.0, w=0.25, seed=2)
+    run = ps.start(x0); o.init(x0)
+    run.step(3); [o.step() for _ in range(3)]
+    compare_state(run, o, True, "zero coefficients")
+
+
+def test_large_dimension_and_limits(ctx):
+    for n, N, mode in ((1000, 300, E.PsoMode.SYNCHRONOUS), (257, 3000, E.PsoMode.SYNCHRONOUS),
+                       (130, 260, E.PsoMode.SEQUENTIAL_EXACT)):
+        g, o = make(E.Objective.ROSENBROCK, n, N, mode, seed=n, lo=-2.0, hi=2.0)
+        x0 = np.full(n, 0.5)
+        run = g.with_context(ctx).start(x0); o.init(x0)
+        run.step(2); [o.step() for _ in range(2)]
+        compare_state(run, o, True, f"n={n}")
+    # the gbest tile lives in shared memory: n is capped
+    with pytest.raises(E.IncorrectInput):
+        E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * 13000, [1.0] * 13000).with_context(ctx).solve([0.0] * 13000)
+    ps = (E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * 12800, [1.0] * 12800).with_particle_count(64).with_iter_max(2)
+          .with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx))
+    assert ps.solve([0.5] * 12800).shape == (12800,)
+
+
 def test_device_cos_accuracy(ctx):
     """eqs_cos (objectives.cuh) against glibc: <= 2 ulp on the arguments the path produces, exact special cases."""
     rng = np.random.default_rng(7)
