@@ -37,6 +37,11 @@ class CeParams(C.Structure):
                 ("virtual_rank", C.c_int32), ("virtual_world", C.c_int32)]
 
 
+class McParams(C.Structure):
+    _fields_ = [("n", C.c_int32), ("integrand_id", C.c_int32), ("sample_count", C.c_int64),
+                ("from_", dp), ("to", dp), ("seed", C.c_uint64), ("replay_u", dp)]
+
+
 class Report(C.Structure):
     _fields_ = [("iters_run", C.c_int64), ("evals", C.c_int64), ("best_cost", C.c_double),
                 ("stalled", C.c_int32), ("world", C.c_int32), ("kernel_launches", C.c_int64),
@@ -96,6 +101,8 @@ SYMBOLS = {
     "eqs_ce_exchange_words": (C.c_int64, [_vp, C.c_int32]),
     "eqs_ce_get_exchange": (C.c_int, [_vp, C.c_int32, _vp]),
     "eqs_ce_set_exchange": (C.c_int, [_vp, C.c_int32, _vp]),
+    "eqs_mc_validate": (C.c_int, [C.POINTER(McParams)]),
+    "eqs_mc_integrate": (C.c_int, [_vp, C.POINTER(McParams), dp, dp, C.POINTER(Report)]),
 }
 
 _lib = None

@@ -20,7 +20,7 @@ OBJ_DIR = os.path.join(os.path.dirname(ROOT), "build")
 LIB_DIR = os.path.join(ROOT, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libeqsolver_b200.so")
 
-SOURCES = ["api.cu", "pso.cu", "ce.cu", "comm.cu"]
+SOURCES = ["api.cu", "pso.cu", "ce.cu", "mc.cu", "comm.cu"]
 # -fmad=false: rustc never contracts a*b+c, and replay parity with the CPU restatement is bit-level.
 NVCC_FLAGS = ["-std=c++20", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

@@ -181,7 +181,8 @@ int eqs_objective_eval(eqs_ctx *ctx, int32_t objective_id, const double *x, int3
 {
     if (!ctx || !x || !out || n <= 0 || count < 0) return EQS_ERR_INCORRECT_INPUT;
     Ctx *c = &ctx->c;
-    if (objective_id == EQS_OBJ_THREE_CIRCLES && n != 2) return c->fail(EQS_ERR_INCORRECT_INPUT, "three-circles objective needs n = 2");
+    if ((objective_id == EQS_OBJ_THREE_CIRCLES || objective_id == EQS_OBJ_SINCOS) && n != 2)
+        return c->fail(EQS_ERR_INCORRECT_INPUT, "this objective needs n = 2");
     if (count == 0) return EQS_OK;
     EQS_CUDA(c, cudaSetDevice(c->device));
     double *dx = nullptr, *dout = nullptr;

@@ -522,7 +522,8 @@ int validate_ce_params(const eqs_ce_params *p, std::string *why)
         return bad(EQS_ERR_INCORRECT_INPUT, "importance selection size must satisfy 2 <= k <= sample size");
     if (p->iter_max < 0) return bad(EQS_ERR_INCORRECT_INPUT, "negative iteration count");
     if (p->objective_id < 0 || p->objective_id >= EQS_OBJ_COUNT) return bad(EQS_ERR_INCORRECT_INPUT, "unknown objective id");
-    if (p->objective_id == EQS_OBJ_THREE_CIRCLES && p->n != 2) return bad(EQS_ERR_INCORRECT_INPUT, "three-circles objective needs n = 2");
+    if ((p->objective_id == EQS_OBJ_THREE_CIRCLES || p->objective_id == EQS_OBJ_SINCOS) && p->n != 2)
+        return bad(EQS_ERR_INCORRECT_INPUT, "this objective needs n = 2");
     if (p->mean_divisor != EQS_CE_DIV_REFERENCE_TEN && p->mean_divisor != EQS_CE_DIV_ELITE_COUNT)
         return bad(EQS_ERR_INCORRECT_INPUT, "unknown mean divisor mode");
     return EQS_OK;

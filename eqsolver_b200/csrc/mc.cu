@@ -1,0 +1,271 @@
+// mc.cu -- MonteCarlo integration over an orthotope on sm_100a.
+//
+// Replaces MonteCarlo::integrate_with_rng / integrate_with_sampler, reference src/integrators/monte_carlo.rs:143-212,
+// and MeanVariance::from_iterator_using_welford, src/lib.rs:172-202.  Same sample -> evaluate -> reduce shape as the
+// CrossEntropy sample kernel: draws (Philox stream 3, one block per dimension pair) and the integrand stay in
+// registers, nothing is read from HBM.  The reference's sequential Welford recurrence becomes per-thread Welford over a
+// grid-stride subsequence + Chan's pairwise merge (lanes, warps, CTAs, ranks, always in the same fixed order, so the result is
+// deterministic); it agrees with the sequential recurrence to rounding (tests: 1e-12 on the mean).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "objectives.cuh"
+#include "philox.cuh"
+
+namespace eqs {
+
+namespace {
+
+constexpr int MC_BLOCK = 256;
+constexpr uint32_t STREAM_MC = 3u;
+
+struct Moments { // count, mean, sum of squared deviations
+    double n, mean, m2;
+};
+
+__host__ __device__ inline Moments merge(const Moments &a, const Moments &b)
+{
+    if (b.n == 0.0) return a;
+    if (a.n == 0.0) return b;
+    const double n = a.n + b.n, delta = b.mean - a.mean;
+    return Moments{n, a.mean + delta * (b.n / n), a.m2 + b.m2 + delta * delta * (a.n * b.n / n)};
+}
+
+struct McDev {
+    const double *from, *to; // [n]
+    const double *replay;    // [count][n] or nullptr
+    Moments *part;           // [grid]
+    Moments *out;            // this rank's result
+    unsigned int *counter;
+    long long first, nloc;
+    int n;
+    PhiloxKey key;
+};
+
+template <class Obj, bool REPLAY> __global__ void __launch_bounds__(MC_BLOCK) mc_kernel(const McDev P)
+{
+    extern __shared__ double s_box[]; // from[n], scale[n]
+    __shared__ Moments s_w[MC_BLOCK / 32];
+    __shared__ int s_last;
+    const int n = P.n, tid = threadIdx.x;
+    for (int d = tid; d < n; d += blockDim.x) {
+        s_box[d] = P.from[d];
+        s_box[n + d] = P.to[d] - P.from[d]; // Uniform::new_inclusive(x, y): u * scale + low, :191-195
+    }
+    __syncthreads();
+    Moments m{0.0, 0.0, 0.0};
+    for (long long li = (long long)blockIdx.x * blockDim.x + tid; li < P.nloc; li += (long long)gridDim.x * blockDim.x) {
+        const long long gi = P.first + li;
+        double sample;
+        {
+            ObjAcc acc;
+            double xs_prev = 0.0;
+            (void)xs_prev;
+            if constexpr (Obj::streaming) Obj::begin(acc, n);
+            auto coord = [&](double u, int d) {
+                const double x = u * s_box[n + d] + s_box[d];
+                if constexpr (Obj::streaming) Obj::feed(acc, x, d);
+            };
+            if constexpr (REPLAY) {
+                for (int d = 0; d < n; ++d) coord(P.replay[gi * n + d], d);
+            } else {
+                for (int p = 0; 2 * p < n; ++p) {
+                    const uint4 w = philox_draw(P.key, STREAM_MC, 0u, gi, (uint32_t)p);
+                    coord(u01(w.x, w.y), 2 * p);
+                    if (2 * p + 1 < n) coord(u01(w.z, w.w), 2 * p + 1);
+                }
+            }
+            if constexpr (Obj::streaming) sample = Obj::end(acc, n);
+            else sample = 0.0;
+        }
+        // Welford, lib.rs:184-186
+        m.n += 1.0;
+        const double delta = sample - m.mean;
+        m.mean = m.mean + delta / m.n;
+        m.m2 = m.m2 + delta * (sample - m.mean);
+    }
+    // lanes -> warp -> CTA, always merging the lower index range on the left
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Moments b;
+        b.n = __shfl_down_sync(0xffffffffu, m.n, o);
+        b.mean = __shfl_down_sync(0xffffffffu, m.mean, o);
+        b.m2 = __shfl_down_sync(0xffffffffu, m.m2, o);
+        if ((tid & (2 * o - 1)) == 0) m = merge(m, b);
+    }
+    if ((tid & 31) == 0) s_w[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+        Moments b = s_w[0];
+        for (int w = 1; w < MC_BLOCK / 32; ++w) b = merge(b, s_w[w]);
+        P.part[blockIdx.x] = b;
+        __threadfence();
+        s_last = atomicAdd(P.counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && tid == 0) {
+        __threadfence();
+        Moments b{0.0, 0.0, 0.0};
+        for (unsigned j = 0; j < gridDim.x; ++j) {
+            Moments pj;
+            pj.n = __ldcg(&P.part[j].n);
+            pj.mean = __ldcg(&P.part[j].mean);
+            pj.m2 = __ldcg(&P.part[j].m2);
+            b = merge(b, pj);
+        }
+        *P.out = b;
+        *P.counter = 0;
+    }
+}
+
+} // namespace
+
+int validate_mc_params(const eqs_mc_params *p, std::string *why)
+{
+    auto bad = [&](int st, const char *m) {
+        if (why) *why = m;
+        return st;
+    };
+    if (!p) return bad(EQS_ERR_INCORRECT_INPUT, "null parameters");
+    if (p->n <= 0 || p->n > 12800) return bad(EQS_ERR_INCORRECT_INPUT, "dimension n out of range");
+    if (p->integrand_id < 0 || p->integrand_id >= EQS_OBJ_COUNT) return bad(EQS_ERR_INCORRECT_INPUT, "unknown integrand id");
+    if ((p->integrand_id == EQS_OBJ_THREE_CIRCLES || p->integrand_id == EQS_OBJ_SINCOS) && p->n != 2)
+        return bad(EQS_ERR_INCORRECT_INPUT, "this integrand needs n = 2");
+    if (!p->from || !p->to) return bad(EQS_ERR_INCORRECT_INPUT, "null bounds");
+    double volume = 1.0;
+    for (int d = 0; d < p->n; ++d) { // Uniform::new_inclusive -> ExternalError, monte_carlo.rs:171-172,191-195
+        const double lo = p->from[d], hi = p->to[d];
+        if (!(lo <= hi)) return bad(EQS_ERR_EXTERNAL, "low > high (or equal if exclusive) in uniform distribution");
+        if (!std::isfinite(lo) || !std::isfinite(hi) || !std::isfinite(hi - lo))
+            return bad(EQS_ERR_EXTERNAL, "Non-finite range in uniform distribution");
+        volume *= hi - lo;
+    }
+    if (volume < 0.0) return bad(EQS_ERR_INCORRECT_INPUT, "the input volume should be non-negative"); // :148-152
+    if (p->sample_count < 2) return bad(EQS_ERR_INCORRECT_INPUT, "the iterator must be over at least 2 elements"); // lib.rs:190-193
+    return EQS_OK;
+}
+
+} // namespace eqs
+
+using namespace eqs;
+
+extern "C" {
+
+int eqs_mc_validate(const eqs_mc_params *p) { return validate_mc_params(p, nullptr); }
+
+int eqs_mc_integrate(eqs_ctx *ctx, const eqs_mc_params *p, double *mean, double *variance, eqs_report *report)
+{
+    if (!ctx) return EQS_ERR_INCORRECT_INPUT;
+    Ctx *c = &ctx->c;
+    if (!mean || !variance) return c->fail(EQS_ERR_INCORRECT_INPUT, "null result pointers");
+    std::string why;
+    const int st = validate_mc_params(p, &why);
+    if (st != EQS_OK) return c->fail(st, "%s", why.c_str());
+    bool streaming = true;
+    dispatch_objective(p->integrand_id, [&]<class Obj>() { streaming = Obj::streaming; });
+    if (!streaming) return c->fail(EQS_ERR_INCORRECT_INPUT, "random-access integrands are not supported by the Monte Carlo kernel");
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int n = p->n, world = c->world, rank = c->rank;
+    int64_t first = 0, nloc = 0;
+    eqs_shard_range(p->sample_count, world, rank, &first, &nloc);
+    const int grid = (int)std::min<long long>(std::max<long long>(1, (nloc + MC_BLOCK - 1) / MC_BLOCK), 8LL * c->sm_count);
+    // arena: from, to, partials, result (+ all ranks' results), counter
+    const size_t o_from = 0, o_to = (size_t)n * 8, o_part = 2 * (size_t)n * 8;
+    const size_t o_out = o_part + (size_t)grid * sizeof(Moments), o_all = o_out + sizeof(Moments);
+    const size_t o_cnt = o_all + (size_t)world * sizeof(Moments), total = o_cnt + 256;
+    void *arena = nullptr;
+    size_t got = 0;
+    EQS_CUDA(c, c->acquire_arena(total, &arena, &got));
+    char *base = (char *)arena;
+    double *d_replay = nullptr;
+    int rc = EQS_OK;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(s);
+        if (d_replay) cudaFree(d_replay);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        c->release_arena(arena, got);
+    };
+#define MC_TRY(expr)                                                                                             \
+    do {                                                                                                         \
+        cudaError_t _e = (expr);                                                                                 \
+        if (_e != cudaSuccess) {                                                                                 \
+            cleanup();                                                                                           \
+            return c->fail(EQS_ERR_EXTERNAL, "CUDA error %s: %s", cudaGetErrorName(_e), cudaGetErrorString(_e)); \
+        }                                                                                                        \
+    } while (0)
+    MC_TRY(cudaMemcpyAsync(base + o_from, p->from, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    MC_TRY(cudaMemcpyAsync(base + o_to, p->to, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    MC_TRY(cudaMemsetAsync(base + o_cnt, 0, 256, s));
+    if (p->replay_u) {
+        const size_t bytes = (size_t)p->sample_count * n * 8;
+        MC_TRY(cudaMalloc(&d_replay, bytes));
+        MC_TRY(cudaMemcpyAsync(d_replay, p->replay_u, bytes, cudaMemcpyHostToDevice, s));
+    }
+    McDev D{};
+    D.from = (const double *)(base + o_from);
+    D.to = (const double *)(base + o_to);
+    D.replay = d_replay;
+    D.part = (Moments *)(base + o_part);
+    D.out = (Moments *)(base + o_out);
+    D.counter = (unsigned int *)(base + o_cnt);
+    D.first = first;
+    D.nloc = nloc;
+    D.n = n;
+    D.key = philox_key(p->seed);
+    MC_TRY(cudaEventCreate(&e0));
+    MC_TRY(cudaEventCreate(&e1));
+    MC_TRY(cudaEventRecord(e0, s));
+    const size_t smem = (size_t)2 * n * sizeof(double);
+    dispatch_objective(p->integrand_id, [&]<class Obj>() {
+        if constexpr (Obj::streaming) {
+            auto run = [&](auto kernel) {
+                if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                kernel<<<grid, MC_BLOCK, smem, s>>>(D);
+            };
+            if (d_replay) run(mc_kernel<Obj, true>);
+            else run(mc_kernel<Obj, false>);
+        }
+    });
+    MC_TRY(cudaGetLastError());
+    Moments *all = (Moments *)(base + o_all);
+    if (world > 1) {
+        rc = comm_allgather_f64(c, (const double *)D.out, (double *)all, 3, s);
+        if (rc != EQS_OK) {
+            cleanup();
+            return rc;
+        }
+    }
+    MC_TRY(cudaEventRecord(e1, s));
+    std::vector<Moments> host((size_t)world);
+    MC_TRY(cudaMemcpyAsync(host.data(), world > 1 ? (const void *)all : (const void *)D.out, sizeof(Moments) * (size_t)world,
+                           cudaMemcpyDeviceToHost, s));
+    MC_TRY(cudaStreamSynchronize(s));
+    Moments m{0.0, 0.0, 0.0};
+    for (int r = 0; r < world; ++r) m = merge(m, host[(size_t)r]); // ranks in index order
+    double volume = 1.0;
+    for (int d = 0; d < n; ++d) volume *= p->to[d] - p->from[d]; // (to - &from).product(), :197
+    const double var = m.m2 / (m.n - 1.0);                        // bessel, lib.rs:195-199
+    *mean = m.mean * volume;                                       // scale_mean, lib.rs:143-148
+    *variance = var * volume * volume;
+    if (report) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *report = eqs_report{};
+        report->iters_run = 1;
+        report->evals = p->sample_count;
+        report->best_cost = *mean;
+        report->world = world;
+        report->kernel_launches = 1;
+        report->loop_ms = ms;
+    }
+    cleanup();
+#undef MC_TRY
+    return EQS_OK;
+}
+
+} // extern "C"

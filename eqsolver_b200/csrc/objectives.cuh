@@ -120,6 +120,25 @@ template <> struct Objective<EQS_OBJ_HEAVY> {
     }
 };
 
+// integrands of the reference's integrator tests (tests/integrators.rs:11-17)
+template <> struct Objective<EQS_OBJ_GAUSSIAN> { // (-x * x).exp(); the squares are summed for n > 1
+    static constexpr bool streaming = true;
+    __device__ __forceinline__ static void begin(ObjAcc &s, int) { s.a = 0.0; }
+    __device__ __forceinline__ static void feed(ObjAcc &s, double x, int) { s.a += x * x; }
+    __device__ __forceinline__ static double end(const ObjAcc &s, int) { return exp(-s.a); }
+};
+
+template <> struct Objective<EQS_OBJ_SINCOS> { // (v[1].cos() + v[0]).sin(), n = 2
+    static constexpr bool streaming = true;
+    __device__ __forceinline__ static void begin(ObjAcc &s, int) { s.a = 0.0; s.p = 0.0; }
+    __device__ __forceinline__ static void feed(ObjAcc &s, double x, int d)
+    {
+        if (d == 0) s.p = x;
+        if (d == 1) s.a = sin(cos(x) + s.p);
+    }
+    __device__ __forceinline__ static double end(const ObjAcc &s, int) { return s.a; }
+};
+
 } // namespace eqs
 
 #include "user_objective.cuh"
@@ -151,6 +170,8 @@ template <class F> inline bool dispatch_objective(int id, F &&f)
     case EQS_OBJ_THREE_CIRCLES: f.template operator()<Objective<EQS_OBJ_THREE_CIRCLES>>(); return true;
     case EQS_OBJ_HEAVY: f.template operator()<Objective<EQS_OBJ_HEAVY>>(); return true;
     case EQS_OBJ_USER: f.template operator()<Objective<EQS_OBJ_USER>>(); return true;
+    case EQS_OBJ_GAUSSIAN: f.template operator()<Objective<EQS_OBJ_GAUSSIAN>>(); return true;
+    case EQS_OBJ_SINCOS: f.template operator()<Objective<EQS_OBJ_SINCOS>>(); return true;
     default: return false;
     }
 }

@@ -774,7 +774,8 @@ int validate_pso_params(const eqs_pso_params *p, std::string *why)
     if (p->n >= (1 << 28)) return bad(EQS_ERR_INCORRECT_INPUT, "dimension n must be below 2^28");
     if (p->particle_count < 0 || p->iter_max < 0) return bad(EQS_ERR_INCORRECT_INPUT, "negative count");
     if (p->objective_id < 0 || p->objective_id >= EQS_OBJ_COUNT) return bad(EQS_ERR_INCORRECT_INPUT, "unknown objective id");
-    if (p->objective_id == EQS_OBJ_THREE_CIRCLES && p->n != 2) return bad(EQS_ERR_INCORRECT_INPUT, "three-circles objective needs n = 2");
+    if ((p->objective_id == EQS_OBJ_THREE_CIRCLES || p->objective_id == EQS_OBJ_SINCOS) && p->n != 2)
+        return bad(EQS_ERR_INCORRECT_INPUT, "this objective needs n = 2");
     if (p->mode != EQS_PSO_SEQUENTIAL_EXACT && p->mode != EQS_PSO_SYNCHRONOUS) return bad(EQS_ERR_INCORRECT_INPUT, "unknown mode");
     if (!p->lower || !p->upper) return bad(EQS_ERR_INCORRECT_INPUT, "null bounds");
     // Uniform::new_inclusive(low, high): rand's error strings, surfaced as SolverError::ExternalError (:129,:139)

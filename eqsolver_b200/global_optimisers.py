@@ -38,6 +38,8 @@ class Objective(enum.IntEnum):
     THREE_CIRCLES = 4
     HEAVY = 5
     USER = 6
+    GAUSSIAN = 7       # exp(-sum x^2), tests/integrators.rs:11-13
+    SINCOS = 8         # sin(cos(x1) + x0), tests/integrators.rs:15-17
 
 
 class PsoMode(enum.IntEnum):

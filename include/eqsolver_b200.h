@@ -50,7 +50,9 @@ typedef enum {
     EQS_OBJ_THREE_CIRCLES = 4, /* examples/global_optimiser_as_solver.rs:22-42 (n = 2) */
     EQS_OBJ_HEAVY = 5,         /* benchmarks/multi.rs:106-115,137 */
     EQS_OBJ_USER = 6,          /* eqsolver_b200/csrc/user_objective.cuh, rebuilt by the user */
-    EQS_OBJ_COUNT = 7
+    EQS_OBJ_GAUSSIAN = 7,      /* exp(-sum x^2): the integrand of tests/integrators.rs:11-13 (n = 1 there) */
+    EQS_OBJ_SINCOS = 8,        /* sin(cos(x1) + x0), n = 2: tests/integrators.rs:15-17 */
+    EQS_OBJ_COUNT = 9
 } eqs_objective;
 
 typedef enum {
@@ -213,6 +215,24 @@ int eqs_ce_phase(eqs_ce *h, int32_t phase, const double *replay_normals);
 int64_t eqs_ce_exchange_words(eqs_ce *h, int32_t phase);
 int eqs_ce_get_exchange(eqs_ce *h, int32_t phase, void *words);
 int eqs_ce_set_exchange(eqs_ce *h, int32_t phase, const void *words /*[world][words]*/);
+
+/* ---- MonteCarlo (first row of SURVEY.md §8f after the optimisers) --------------------------------
+ * MonteCarlo::new(f).with_sample_count(..).integrate_with_rng(from, to, rng), reference
+ * src/integrators/monte_carlo.rs:85-212 with MeanVariance::from_iterator_using_welford (src/lib.rs:172-202):
+ * sample_count points uniform in [from, to] (default 1000, integrators/mod.rs:18), integrand by ID, mean and
+ * Bessel-corrected variance of the integrand values scaled by the volume / its square. */
+typedef struct {
+    int32_t n;
+    int32_t integrand_id;     /* eqs_objective */
+    int64_t sample_count;     /* GLOBAL; >= 2 */
+    const double *from;       /* [n] */
+    const double *to;         /* [n] */
+    uint64_t seed;            /* Philox key (replaces the `rng` argument) */
+    const double *replay_u;   /* NULL, or u in [0,1) [sample_count][n] in draw order (parity mode) */
+} eqs_mc_params;
+
+int eqs_mc_validate(const eqs_mc_params *p); /* EXTERNAL for from > to / non-finite, INCORRECT_INPUT for count < 2 */
+int eqs_mc_integrate(eqs_ctx *ctx, const eqs_mc_params *p, double *mean, double *variance, eqs_report *report);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

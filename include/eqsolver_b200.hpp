@@ -8,6 +8,7 @@
 //   CrossEntropy(objective).with_*(..).solve(x0)     ~ cross_entropy.rs:75-85, 108-223, 245-306
 // The closure `f` is an Objective ID (device functors are compiled ahead of time).  Link with -leqsolver_b200.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <memory>
 #include <string>
@@ -22,7 +23,7 @@ namespace eqsolver {
 constexpr double DEFAULT_TOL = 1e-6;      // lib.rs:13
 constexpr int64_t DEFAULT_ITERMAX = 50;   // lib.rs:16
 
-enum class Objective : int32_t { Sphere = 0, Rosenbrock, Rastrigin, Ackley, ThreeCircles, Heavy, User };
+enum class Objective : int32_t { Sphere = 0, Rosenbrock, Rastrigin, Ackley, ThreeCircles, Heavy, User, Gaussian, SinCos };
 
 // SolverError, lib.rs:19-44
 struct SolverError {
@@ -196,4 +197,59 @@ private:
 };
 
 } // namespace global_optimisers
+
+namespace integrators {
+
+constexpr int64_t DEFAULT_SAMPLE_COUNT = 1000; // integrators/mod.rs:18
+
+// MeanVariance<T>, lib.rs:56-60
+struct MeanVariance {
+    double mean, variance;
+    double standard_deviation() const { return std::sqrt(variance); } // lib.rs:133-135
+};
+
+// MonteCarlo, integrators/monte_carlo.rs:85-212; the integrand is an objective ID, the rng a Philox seed
+class MonteCarlo {
+public:
+    explicit MonteCarlo(Objective integrand) : integrand_(integrand) {}
+    MonteCarlo &with_sample_count(int64_t v) { sample_count_ = v; return *this; } // :111-114
+    MonteCarlo &with_context(std::shared_ptr<Context> c) { ctx_ = std::move(c); return *this; }
+
+    // integrate_with_rng, :181-212
+    SolverResult<MeanVariance> integrate_with_seed(const Vector &from, const Vector &to, uint64_t seed = 0, eqs_report *report = nullptr)
+    {
+        if (from.size() != to.size()) return SolverError{SolverError::IncorrectInput, "bounds differ in length"};
+        auto ctx = ctx_;
+        if (!ctx) {
+            auto made = Context::create(0);
+            if (!made.is_ok()) return made.unwrap_err();
+            ctx = made.unwrap();
+        }
+        eqs_mc_params p{};
+        p.n = static_cast<int32_t>(from.size());
+        p.integrand_id = static_cast<int32_t>(integrand_);
+        p.sample_count = sample_count_;
+        p.from = from.data();
+        p.to = to.data();
+        p.seed = seed;
+        MeanVariance out{};
+        const int st = eqs_mc_integrate(ctx->raw(), &p, &out.mean, &out.variance, report);
+        if (st != EQS_OK) return ctx->error(st);
+        return out;
+    }
+    // integrate, integrators/mod.rs:95-98
+    SolverResult<double> integrate(const Vector &from, const Vector &to)
+    {
+        auto r = integrate_with_seed(from, to);
+        if (!r.is_ok()) return r.unwrap_err();
+        return r.unwrap().mean;
+    }
+
+private:
+    Objective integrand_;
+    int64_t sample_count_ = DEFAULT_SAMPLE_COUNT;
+    std::shared_ptr<Context> ctx_;
+};
+
+} // namespace integrators
 } // namespace eqsolver

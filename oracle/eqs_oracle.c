@@ -89,6 +89,13 @@ double orc_objective(int id, const double *x, int n)
         double q = s2 * s2;
         return s1 + q + q * q;
     }
+    case ORC_OBJ_GAUSSIAN: { /* tests/integrators.rs:11-13: (-x * x).exp(); summed over the dimensions for n > 1 */
+        double s2 = 0.0;
+        for (int d = 0; d < n; ++d) s2 += x[d] * x[d];
+        return exp(-s2);
+    }
+    case ORC_OBJ_SINCOS: /* tests/integrators.rs:15-17: (v[1].cos() + v[0]).sin() */
+        return sin(cos(x[1]) + x[0]);
     default:
         return NAN;
     }
@@ -125,7 +132,7 @@ double orc_u01(uint32_t w_lo, uint32_t w_hi)
 
 /* Draw-index contract: key = (seed lo, seed hi);
  * ctr = (gidx lo, gidx hi, stream<<28 | dim-or-pair index, iteration). */
-enum { STREAM_PSO_INIT = 0, STREAM_PSO_STEP = 1, STREAM_CE = 2 };
+enum { STREAM_PSO_INIT = 0, STREAM_PSO_STEP = 1, STREAM_CE = 2, STREAM_MC = 3 };
 
 static void philox_draw(uint64_t seed, int stream, int64_t t, int64_t gidx, uint32_t j, uint32_t out[4])
 {
@@ -711,6 +718,51 @@ void orc_ce_apply(orc_ce *s, const double *mu_new, const double *sigma_new)
     memcpy(s->mu, mu_new, sizeof(double) * s->p.n);
     memcpy(s->sigma, sigma_new, sizeof(double) * s->p.n);
     s->iter++;
+}
+
+/* ============================== MonteCarlo ================================================== */
+
+void orc_mc_draws(uint64_t seed, int64_t index, int n, double *u)
+{
+    for (int p = 0; 2 * p < n; ++p) {
+        uint32_t w[4];
+        philox_draw(seed, STREAM_MC, 0, index, (uint32_t)p, w);
+        u[2 * p] = orc_u01(w[0], w[1]);
+        if (2 * p + 1 < n) u[2 * p + 1] = orc_u01(w[2], w[3]);
+    }
+}
+
+int orc_mc_integrate(int integrand_id, int n, int64_t count, const double *from, const double *to, uint64_t seed,
+                     const double *replay_u, double *mean_out, double *variance_out)
+{
+    if (n <= 0) return ORC_ERR_INCORRECT_INPUT;
+    double volume = 1.0;
+    for (int d = 0; d < n; ++d) {
+        /* Uniform::new_inclusive(x, y) -> ExternalError, monte_carlo.rs:171-172,191-195 */
+        if (!(from[d] <= to[d]) || !isfinite(from[d]) || !isfinite(to[d]) || !isfinite(to[d] - from[d])) return ORC_ERR_EXTERNAL;
+        volume *= to[d] - from[d];                      /* (to - &from).product(), :197 */
+    }
+    if (volume < 0.0) return ORC_ERR_INCORRECT_INPUT;   /* :148-152 */
+    double *x = (double *)malloc(sizeof(double) * (size_t)n), *u = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+    double mean = 0.0, sum_of_squares = 0.0;             /* lib.rs:176-178 */
+    int64_t total = 0;
+    for (int64_t i = 0; i < count; ++i) {
+        if (replay_u) memcpy(u, replay_u + (size_t)i * n, sizeof(double) * (size_t)n);
+        else orc_mc_draws(seed, i, n, u);
+        for (int d = 0; d < n; ++d) x[d] = u[d] * (to[d] - from[d]) + from[d];
+        const double sample = orc_objective(integrand_id, x, n);
+        const double c = (double)(i + 1);
+        const double delta_mean = sample - mean;         /* lib.rs:184-186 */
+        mean = mean + delta_mean / c;
+        sum_of_squares = sum_of_squares + delta_mean * (sample - mean);
+        total += 1;
+    }
+    free(x); free(u);
+    if (total < 2) return ORC_ERR_INCORRECT_INPUT;      /* lib.rs:190-193 */
+    const double variance = sum_of_squares / (double)(total - 1); /* bessel, lib.rs:195-199 */
+    *mean_out = mean * volume;                           /* scale_mean, lib.rs:143-148 */
+    *variance_out = variance * volume * volume;
+    return ORC_OK;
 }
 
 /* ============================== timing helpers ============================================== */

@@ -36,7 +36,9 @@ enum {
     ORC_OBJ_ACKLEY = 3,
     ORC_OBJ_THREE_CIRCLES = 4,  /* reference examples/global_optimiser_as_solver.rs:22-42 (n = 2) */
     ORC_OBJ_HEAVY = 5,          /* reference benchmarks/multi.rs:106-115,137 */
-    ORC_OBJ_USER = 6            /* twin of the shipped user-hook example (Zakharov); not in the reference */
+    ORC_OBJ_USER = 6,           /* twin of the shipped user-hook example (Zakharov); not in the reference */
+    ORC_OBJ_GAUSSIAN = 7,       /* exp(-sum x^2): reference tests/integrators.rs:11-13 for n = 1 */
+    ORC_OBJ_SINCOS = 8          /* sin(cos(x1) + x0), n = 2: reference tests/integrators.rs:15-17 */
 };
 
 /* Status codes = SolverError variants, reference src/lib.rs:19-44. */
@@ -161,6 +163,16 @@ void orc_ce_apply(orc_ce *s, const double *mu_new, const double *sigma_new);
 int orc_ce_active(const orc_ce *s); /* loop condition :255 */
 
 /* timing helper for bench.py's cpu_baseline: runs `iters` PSO steps, returns seconds */
+/* ---- MonteCarlo -------------------------------------------------------
+ * MonteCarlo::integrate_with_rng over [from, to], reference src/integrators/monte_carlo.rs:164-212:
+ * `count` points uniform in the box (Uniform::new_inclusive per dimension, :191-195), integrand values
+ * through MeanVariance::from_iterator_using_welford(.., bessel = true) (src/lib.rs:172-202), mean scaled
+ * by the volume and variance by its square (:154-157, lib.rs:143-148).  replay_u: NULL (host Philox,
+ * stream 3, one block per dimension pair) or u in [0,1) [count][n] in draw order.  returns a status. */
+int orc_mc_integrate(int integrand_id, int n, int64_t count, const double *from, const double *to, uint64_t seed,
+                     const double *replay_u, double *mean, double *variance);
+void orc_mc_draws(uint64_t seed, int64_t index, int n, double *u);
+
 double orc_time_pso_steps(orc_pso *s, int64_t iters);
 double orc_time_ce_steps(orc_ce *s, int64_t iters);
 

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 
-SPHERE, ROSENBROCK, RASTRIGIN, ACKLEY, THREE_CIRCLES, HEAVY, USER = range(7)
+SPHERE, ROSENBROCK, RASTRIGIN, ACKLEY, THREE_CIRCLES, HEAVY, USER, GAUSSIAN, SINCOS = range(9)
 SEQUENTIAL, SYNCHRONOUS = 0, 1
 DIV_REFERENCE_TEN, DIV_ELITE_COUNT = 0, 1
 OK, ERR_MAX_ITER, ERR_NAN, ERR_INCORRECT_INPUT, ERR_BAD_JACOBIAN, ERR_TYPE_CONVERSION, ERR_EXTERNAL = range(7)
@@ -131,6 +131,25 @@ def ce_normals(seed, t, gidx, n):
     z = np.empty(n)
     lib().orc_ce_normals(C.c_uint64(seed), C.c_int64(t), C.c_int64(gidx), C.c_int(n), z.ctypes.data_as(_dp))
     return z
+
+
+def mc_draws(seed, index, n):
+    u = np.empty(n)
+    lib().orc_mc_draws(C.c_uint64(seed), C.c_int64(index), C.c_int(n), u.ctypes.data_as(_dp))
+    return u
+
+
+def mc_integrate(integrand_id, lower, upper, sample_count=1000, seed=0, replay_u=None):
+    """MonteCarlo::integrate_with_rng (reference monte_carlo.rs:164-212): returns (status, mean, variance)."""
+    lo, plo = _d(lower); hi, phi = _d(upper)
+    n = int(lo.size)
+    pr = None
+    if replay_u is not None:
+        r, pr = _d(replay_u); assert r.size == sample_count * n
+    m, v = C.c_double(0), C.c_double(0)
+    st = lib().orc_mc_integrate(C.c_int(int(integrand_id)), C.c_int(n), C.c_int64(sample_count), plo, phi,
+                                C.c_uint64(seed), pr, C.byref(m), C.byref(v))
+    return int(st), m.value, v.value
 
 
 class Pso:

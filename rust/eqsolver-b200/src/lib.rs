@@ -6,6 +6,7 @@ use std::{ffi::CStr, ptr, sync::Arc};
 use thiserror::Error;
 
 pub mod global_optimisers;
+pub mod integrators;
 
 /// Default tolerance, eqsolver `src/lib.rs:13`
 pub const DEFAULT_TOL: f64 = 1e-6;
@@ -44,6 +45,10 @@ pub enum Objective {
     ThreeCircles = 4,
     Heavy = 5,
     User = 6,
+    /// exp(-sum x^2): the integrand of eqsolver's tests/integrators.rs:11-13
+    Gaussian = 7,
+    /// sin(cos(x1) + x0): tests/integrators.rs:15-17
+    SinCos = 8,
 }
 
 /// One GPU: stream, device memory arena, NCCL communicator.  Cheap to clone (shared).

@@ -22,6 +22,8 @@ pub const EQS_OBJ_ACKLEY: i32 = 3;
 pub const EQS_OBJ_THREE_CIRCLES: i32 = 4;
 pub const EQS_OBJ_HEAVY: i32 = 5;
 pub const EQS_OBJ_USER: i32 = 6;
+pub const EQS_OBJ_GAUSSIAN: i32 = 7;
+pub const EQS_OBJ_SINCOS: i32 = 8;
 
 pub const EQS_PSO_SEQUENTIAL_EXACT: i32 = 0;
 pub const EQS_PSO_SYNCHRONOUS: i32 = 1;
@@ -79,6 +81,18 @@ pub struct eqs_ce_params {
     pub seed: u64,
     pub virtual_rank: i32,
     pub virtual_world: i32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct eqs_mc_params {
+    pub n: i32,
+    pub integrand_id: i32,
+    pub sample_count: i64,
+    pub from: *const c_double,
+    pub to: *const c_double,
+    pub seed: u64,
+    pub replay_u: *const c_double,
 }
 
 #[repr(C)]
@@ -154,4 +168,8 @@ extern "C" {
     pub fn eqs_ce_exchange_words(h: *mut eqs_ce, phase: i32) -> i64;
     pub fn eqs_ce_get_exchange(h: *mut eqs_ce, phase: i32, words: *mut c_void) -> c_int;
     pub fn eqs_ce_set_exchange(h: *mut eqs_ce, phase: i32, words: *const c_void) -> c_int;
+
+    pub fn eqs_mc_validate(p: *const eqs_mc_params) -> c_int;
+    pub fn eqs_mc_integrate(ctx: *mut eqs_ctx, p: *const eqs_mc_params, mean: *mut c_double, variance: *mut c_double,
+                            report: *mut eqs_report) -> c_int;
 }

@@ -66,6 +66,16 @@ static int gpu_tests()
         auto r = CrossEntropy(Objective::Sphere).with_context(ctx).with_std_dev({1.0, INFINITY}).solve({0.0, 0.0});
         CHECK(!r.is_ok() && r.unwrap_err().kind == SolverError::NotANumber);
     }
+    // tests/integrators.rs:87-106: the two known integrals at the default 1000 samples, tolerance 0.1
+    {
+        using eqsolver::integrators::MonteCarlo;
+        auto g = MonteCarlo(Objective::Gaussian).with_context(ctx).integrate({0.0}, {1.0});
+        CHECK(g.is_ok() && std::fabs(g.unwrap() - 0.746824132812427025) <= 0.1);
+        auto sc = MonteCarlo(Objective::SinCos).with_context(ctx).with_sample_count(1 << 20).integrate_with_seed({0.0, 0.0}, {1.0, 1.0}, 7);
+        CHECK(sc.is_ok() && std::fabs(sc.unwrap().mean - 0.9248464799519) <= 1e-2);
+        auto bad = MonteCarlo(Objective::Gaussian).with_context(ctx).integrate({1.0}, {0.0});
+        CHECK(!bad.is_ok() && bad.unwrap_err().kind == SolverError::ExternalError);
+    }
     std::printf("gpu tests ok\n");
     return 0;
 }

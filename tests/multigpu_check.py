@@ -120,6 +120,14 @@ def main():
         assert allel.tolist() == np.sort(oc.elites()).tolist(), f"CE elite set pass {t}"
     crun.close()
 
+    # ---- MonteCarlo: samples sharded over the ranks, moments merged in rank order == unsharded oracle -----------
+    for (integrand, n, count) in [(E.Objective.GAUSSIAN, 3, 100003), (E.Objective.SINCOS, 2, 2 * world + 1)]:
+        lower, upper = [0.0] * n, [1.5] * n
+        r = E.MonteCarlo.new(integrand).with_sample_count(count).with_context(ctx).integrate_with_seed(lower, upper, 5)
+        st, mean, var = O.mc_integrate(int(integrand), lower, upper, count, 5)
+        assert st == 0 and abs(r.mean - mean) <= 1e-12 * abs(mean) and abs(r.variance - var) <= 1e-10 * abs(var)
+        same_everywhere([r.mean, r.variance], "MC result")
+
     dist.barrier()
     if rank == 0:
         print(f"multigpu_check OK on {world} GPUs")

@@ -144,3 +144,32 @@ def test_known_optima():
     mu = O.Ce(O.SPHERE, [3.0] * 4, sample_size=400, elite_count=40, iter_max=80, std_dev=[2.0] * 4,
               mean_divisor=O.DIV_ELITE_COUNT, seed=3).solve()
     assert O.objective(O.SPHERE, mu) < 1e-8
+
+
+def test_mc_oracle_against_pure_python_welford():
+    """orc_mc_integrate (lib.rs:172-202, monte_carlo.rs:143-212) against a pure-Python restatement, bit for bit."""
+    import math
+    n, count, seed = 3, 257, 5
+    lower, upper = [-1.0, 0.0, 2.0], [1.0, 0.5, 3.5]
+    mean = ssq = 0.0
+    for i in range(count):
+        u = O.mc_draws(seed, i, n)
+        x = [u[d] * (upper[d] - lower[d]) + lower[d] for d in range(n)]
+        s = 0.0
+        for d in range(n - 1):
+            a = x[d + 1] - x[d] * x[d]; b = 1.0 - x[d]
+            s += 100.0 * (a * a) + b * b
+        delta = s - mean
+        mean = mean + delta / float(i + 1)
+        ssq = ssq + delta * (s - mean)
+    vol = 1.0
+    for d in range(n):
+        vol *= upper[d] - lower[d]
+    st, m, v = O.mc_integrate(O.ROSENBROCK, lower, upper, count, seed)
+    assert st == 0
+    assert_bit_equal([m, v], [mean * vol, ssq / (count - 1) * vol * vol])
+    assert O.mc_integrate(O.SPHERE, [1.0], [0.0], 10, 1)[0] == O.ERR_EXTERNAL
+    assert O.mc_integrate(O.SPHERE, [0.0], [1.0], 1, 1)[0] == O.ERR_INCORRECT_INPUT
+    # the reference's own tests (tests/integrators.rs:87-106): 1000 samples, tolerance 0.1
+    assert abs(O.mc_integrate(O.GAUSSIAN, [0.0], [1.0], 1000, 1729)[1] - 0.746824132812427025) <= 0.1
+    assert abs(O.mc_integrate(O.SINCOS, [0.0, 0.0], [1.0, 1.0], 1000, 1729)[1] - 0.9248464799519) <= 0.1
