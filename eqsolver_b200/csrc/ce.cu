@@ -13,6 +13,7 @@
 #include <cmath>
 #include <new>
 
+#define EQS_COS_TABLE 1 // issue-bound sample kernels: constant-operand cos (devmath.cuh)
 #include "common.cuh"
 #include "objectives.cuh"
 #include "philox.cuh"

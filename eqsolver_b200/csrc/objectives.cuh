@@ -14,7 +14,21 @@
 #include "../../include/eqsolver_b200.h"
 #include "devmath.cuh"
 
+// Where eqs_cos takes its coefficients from (devmath.cuh): 0 = literals (pso.cu, api.cu), 1 = __constant__ operands
+// (ce.cu, mc.cu define it before including this header).  The functors live in an inline namespace named after the
+// choice, so the two instantiations are distinct entities.
+#ifndef EQS_COS_TABLE
+#define EQS_COS_TABLE 0
+#endif
+
 namespace eqs {
+#if EQS_COS_TABLE
+inline namespace cos_table {
+#else
+inline namespace cos_literal {
+#endif
+
+__device__ __forceinline__ double obj_cos(double y) { return eqs_cos_t<(EQS_COS_TABLE != 0)>(y); }
 
 struct ObjAcc {
     double a, b, p;
@@ -63,7 +77,7 @@ template <> struct Objective<EQS_OBJ_ROSENBROCK> {
 template <> struct Objective<EQS_OBJ_RASTRIGIN> {
     static constexpr bool streaming = true;
     __device__ __forceinline__ static void begin(ObjAcc &s, int n) { s.a = 10.0 * (double)n; }
-    __device__ __forceinline__ static void feed(ObjAcc &s, double x, int) { s.a += x * x - 10.0 * eqs_cos(kTwoPi * x); }
+    __device__ __forceinline__ static void feed(ObjAcc &s, double x, int) { s.a += x * x - 10.0 * obj_cos(kTwoPi * x); }
     __device__ __forceinline__ static double end(const ObjAcc &s, int) { return s.a; }
 };
 
@@ -73,7 +87,7 @@ template <> struct Objective<EQS_OBJ_ACKLEY> {
     __device__ __forceinline__ static void feed(ObjAcc &s, double x, int)
     {
         s.a += x * x;
-        s.b += eqs_cos(kTwoPi * x);
+        s.b += obj_cos(kTwoPi * x);
     }
     __device__ __forceinline__ static double end(const ObjAcc &s, int n)
     {
@@ -139,11 +153,17 @@ template <> struct Objective<EQS_OBJ_SINCOS> { // (v[1].cos() + v[0]).sin(), n =
     __device__ __forceinline__ static double end(const ObjAcc &s, int) { return s.a; }
 };
 
+} // inline namespace
 } // namespace eqs
 
 #include "user_objective.cuh"
 
 namespace eqs {
+#if EQS_COS_TABLE
+inline namespace cos_table {
+#else
+inline namespace cos_literal {
+#endif
 template <> struct Objective<EQS_OBJ_USER> : public UserObjective {};
 
 // evaluate any functor through a view (eqs_objective_eval, f(x0), random-access functors)
@@ -175,4 +195,5 @@ template <class F> inline bool dispatch_objective(int id, F &&f)
     default: return false;
     }
 }
+} // inline namespace
 } // namespace eqs

@@ -292,6 +292,35 @@ class ParticleSwarm:
         self.last_report = rep
         return out
 
+    def solve_with_seed(self, x0, seed: int) -> np.ndarray:
+        """`solve` with an explicit generator state, the optimisers' twin of
+        `OrthotopeRandomIntegrator::integrate_with_rng` (integrators/mod.rs:56-61): same seed, same result."""
+        self.seed = int(seed)
+        return self.solve(x0)
+
+    def solve_with_draws(self, x0, init_draws, step_draws) -> np.ndarray:
+        """`solve` on host-supplied draws instead of a generator (the replay mode of the parity tests as a feature).
+        `init_draws` [N][2][n]: u in [0, 1) for the start positions, then for the velocities, which the samplers of
+        particle_swarm.rs:367,373 scale into their ranges; `step_draws` [passes][N][n][2]: (r_p, r_g) (:407-408).  Runs
+        min(passes, iter_max) passes, or fewer when the stall test (:433-441) fires."""
+        init_draws = _arr(init_draws, self.particle_count * 2 * self.lower.size)
+        per_pass = self.particle_count * self.lower.size * 2
+        step_draws = _arr(step_draws)
+        if step_draws.size % per_pass:
+            raise IncorrectInput("step_draws must hold whole passes of particle_count * n * 2 draws")
+        saved = self.replay_init
+        self.replay_init = init_draws
+        try:
+            run = self.start(x0)
+        finally:
+            self.replay_init = saved
+        try:
+            for t in range(min(step_draws.size // per_pass, self.iter_max)):
+                run.step(1, step_draws[t * per_pass:(t + 1) * per_pass])
+            return run.gbest()[0]
+        finally:
+            run.close()
+
     def start(self, x0=None) -> "PsoRun":
         """Step-granular twin of solve() with the population resident in HBM (parity, tracing, benchmarks)."""
         run = PsoRun(self.context or default_context(), self)
@@ -440,6 +469,27 @@ class CrossEntropy:
         ctx.check(_ffi.lib().eqs_ce_solve(ctx._h, C.byref(self._params(x0.size)), _p(x0), _p(out), C.byref(rep)))
         self.last_report = rep
         return out
+
+    def solve_with_seed(self, x0, seed: int) -> np.ndarray:
+        """`solve` with an explicit generator state (see ParticleSwarm.solve_with_seed)."""
+        self.seed = int(seed)
+        return self.solve(x0)
+
+    def solve_with_draws(self, x0, normals) -> np.ndarray:
+        """`solve` on host-supplied standard normals `normals` [passes][N][n] (the z of `Normal::sample`,
+        cross_entropy.rs:270); runs min(passes, iter_max - 1) passes (`iter` starts at 1, :253) or stops on tol."""
+        x0 = _arr(x0)
+        per_pass = self.sample_size * x0.size
+        normals = _arr(normals)
+        if normals.size % per_pass:
+            raise IncorrectInput("normals must hold whole passes of sample_size * n draws")
+        run = self.start(x0)
+        try:
+            for t in range(min(normals.size // per_pass, max(0, self.iter_max - 1))):
+                run.step(1, normals[t * per_pass:(t + 1) * per_pass])
+            return run.state()[0]
+        finally:
+            run.close()
 
     def start(self, x0) -> "CeRun":
         return CeRun(self.context or default_context(), self, _arr(x0))

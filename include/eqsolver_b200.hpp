@@ -97,6 +97,12 @@ public:
     ParticleSwarm &with_mode(PsoMode m) { mode_ = m; return *this; }
     ParticleSwarm &with_context(std::shared_ptr<Context> c) { ctx_ = std::move(c); return *this; }
 
+    // solve with an explicit generator state, the twin of integrate_with_rng (integrators/mod.rs:56-61)
+    SolverResult<Vector> solve_with_seed(const Vector &x0, uint64_t seed, eqs_report *report = nullptr)
+    {
+        seed_ = seed;
+        return solve(x0, report);
+    }
     // solve(x0), particle_swarm.rs:356-431: the global best position
     SolverResult<Vector> solve(const Vector &x0, eqs_report *report = nullptr) const
     {
@@ -157,6 +163,11 @@ public:
     CrossEntropy &with_mean_divisor(MeanDivisor m) { divisor_ = m; return *this; }
     CrossEntropy &with_context(std::shared_ptr<Context> c) { ctx_ = std::move(c); return *this; }
 
+    SolverResult<Vector> solve_with_seed(const Vector &x0, uint64_t seed, eqs_report *report = nullptr)
+    {
+        seed_ = seed;
+        return solve(x0, report);
+    }
     // solve(x0), cross_entropy.rs:245-306: the final mean; the reference's panics become NotANumber
     SolverResult<Vector> solve(const Vector &x0, eqs_report *report = nullptr) const
     {

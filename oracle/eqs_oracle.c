@@ -12,6 +12,7 @@
 #include "eqs_oracle.h"
 
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -315,33 +316,35 @@ void orc_pso_init(orc_pso *s, const double *x0)
     }
 }
 
-static void fetch_step_draws(orc_pso *s, int64_t li)
+static void fetch_step_draws(const orc_pso *s, int64_t li, double *rp, double *rg)
 {
     const orc_pso_params *p = &s->p;
     int n = p->n;
     int64_t gi = p->first_index + li;
     if (p->replay_step) {
         const double *src = p->replay_step + ((size_t)s->iters * p->particle_count + gi) * 2 * n;
-        for (int d = 0; d < n; ++d) { s->rp[d] = src[2 * d]; s->rg[d] = src[2 * d + 1]; }
+        for (int d = 0; d < n; ++d) { rp[d] = src[2 * d]; rg[d] = src[2 * d + 1]; }
     } else {
-        orc_pso_step_draws(p->seed, s->iters, gi, n, s->rp, s->rg);
+        orc_pso_step_draws(p->seed, s->iters, gi, n, rp, rg);
     }
 }
 
 /* velocity + position update and evaluation of one particle against gbest G, :406-415 */
-static double move_particle(orc_pso *s, int64_t li)
+static double move_particle_with(orc_pso *s, int64_t li, double *rps, double *rgs)
 {
     const orc_pso_params *p = &s->p;
     int n = p->n;
     double *x = s->x + (size_t)li * n, *v = s->v + (size_t)li * n, *pb = s->pb + (size_t)li * n;
-    fetch_step_draws(s, li);
+    fetch_step_draws(s, li, rps, rgs);
     for (int d = 0; d < n; ++d) {
-        double rp = s->rp[d], rg = s->rg[d];
+        double rp = rps[d], rg = rgs[d];
         v[d] = p->w * v[d] + p->c1 * rp * (pb[d] - x[d]) + p->c2 * rg * (s->G[d] - x[d]); /* :409-411 */
     }
     for (int d = 0; d < n; ++d) x[d] += v[d];          /* :413 */
     return orc_objective(p->objective_id, x, n);       /* :415 */
 }
+
+static double move_particle(orc_pso *s, int64_t li) { return move_particle_with(s, li, s->rp, s->rg); }
 
 static int step_sequential(orc_pso *s)
 {
@@ -765,6 +768,56 @@ int orc_mc_integrate(int integrand_id, int n, int64_t count, const double *from,
     return ORC_OK;
 }
 
+/* ============================== all-cores variant =============================== */
+/* Synchronous mode only: the particles of one pass are independent, so T threads each take a contiguous slice
+ * (own draw scratch); the min-loc and the gbest update stay on the calling thread.  Bit-identical to orc_pso_step. */
+
+typedef struct {
+    orc_pso *s;
+    int64_t lo, hi;
+} mt_job;
+
+static void *mt_worker(void *arg)
+{
+    mt_job *j = (mt_job *)arg;
+    orc_pso *s = j->s;
+    int n = s->p.n;
+    double *scratch = (double *)malloc(sizeof(double) * 2 * (size_t)n);
+    for (int64_t i = j->lo; i < j->hi; ++i) {
+        double cost = move_particle_with(s, i, scratch, scratch + n);
+        s->cost[i] = cost;
+        if (cost < s->pbc[i]) {
+            memcpy(s->pb + (size_t)i * n, s->x + (size_t)i * n, sizeof(double) * n);
+            s->pbc[i] = cost;
+        }
+    }
+    free(scratch);
+    return NULL;
+}
+
+int orc_pso_step_mt(orc_pso *s, int threads)
+{
+    if (s->p.mode == ORC_PSO_SEQUENTIAL) return -1;
+    if (stalled_too_long(s)) return 1;
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t tid[256];
+    mt_job job[256];
+    int64_t N = s->p.local_count;
+    for (int t = 0; t < threads; ++t) {
+        job[t].s = s;
+        job[t].lo = N * t / threads;
+        job[t].hi = N * (t + 1) / threads;
+        pthread_create(&tid[t], NULL, mt_worker, &job[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(tid[t], NULL);
+    double *record = (double *)malloc(sizeof(double) * (2 + s->p.n));
+    local_minloc(s, record);
+    orc_pso_step_apply(s, 1, record);
+    free(record);
+    return 0;
+}
+
 /* ============================== timing helpers ============================================== */
 
 static double now_s(void)
@@ -778,6 +831,13 @@ double orc_time_pso_steps(orc_pso *s, int64_t iters)
 {
     double t0 = now_s();
     for (int64_t i = 0; i < iters; ++i) orc_pso_step(s);
+    return now_s() - t0;
+}
+
+double orc_time_pso_steps_mt(orc_pso *s, int64_t iters, int threads)
+{
+    double t0 = now_s();
+    for (int64_t i = 0; i < iters; ++i) orc_pso_step_mt(s, threads);
     return now_s() - t0;
 }
 

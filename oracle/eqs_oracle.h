@@ -174,6 +174,9 @@ int orc_mc_integrate(int integrand_id, int n, int64_t count, const double *from,
 void orc_mc_draws(uint64_t seed, int64_t index, int n, double *u);
 
 double orc_time_pso_steps(orc_pso *s, int64_t iters);
+/* all-cores variant of a synchronous pass (threads over particles), bit-identical to orc_pso_step */
+int orc_pso_step_mt(orc_pso *s, int threads);
+double orc_time_pso_steps_mt(orc_pso *s, int64_t iters, int threads);
 double orc_time_ce_steps(orc_ce *s, int64_t iters);
 
 #ifdef __cplusplus

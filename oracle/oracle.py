@@ -34,7 +34,7 @@ def build(force: bool = False) -> str:
         return _LIB_PATH
     os.makedirs(os.path.dirname(_LIB_PATH), exist_ok=True)
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-o", _LIB_PATH,
-                           src, "-lm"])
+                           src, "-lm", "-pthread"])
     return _LIB_PATH
 
 
@@ -76,6 +76,10 @@ def lib():
         L.orc_ce_iters.restype = C.c_int64
         L.orc_time_pso_steps.restype = C.c_double
         L.orc_time_pso_steps.argtypes = [C.c_void_p, C.c_int64]
+        L.orc_time_pso_steps_mt.restype = C.c_double
+        L.orc_time_pso_steps_mt.argtypes = [C.c_void_p, C.c_int64, C.c_int]
+        L.orc_pso_step_mt.restype = C.c_int
+        L.orc_pso_step_mt.argtypes = [C.c_void_p, C.c_int]
         L.orc_time_ce_steps.restype = C.c_double
         L.orc_time_ce_steps.argtypes = [C.c_void_p, C.c_int64]
         for name in ("orc_pso_destroy", "orc_pso_init", "orc_pso_step", "orc_pso_iters", "orc_pso_gbest_cost",
@@ -250,6 +254,13 @@ class Pso:
 
     def time_steps(self, iters) -> float:
         return float(lib().orc_time_pso_steps(C.c_void_p(self._h), C.c_int64(iters)))
+
+    def step_mt(self, threads: int) -> int:
+        """One synchronous pass with `threads` host threads over the particles (bit-identical to step())."""
+        return int(lib().orc_pso_step_mt(C.c_void_p(self._h), int(threads)))
+
+    def time_steps_mt(self, iters, threads: int) -> float:
+        return float(lib().orc_time_pso_steps_mt(C.c_void_p(self._h), C.c_int64(iters), int(threads)))
 
 
 class Ce:

@@ -137,6 +137,13 @@ where
         }
     }
 
+    /// `solve` with an explicit generator state: the optimisers' twin of
+    /// `OrthotopeRandomIntegrator::integrate_with_rng` (`integrators/mod.rs:56-61`).
+    pub fn solve_with_seed(&mut self, x0: VectorType<D>, seed: u64) -> SolverResult<VectorType<D>> {
+        self.seed = seed;
+        self.solve(x0)
+    }
+
     /// `solve(x0)`, `particle_swarm.rs:356-431`: the global best position.
     pub fn solve(&self, x0: VectorType<D>) -> SolverResult<VectorType<D>> {
         let ctx = match &self.context {
@@ -216,6 +223,12 @@ where
     pub fn with_context(&mut self, context: Context) -> &mut Self {
         self.context = Some(context);
         self
+    }
+
+    /// `solve` with an explicit generator state (see `ParticleSwarm::solve_with_seed`).
+    pub fn solve_with_seed(&mut self, x0: VectorType<D>, seed: u64) -> SolverResult<VectorType<D>> {
+        self.seed = seed;
+        self.solve(x0)
     }
 
     /// `solve(x0)`, `cross_entropy.rs:245-306`: the final mean.  Where the reference panics (NaN cost, non-finite

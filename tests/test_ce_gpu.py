@@ -259,3 +259,19 @@ def test_small_kernel_equals_phase_pipeline(ctx, objective, monkeypatch):
         close(small.state()[1], big.state()[1], 5.0, f"sigma pass {t}")
         assert small.state()[2:] == big.state()[2:]
     assert small.last_step_ms()[1] == 1 and big.last_step_ms()[1] > 10
+
+
+def test_seeded_and_replay_solves_are_public_api(ctx):
+    """CrossEntropy.solve_with_seed / solve_with_draws."""
+    n, N, k, iters = 4, 500, 10, 8
+    x0 = np.full(n, 3.0)
+    ce = E.CrossEntropy.new(E.Objective.SPHERE).with_sample_size(N).with_importance_selection_size(k) \
+        .with_iter_max(iters).with_tol(0.0).with_std_dev(np.full(n, 2.0)).with_context(ctx)
+    a = ce.solve_with_seed(x0, 5)
+    assert np.array_equal(a, ce.solve_with_seed(x0, 5)) and not np.array_equal(a, ce.solve_with_seed(x0, 6))
+    z = np.random.Generator(np.random.Philox(3)).standard_normal((iters - 1, N, n))
+    got = ce.solve_with_draws(x0, z)
+    o = O.Ce(O.SPHERE, x0, sample_size=N, elite_count=k, iter_max=iters, tol=0.0, std_dev=np.full(n, 2.0),
+             replay_normals=z)
+    mu = o.solve()
+    np.testing.assert_allclose(got, mu, rtol=1e-12, atol=1e-13)

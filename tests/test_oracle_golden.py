@@ -173,3 +173,21 @@ def test_mc_oracle_against_pure_python_welford():
     # the reference's own tests (tests/integrators.rs:87-106): 1000 samples, tolerance 0.1
     assert abs(O.mc_integrate(O.GAUSSIAN, [0.0], [1.0], 1000, 1729)[1] - 0.746824132812427025) <= 0.1
     assert abs(O.mc_integrate(O.SINCOS, [0.0, 0.0], [1.0, 1.0], 1000, 1729)[1] - 0.9248464799519) <= 0.1
+
+
+def test_all_cores_pass_is_bit_identical_to_the_scalar_pass():
+    """orc_pso_step_mt (threads over particles, SURVEY 8d's all-cores baseline) == orc_pso_step, bit for bit."""
+    n, N = 7, 1031
+    lower, upper, x0 = [-5.0] * n, [10.0] * n, np.full(n, 2.0)
+    a = O.Pso(O.ROSENBROCK, lower, upper, particle_count=N, tol=0.0, mode=O.SYNCHRONOUS, seed=11)
+    b = O.Pso(O.ROSENBROCK, lower, upper, particle_count=N, tol=0.0, mode=O.SYNCHRONOUS, seed=11)
+    a.init(x0); b.init(x0)
+    for t in range(6):
+        assert a.step() == 0 and b.step_mt(1 + t) == 0
+        for u, w in zip(a.state(), b.state()):
+            assert_bit_equal(u, w)
+        assert_bit_equal(a.gbest(), b.gbest())
+        assert a.gbest_cost() == b.gbest_cost() and a.iters() == b.iters()
+    c = O.Pso(O.ROSENBROCK, lower, upper, particle_count=N, tol=0.0, mode=O.SEQUENTIAL, seed=11)
+    c.init(x0)
+    assert c.step_mt(4) == -1      # the reference's sequential gbest semantics cannot be threaded

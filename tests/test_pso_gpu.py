@@ -411,3 +411,23 @@ def test_device_cos_accuracy(ctx):
     sp = ctx.device_cos(np.array([np.inf, -np.inf, np.nan]))
     assert np.isnan(sp).all()
     assert ctx.device_cos(np.array([0.0]))[0] == 1.0
+
+
+def test_seeded_and_replay_solves_are_public_api(ctx):
+    """solve_with_seed / solve_with_draws (the optimisers' twin of integrate_with_rng)."""
+    n, N, iters = 5, 777, 9
+    lower, upper, x0 = [-5.0] * n, [10.0] * n, np.full(n, 3.0)
+    ps = E.ParticleSwarm.new(E.Objective.ROSENBROCK, lower, upper).with_particle_count(N).with_iter_max(iters) \
+        .with_tol(0.0).with_context(ctx)
+    a = ps.solve_with_seed(x0, 42)
+    assert np.array_equal(a, ps.solve_with_seed(x0, 42)) and not np.array_equal(a, ps.solve_with_seed(x0, 43))
+    o = O.Pso(O.ROSENBROCK, lower, upper, particle_count=N, iter_max=iters, tol=0.0, mode=O.SEQUENTIAL, seed=42)
+    assert np.array_equal(a.view(np.uint64), o.solve(x0).view(np.uint64))
+    rng = np.random.Generator(np.random.Philox(7))
+    init, steps = rng.random((N, 2, n)), rng.random((iters, N, n, 2))
+    got = ps.solve_with_draws(x0, init, steps)
+    od = O.Pso(O.ROSENBROCK, lower, upper, particle_count=N, iter_max=iters, tol=0.0, mode=O.SEQUENTIAL,
+               replay_init=init, replay_step=steps)
+    assert np.array_equal(got.view(np.uint64), od.solve(x0).view(np.uint64))
+    with pytest.raises(E.IncorrectInput):
+        ps.solve_with_draws(x0, init, steps.reshape(-1)[:-1])
