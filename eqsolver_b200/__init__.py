@@ -10,9 +10,9 @@ from .global_optimisers import (  # noqa: F401
     TypeConversionError, default_context, shard_range, unique_id,
 )
 from ._ffi import KernelLibraryMissing  # noqa: F401
-from .integrators import MeanVariance, MonteCarlo  # noqa: F401
+from .integrators import MISER, MeanVariance, MonteCarlo  # noqa: F401
 
 __all__ = ["ParticleSwarm", "CrossEntropy", "Objective", "PsoMode", "MeanDivisor", "Exchange", "Context",
            "SolverError", "MaxIterReached", "NotANumber", "IncorrectInput", "BadJacobian", "TypeConversionError",
            "ExternalError", "KernelLibraryMissing", "DEFAULT_TOL", "DEFAULT_ITERMAX", "default_context",
-           "shard_range", "unique_id", "PsoRun", "CeRun", "MonteCarlo", "MeanVariance"]
+           "shard_range", "unique_id", "PsoRun", "CeRun", "MonteCarlo", "MISER", "MeanVariance"]

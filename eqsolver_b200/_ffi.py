@@ -42,6 +42,12 @@ class McParams(C.Structure):
                 ("from_", dp), ("to", dp), ("seed", C.c_uint64), ("replay_u", dp)]
 
 
+class MiserParams(C.Structure):
+    _fields_ = [("n", C.c_int32), ("integrand_id", C.c_int32), ("sample_count", C.c_int64),
+                ("minimum_dimensional_sample_count", C.c_int64), ("maximum_depth", C.c_int32), ("reserved", C.c_int32),
+                ("alpha", C.c_double), ("dither", C.c_double), ("from_", dp), ("to", dp), ("seed", C.c_uint64)]
+
+
 class Report(C.Structure):
     _fields_ = [("iters_run", C.c_int64), ("evals", C.c_int64), ("best_cost", C.c_double),
                 ("stalled", C.c_int32), ("world", C.c_int32), ("kernel_launches", C.c_int64),
@@ -103,6 +109,8 @@ SYMBOLS = {
     "eqs_ce_set_exchange": (C.c_int, [_vp, C.c_int32, _vp]),
     "eqs_mc_validate": (C.c_int, [C.POINTER(McParams)]),
     "eqs_mc_integrate": (C.c_int, [_vp, C.POINTER(McParams), dp, dp, C.POINTER(Report)]),
+    "eqs_miser_validate": (C.c_int, [C.POINTER(MiserParams)]),
+    "eqs_miser_integrate": (C.c_int, [_vp, C.POINTER(MiserParams), dp, dp, C.POINTER(Report)]),
 }
 
 _lib = None

@@ -8,6 +8,9 @@
 // deterministic); it agrees with the sequential recurrence to rounding (tests: 1e-12 on the mean).
 #include <algorithm>
 #include <cmath>
+#include <functional>
+#include <limits>
+#include <string>
 #include <vector>
 
 #define EQS_COS_TABLE 1 // issue-bound sample kernels: constant-operand cos (devmath.cuh)
@@ -121,6 +124,123 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(MC_BLOCK) mc
     }
 }
 
+
+// ---- MISER (miser.rs:301-443): all Welford batches (variance probes and leaves) of one recursion level ------------
+
+constexpr int MS_BLOCK = 256, MS_SPT = 4, MS_CHUNK = MS_BLOCK * MS_SPT;
+constexpr uint32_t STREAM_MISER = 4u;
+
+struct MiserBatch {      // `count` points uniform in the node's region, dimension d narrowed to one half (d < 0: leaf)
+    long long count;
+    long long chunk0;    // first chunk of this batch in the launch
+    long long gbase;     // batch id << 40: high part of the Philox index
+    double mid;          // the bisection coordinate (probes)
+    int slot;            // row of the region arrays
+    int d;
+    int upper;           // 0: [from_d, mid], 1: [mid, to_d]
+    uint32_t node_id;    // Philox counter word 3
+};
+
+struct MiserDev {
+    const MiserBatch *batch;
+    const double *rfrom, *rto; // [slots][n]
+    Moments *part;             // [nchunks]
+    Moments *out;              // [nbatch]
+    long long nchunks;
+    int nbatch, n;
+    PhiloxKey key;
+};
+
+__device__ __forceinline__ Moments shfl_down(const Moments &m, int o)
+{
+    Moments b;
+    b.n = __shfl_down_sync(0xffffffffu, m.n, o);
+    b.mean = __shfl_down_sync(0xffffffffu, m.mean, o);
+    b.m2 = __shfl_down_sync(0xffffffffu, m.m2, o);
+    return b;
+}
+
+// one CTA per chunk of MS_CHUNK points (grid-stride); the partition into chunks, threads and merge order depends on
+// the batch sizes only, never on the grid, so a level is bit-reproducible
+template <class Obj> __global__ void __launch_bounds__(MS_BLOCK) miser_chunk_kernel(const MiserDev P)
+{
+    extern __shared__ double s_box[]; // low[n], scale[n]
+    __shared__ Moments s_w[MS_BLOCK / 32];
+    __shared__ int s_b;
+    const int n = P.n, tid = threadIdx.x;
+    for (long long chunk = blockIdx.x; chunk < P.nchunks; chunk += gridDim.x) {
+        if (tid == 0) { // the batch owning this chunk: last b with chunk0 <= chunk
+            int lo = 0, hi = P.nbatch - 1;
+            while (lo < hi) {
+                const int md = (lo + hi + 1) >> 1;
+                if (P.batch[md].chunk0 <= chunk) lo = md;
+                else hi = md - 1;
+            }
+            s_b = lo;
+        }
+        __syncthreads();
+        const MiserBatch B = P.batch[s_b];
+        for (int d = tid; d < n; d += MS_BLOCK) {
+            double lo = P.rfrom[(size_t)B.slot * n + d], hi = P.rto[(size_t)B.slot * n + d];
+            if (d == B.d) { // lower_d_sampler / upper_d_sampler, miser.rs:366-367
+                if (B.upper) lo = B.mid;
+                else hi = B.mid;
+            }
+            s_box[d] = lo;
+            s_box[n + d] = hi - lo;
+        }
+        __syncthreads();
+        Moments m{0.0, 0.0, 0.0};
+        const long long base = (chunk - B.chunk0) * MS_CHUNK;
+#pragma unroll 1
+        for (int k = 0; k < MS_SPT; ++k) {
+            const long long i = base + (long long)k * MS_BLOCK + tid;
+            if (i >= B.count) break;
+            ObjAcc acc;
+            Obj::begin(acc, n);
+            for (int pr = 0; 2 * pr < n; ++pr) {
+                const uint4 w = philox_draw(P.key, STREAM_MISER, B.node_id, B.gbase | i, (uint32_t)pr);
+                Obj::feed(acc, u01(w.x, w.y) * s_box[n + 2 * pr] + s_box[2 * pr], 2 * pr);
+                if (2 * pr + 1 < n) Obj::feed(acc, u01(w.z, w.w) * s_box[n + 2 * pr + 1] + s_box[2 * pr + 1], 2 * pr + 1);
+            }
+            const double sample = Obj::end(acc, n);
+            m.n += 1.0; // Welford, lib.rs:184-186
+            const double delta = sample - m.mean;
+            m.mean = m.mean + delta / m.n;
+            m.m2 = m.m2 + delta * (sample - m.mean);
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const Moments b = shfl_down(m, o);
+            if ((tid & (2 * o - 1)) == 0) m = merge(m, b);
+        }
+        if ((tid & 31) == 0) s_w[tid >> 5] = m;
+        __syncthreads();
+        if (tid == 0) {
+            Moments b = s_w[0];
+            for (int w = 1; w < MS_BLOCK / 32; ++w) b = merge(b, s_w[w]);
+            P.part[chunk] = b;
+        }
+    }
+}
+
+// one warp per batch: lanes merge contiguous runs of chunk partials, then the lanes merge in order
+__global__ void __launch_bounds__(MS_BLOCK) miser_merge_kernel(const MiserDev P)
+{
+    const int b = (int)(((long long)blockIdx.x * MS_BLOCK + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (b >= P.nbatch) return;
+    const MiserBatch B = P.batch[b];
+    const long long nch = (B.count + MS_CHUNK - 1) / MS_CHUNK, per = (nch + 31) / 32;
+    Moments m{0.0, 0.0, 0.0};
+    for (long long c = lane * per; c < nch && c < (lane + 1) * per; ++c) m = merge(m, P.part[B.chunk0 + c]);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const Moments x = shfl_down(m, o);
+        if ((lane & (2 * o - 1)) == 0) m = merge(m, x);
+    }
+    if (lane == 0) P.out[b] = m;
+}
+
 } // namespace
 
 int validate_mc_params(const eqs_mc_params *p, std::string *why)
@@ -147,6 +267,55 @@ int validate_mc_params(const eqs_mc_params *p, std::string *why)
     if (p->sample_count < 2) return bad(EQS_ERR_INCORRECT_INPUT, "the iterator must be over at least 2 elements"); // lib.rs:190-193
     return EQS_OK;
 }
+
+
+int validate_miser_params(const eqs_miser_params *p, std::string *why)
+{
+    auto bad = [&](int st, const char *m) {
+        if (why) *why = m;
+        return st;
+    };
+    if (!p) return bad(EQS_ERR_INCORRECT_INPUT, "null parameters");
+    if (p->n <= 0 || p->n > 12800) return bad(EQS_ERR_INCORRECT_INPUT, "dimension n out of range");
+    if (p->integrand_id < 0 || p->integrand_id >= EQS_OBJ_COUNT) return bad(EQS_ERR_INCORRECT_INPUT, "unknown integrand id");
+    if ((p->integrand_id == EQS_OBJ_THREE_CIRCLES || p->integrand_id == EQS_OBJ_SINCOS) && p->n != 2)
+        return bad(EQS_ERR_INCORRECT_INPUT, "this integrand needs n = 2");
+    if (!p->from || !p->to) return bad(EQS_ERR_INCORRECT_INPUT, "null bounds");
+    if (p->sample_count < 0 || p->sample_count > (1LL << 40)) return bad(EQS_ERR_INCORRECT_INPUT, "sample_count out of range");
+    if (p->minimum_dimensional_sample_count < 0 || p->minimum_dimensional_sample_count > (1LL << 40) / p->n)
+        return bad(EQS_ERR_INCORRECT_INPUT, "minimum_dimensional_sample_count out of range");
+    if (p->maximum_depth < 0 || p->maximum_depth > 30) return bad(EQS_ERR_INCORRECT_INPUT, "maximum_depth out of range (0..30)");
+    return EQS_OK;
+}
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline double host_u01(uint32_t w_lo, uint32_t w_hi)
+{
+    return (double)((((uint64_t)(w_hi & 0xFFFFFu)) << 32) | (uint64_t)w_lo) * 0x1.0p-52;
+}
+
+// Uniform::new_inclusive(lo, hi) of rand_distr: lo <= hi, both and their difference finite (miser.rs:296-299)
+inline bool uniform_ok(double lo, double hi) { return lo <= hi && std::isfinite(lo) && std::isfinite(hi) && std::isfinite(hi - lo); }
+
+struct MiserNode {
+    std::vector<double> from, to;
+    long long count = 0;      // points allotted (sample_count of miser_recurse)
+    int depth_remaining = 0;
+    uint32_t id = 1;          // root 1, children 2 id and 2 id + 1
+    int status = EQS_OK;
+    const char *why = "";
+    bool leaf = false;
+    int lower = -1, upper = -1; // children
+    // probes
+    std::vector<double> mid;
+    int first_batch = -1;
+    double mean = 0.0, variance = 0.0;
+};
+
+} // namespace
 
 } // namespace eqs
 
@@ -266,6 +435,263 @@ int eqs_mc_integrate(eqs_ctx *ctx, const eqs_mc_params *p, double *mean, double 
     }
     cleanup();
 #undef MC_TRY
+    return EQS_OK;
+}
+
+
+int eqs_miser_validate(const eqs_miser_params *p) { return validate_miser_params(p, nullptr); }
+
+int eqs_miser_integrate(eqs_ctx *ctx, const eqs_miser_params *p, double *mean, double *variance, eqs_report *report)
+{
+    if (!ctx) return EQS_ERR_INCORRECT_INPUT;
+    Ctx *c = &ctx->c;
+    if (!mean || !variance) return c->fail(EQS_ERR_INCORRECT_INPUT, "null result pointers");
+    std::string why;
+    const int vst = validate_miser_params(p, &why);
+    if (vst != EQS_OK) return c->fail(vst, "%s", why.c_str());
+    bool streaming = true;
+    dispatch_objective(p->integrand_id, [&]<class Obj>() { streaming = Obj::streaming; });
+    if (!streaming) return c->fail(EQS_ERR_INCORRECT_INPUT, "random-access integrands are not supported by the MISER kernel");
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int n = p->n;
+    const PhiloxKey key = philox_key(p->seed);
+    const long long min_count = p->minimum_dimensional_sample_count * n; // miser.rs:319
+    const long long ctl = (long long)(2 * n) << 40, leaf_base = (long long)(2 * n + 1) << 40;
+
+    std::vector<MiserNode> nodes(1);
+    nodes[0].from.assign(p->from, p->from + n);
+    nodes[0].to.assign(p->to, p->to + n);
+    nodes[0].count = p->sample_count;
+    nodes[0].depth_remaining = p->maximum_depth;
+    std::vector<int> level{0};
+    long long evals = 0, launches = 0;
+    int levels = 0;
+    float total_ms = 0.f;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    EQS_CUDA(c, cudaEventCreate(&e0));
+    EQS_CUDA(c, cudaEventCreate(&e1));
+    int rc = EQS_OK;
+
+    while (!level.empty() && rc == EQS_OK) {
+        ++levels;
+        // ---- classify the nodes of this level, lay out their batches ------------------------------------------
+        std::vector<MiserBatch> batches;
+        std::vector<double> rfrom, rto;
+        long long nchunks = 0;
+        auto add_batch = [&](int slot, int d, int upper, double mid, long long count, long long gbase, uint32_t id) {
+            MiserBatch b{};
+            b.count = count;
+            b.chunk0 = nchunks;
+            b.gbase = gbase;
+            b.mid = mid;
+            b.slot = slot;
+            b.d = d;
+            b.upper = upper;
+            b.node_id = id;
+            batches.push_back(b);
+            nchunks += (count + MS_CHUNK - 1) / MS_CHUNK;
+            evals += count;
+        };
+        for (size_t li = 0; li < level.size(); ++li) {
+            MiserNode &nd = nodes[(size_t)level[li]];
+            const int slot = (int)li;
+            rfrom.insert(rfrom.end(), nd.from.begin(), nd.from.end());
+            rto.insert(rto.end(), nd.to.begin(), nd.to.end());
+            bool ok = true;
+            for (int d = 0; d < n; ++d) ok = ok && uniform_ok(nd.from[d], nd.to[d]); // samplers, :320-324
+            if (!ok) {
+                nd.status = EQS_ERR_EXTERNAL;
+                nd.why = "low > high (or non-finite) in uniform distribution";
+                continue;
+            }
+            if (nd.depth_remaining == 0 || nd.count < min_count) { // plain Monte Carlo, :335-349
+                nd.leaf = true;
+                const long long cnt = std::max(nd.count, min_count);
+                if (cnt < 2) {
+                    nd.status = EQS_ERR_INCORRECT_INPUT;
+                    nd.why = "the iterator must be over at least 2 elements"; // lib.rs:190-193
+                    continue;
+                }
+                nd.first_batch = (int)batches.size();
+                add_batch(slot, -1, 0, 0.0, cnt, leaf_base, nd.id);
+                continue;
+            }
+            nd.count = std::max<long long>(nd.count, 2); // :351
+            if (!uniform_ok(-p->dither, p->dither)) {   // dither_sampler, :361
+                nd.status = EQS_ERR_EXTERNAL;
+                nd.why = "low > high (or non-finite) in uniform distribution (dither)";
+                continue;
+            }
+            nd.mid.resize((size_t)n);
+            for (int d = 0; d < n && ok; ++d) {
+                const uint4 w = philox_draw(key, STREAM_MISER, nd.id, ctl | (long long)(1 + d), 0u);
+                const double r = host_u01(w.x, w.y) * (p->dither - (-p->dither)) + (-p->dither);
+                const double delta = nd.to[d] - nd.from[d];
+                const double mid = nd.from[d] + delta * (0.5 + r); // :364-365
+                nd.mid[(size_t)d] = mid;
+                ok = uniform_ok(nd.from[d], mid) && uniform_ok(mid, nd.to[d]); // :366-367
+            }
+            if (!ok) {
+                nd.status = EQS_ERR_EXTERNAL;
+                nd.why = "low > high (or non-finite) in uniform distribution (bisection)";
+                continue;
+            }
+            nd.first_batch = (int)batches.size();
+            for (int d = 0; d < n; ++d)
+                for (int up = 0; up < 2; ++up)
+                    add_batch(slot, d, up, nd.mid[(size_t)d], nd.count, (long long)(2 * d + up) << 40, nd.id);
+        }
+
+        // ---- one launch for every batch of the level ----------------------------------------------------------
+        std::vector<Moments> out(batches.size());
+        if (!batches.empty()) {
+            const size_t b_bytes = batches.size() * sizeof(MiserBatch), r_bytes = rfrom.size() * 8;
+            const size_t o_b = 0, o_rf = align_up(b_bytes, 256), o_rt = o_rf + align_up(r_bytes, 256);
+            const size_t o_part = o_rt + align_up(r_bytes, 256), o_out = o_part + align_up((size_t)nchunks * sizeof(Moments), 256);
+            const size_t total = o_out + align_up(batches.size() * sizeof(Moments), 256);
+            void *arena = nullptr;
+            size_t got = 0;
+            EQS_CUDA(c, c->acquire_arena(total, &arena, &got));
+            char *base = (char *)arena;
+            auto try_cuda = [&](cudaError_t e) {
+                if (e != cudaSuccess && rc == EQS_OK)
+                    rc = c->fail(EQS_ERR_EXTERNAL, "CUDA error %s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+            };
+            try_cuda(cudaMemcpyAsync(base + o_b, batches.data(), b_bytes, cudaMemcpyHostToDevice, s));
+            try_cuda(cudaMemcpyAsync(base + o_rf, rfrom.data(), r_bytes, cudaMemcpyHostToDevice, s));
+            try_cuda(cudaMemcpyAsync(base + o_rt, rto.data(), r_bytes, cudaMemcpyHostToDevice, s));
+            MiserDev D{};
+            D.batch = (const MiserBatch *)(base + o_b);
+            D.rfrom = (const double *)(base + o_rf);
+            D.rto = (const double *)(base + o_rt);
+            D.part = (Moments *)(base + o_part);
+            D.out = (Moments *)(base + o_out);
+            D.nchunks = nchunks;
+            D.nbatch = (int)batches.size();
+            D.n = n;
+            D.key = key;
+            try_cuda(cudaEventRecord(e0, s));
+            const int grid = (int)std::min<long long>(nchunks, 16LL * c->sm_count);
+            const size_t smem = (size_t)2 * n * sizeof(double);
+            if (rc == EQS_OK)
+                dispatch_objective(p->integrand_id, [&]<class Obj>() {
+                    if constexpr (Obj::streaming) {
+                        auto kernel = miser_chunk_kernel<Obj>;
+                        if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        kernel<<<grid, MS_BLOCK, smem, s>>>(D);
+                    }
+                });
+            if (rc == EQS_OK) miser_merge_kernel<<<(D.nbatch * 32 + MS_BLOCK - 1) / MS_BLOCK, MS_BLOCK, 0, s>>>(D);
+            try_cuda(cudaGetLastError());
+            try_cuda(cudaEventRecord(e1, s));
+            try_cuda(cudaMemcpyAsync(out.data(), D.out, out.size() * sizeof(Moments), cudaMemcpyDeviceToHost, s));
+            try_cuda(cudaStreamSynchronize(s));
+            if (rc == EQS_OK) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                total_ms += ms;
+                launches += 2;
+            }
+            c->release_arena(arena, got);
+            if (rc != EQS_OK) break;
+        }
+
+        // ---- decide: leaves are done, inner nodes choose their bisection and hand points to two children ------
+        std::vector<int> next;
+        for (size_t li = 0; li < level.size(); ++li) {
+            const int ni = level[li];
+            if (nodes[(size_t)ni].status != EQS_OK) continue;
+            if (nodes[(size_t)ni].leaf) {
+                MiserNode &nd = nodes[(size_t)ni];
+                const Moments &m = out[(size_t)nd.first_batch];
+                double volume = 1.0;
+                for (int d = 0; d < n; ++d) volume = volume * (nd.to[d] - nd.from[d]); // fold(T::one(), T::mul), :337-341
+                nd.mean = m.mean * volume;                                             // scale_mean
+                nd.variance = (m.m2 / m.n) * volume * volume;                          // no Bessel correction, :345
+                continue;
+            }
+            const MiserNode cur = nodes[(size_t)ni]; // copy: nodes grows below
+            double best_variance = std::numeric_limits<double>::max(), best_lower = best_variance, best_upper = best_variance; // :356-358
+            const uint4 w = philox_draw(key, STREAM_MISER, cur.id, ctl, 0u);
+            int best_d = std::min(n - 1, (int)(host_u01(w.x, w.y) * (double)n));       // uniform(0, n - 1), :359
+            double best_mid = cur.from[best_d] + (cur.to[best_d] - cur.from[best_d]) * 0.5; // :360
+            for (int d = 0; d < n; ++d) {
+                const Moments &ml = out[(size_t)cur.first_batch + 2 * d], &mu = out[(size_t)cur.first_batch + 2 * d + 1];
+                const double vl = ml.m2 / (ml.n - 1.0), vu = mu.m2 / (mu.n - 1.0);      // Bessel-corrected, :382-392
+                const double tv = vl + vu;
+                if (tv < best_variance) { // :396-402
+                    best_variance = tv;
+                    best_lower = vl;
+                    best_upper = vu;
+                    best_d = d;
+                    best_mid = cur.mid[(size_t)d];
+                }
+            }
+            const double beta = 1.0 / (1.0 + p->alpha);                                  // :407
+            const double la = std::pow(best_lower, beta), ua = std::pow(best_upper, beta);
+            const double sum = la + ua;
+            const double nl = (double)cur.count * (la / sum), nu = (double)cur.count * (ua / sum); // :411-419
+            auto as_count = [](double v, long long *o) { // Float::to_usize: NaN, <= -1 and >= 2^64 have no value
+                if (!(v > -1.0 && v < 18446744073709551616.0)) return false;
+                *o = v < 0.0 ? 0 : (long long)std::min(v, 9.0e18);
+                return true;
+            };
+            long long cl = 0, cu = 0;
+            if (!as_count(nl, &cl) || !as_count(nu, &cu)) {
+                nodes[(size_t)ni].status = EQS_ERR_TYPE_CONVERSION;
+                nodes[(size_t)ni].why = "a variance share of the points is not a count";
+                continue;
+            }
+            for (int up = 0; up < 2; ++up) { // lower first, :422-440
+                MiserNode ch;
+                ch.from = cur.from;
+                ch.to = cur.to;
+                if (up) ch.from[(size_t)best_d] = best_mid;
+                else ch.to[(size_t)best_d] = best_mid;
+                ch.count = up ? cu : cl;
+                ch.depth_remaining = cur.depth_remaining - 1;
+                ch.id = 2 * cur.id + (uint32_t)up;
+                nodes.push_back(std::move(ch));
+                (up ? nodes[(size_t)ni].upper : nodes[(size_t)ni].lower) = (int)nodes.size() - 1;
+                next.push_back((int)nodes.size() - 1);
+            }
+        }
+        level.swap(next);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc != EQS_OK) return rc;
+
+    // ---- results in the recursion's own order: a node's error first, then lower, then upper (`?`, :422-440) ------
+    struct Ret {
+        int status;
+        const char *why;
+        double mean, variance;
+    };
+    std::function<Ret(int)> collect = [&](int ni) -> Ret {
+        const MiserNode &nd = nodes[(size_t)ni];
+        if (nd.status != EQS_OK) return Ret{nd.status, nd.why, 0.0, 0.0};
+        if (nd.leaf) return Ret{EQS_OK, "", nd.mean, nd.variance};
+        const Ret lo = collect(nd.lower);
+        if (lo.status != EQS_OK) return lo;
+        const Ret up = collect(nd.upper);
+        if (up.status != EQS_OK) return up;
+        return Ret{EQS_OK, "", lo.mean + up.mean, lo.variance + up.variance}; // MeanVariance::add, :442
+    };
+    const Ret r = collect(0);
+    if (r.status != EQS_OK) return c->fail(r.status, "%s", r.why);
+    *mean = r.mean;
+    *variance = r.variance;
+    if (report) {
+        *report = eqs_report{};
+        report->iters_run = levels;
+        report->evals = evals;
+        report->best_cost = r.mean;
+        report->world = 1;
+        report->kernel_launches = launches;
+        report->loop_ms = total_ms;
+    }
     return EQS_OK;
 }
 

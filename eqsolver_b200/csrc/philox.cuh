@@ -37,7 +37,7 @@ __host__ __device__ inline PhiloxKey philox_key(uint32_t lo, uint32_t hi)
 
 __host__ __device__ inline PhiloxKey philox_key(uint64_t seed) { return philox_key((uint32_t)seed, (uint32_t)(seed >> 32)); }
 
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKey &key)
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKey &key)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -54,7 +54,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
-__device__ __forceinline__ uint4 philox_draw(const PhiloxKey &key, uint32_t stream, uint32_t t, int64_t gidx, uint32_t j)
+__host__ __device__ __forceinline__ uint4 philox_draw(const PhiloxKey &key, uint32_t stream, uint32_t t, int64_t gidx, uint32_t j)
 {
     return philox4x32_10((uint32_t)(uint64_t)gidx, (uint32_t)((uint64_t)gidx >> 32), (stream << 28) | j, t, key);
 }

@@ -36,7 +36,7 @@ typedef enum {
     EQS_ERR_NAN = 2,             /* NotANumber: where the reference panics on NaN cost / non-finite sigma */
     EQS_ERR_INCORRECT_INPUT = 3, /* IncorrectInput{details} */
     EQS_ERR_BAD_JACOBIAN = 4,    /* BadJacobian             -- never produced by this path */
-    EQS_ERR_TYPE_CONVERSION = 5, /* TypeConversionError     -- never produced by this path */
+    EQS_ERR_TYPE_CONVERSION = 5, /* TypeConversionError     -- MISER only (miser.rs:413-419) */
     EQS_ERR_EXTERNAL = 6         /* ExternalError(String): bad bounds (rand's message), CUDA / NCCL failures */
 } eqs_status;
 
@@ -233,6 +233,35 @@ typedef struct {
 
 int eqs_mc_validate(const eqs_mc_params *p); /* EXTERNAL for from > to / non-finite, INCORRECT_INPUT for count < 2 */
 int eqs_mc_integrate(eqs_ctx *ctx, const eqs_mc_params *p, double *mean, double *variance, eqs_report *report);
+
+/* ---- MISER, recursive stratified sampling ------------------------------------------------
+ * MISER::new(f).with_*(..).integrate_with_rng(from, to, rng), reference src/integrators/miser.rs:270-443
+ * (miser_recurse :301-443).  Per region: leaf (plain Monte Carlo, population variance, :335-349) when the depth is
+ * used up or fewer than minimum_dimensional_sample_count * n points are allotted; otherwise 2n variance probes of
+ * sample_count points each (:362-400), bisection of the dimension with the smallest total variance at a dithered
+ * mid-point, points split by variance^(1/(1+alpha)) (:404-420), recursion on both halves, results added (:442).
+ * The recursion is evaluated level by level on one GPU: every probe and leaf of a level is one Welford batch of a
+ * single kernel launch.  Defaults: miser.rs:13-23.  Not sharded over ranks (the levels are latency-bound). */
+typedef struct {
+    int32_t n;
+    int32_t integrand_id;     /* eqs_objective */
+    int64_t sample_count;     /* default 1000, integrators/mod.rs:18; at most 2^40 */
+    int64_t minimum_dimensional_sample_count; /* default 32 */
+    int32_t maximum_depth;    /* default 5; at most 30 */
+    int32_t reserved;
+    double alpha;             /* default 2 */
+    double dither;            /* default 0.05 */
+    const double *from;       /* [n] */
+    const double *to;         /* [n] */
+    uint64_t seed;            /* Philox key (replaces the `rng` argument) */
+} eqs_miser_params;
+
+/* INCORRECT_INPUT for n <= 0, an unknown / non-streaming integrand, depth or count out of range.  Everything the
+ * reference reports while it runs comes from eqs_miser_integrate: EXTERNAL for from > to, non-finite bounds, a bad
+ * dither (Uniform::new_inclusive, :296-299), TYPE_CONVERSION when a variance share is not a count (:413-419, e.g. a
+ * constant integrand: 0/0), INCORRECT_INPUT when a leaf holds fewer than 2 points (lib.rs:190-193). */
+int eqs_miser_validate(const eqs_miser_params *p);
+int eqs_miser_integrate(eqs_ctx *ctx, const eqs_miser_params *p, double *mean, double *variance, eqs_report *report);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -262,5 +262,57 @@ private:
     std::shared_ptr<Context> ctx_;
 };
 
+// MISER, integrators/miser.rs:93-293 (defaults :13-23); the recursion :301-443 runs level by level in the library
+class MISER {
+public:
+    explicit MISER(Objective integrand) : integrand_(integrand) {}
+    MISER &with_sample_count(int64_t v) { sample_count_ = v; return *this; }
+    MISER &with_minimum_dimensional_sample_count(int64_t v) { min_dim_ = v; return *this; }
+    MISER &with_maximum_depth(int32_t v) { depth_ = v; return *this; }
+    MISER &with_alpha(double v) { alpha_ = v; return *this; }
+    MISER &with_dither(double v) { dither_ = v; return *this; }
+    MISER &with_context(std::shared_ptr<Context> c) { ctx_ = std::move(c); return *this; }
+
+    // integrate_with_rng, :277-292
+    SolverResult<MeanVariance> integrate_with_seed(const Vector &from, const Vector &to, uint64_t seed = 0, eqs_report *report = nullptr)
+    {
+        if (from.size() != to.size()) return SolverError{SolverError::IncorrectInput, "bounds differ in length"};
+        auto ctx = ctx_;
+        if (!ctx) {
+            auto made = Context::create(0);
+            if (!made.is_ok()) return made.unwrap_err();
+            ctx = made.unwrap();
+        }
+        eqs_miser_params p{};
+        p.n = static_cast<int32_t>(from.size());
+        p.integrand_id = static_cast<int32_t>(integrand_);
+        p.sample_count = sample_count_;
+        p.minimum_dimensional_sample_count = min_dim_;
+        p.maximum_depth = depth_;
+        p.alpha = alpha_;
+        p.dither = dither_;
+        p.from = from.data();
+        p.to = to.data();
+        p.seed = seed;
+        MeanVariance out{};
+        const int st = eqs_miser_integrate(ctx->raw(), &p, &out.mean, &out.variance, report);
+        if (st != EQS_OK) return ctx->error(st);
+        return out;
+    }
+    SolverResult<double> integrate(const Vector &from, const Vector &to)
+    {
+        auto r = integrate_with_seed(from, to);
+        if (!r.is_ok()) return r.unwrap_err();
+        return r.unwrap().mean;
+    }
+
+private:
+    Objective integrand_;
+    int64_t sample_count_ = DEFAULT_SAMPLE_COUNT, min_dim_ = 32;
+    int32_t depth_ = 5;
+    double alpha_ = 2.0, dither_ = 0.05;
+    std::shared_ptr<Context> ctx_;
+};
+
 } // namespace integrators
 } // namespace eqsolver

@@ -11,6 +11,7 @@
  */
 #include "eqs_oracle.h"
 
+#include <float.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
@@ -133,7 +134,7 @@ double orc_u01(uint32_t w_lo, uint32_t w_hi)
 
 /* Draw-index contract: key = (seed lo, seed hi);
  * ctr = (gidx lo, gidx hi, stream<<28 | dim-or-pair index, iteration). */
-enum { STREAM_PSO_INIT = 0, STREAM_PSO_STEP = 1, STREAM_CE = 2, STREAM_MC = 3 };
+enum { STREAM_PSO_INIT = 0, STREAM_PSO_STEP = 1, STREAM_CE = 2, STREAM_MC = 3, STREAM_MISER = 4 };
 
 static void philox_draw(uint64_t seed, int stream, int64_t t, int64_t gidx, uint32_t j, uint32_t out[4])
 {
@@ -766,6 +767,155 @@ int orc_mc_integrate(int integrand_id, int n, int64_t count, const double *from,
     *mean_out = mean * volume;                           /* scale_mean, lib.rs:143-148 */
     *variance_out = variance * volume * volume;
     return ORC_OK;
+}
+
+
+/* ============================== MISER ======================================================= */
+/* miser_recurse, src/integrators/miser.rs:301-443.  The reference threads one rng through the recursion; here
+ * every draw has a counter: stream 4, word 3 = node id (root 1, children 2 id, 2 id + 1), index =
+ * (batch << 40) | point, batch = 2 d + half for the variance probes, 2 n for the node's own scalars (point 0: the
+ * fallback dimension, point 1 + d: the dither of dimension d), 2 n + 1 for the leaf's Monte Carlo. */
+
+typedef struct {
+    int integrand_id, n;
+    int64_t min_dim_count;
+    double alpha, dither;
+    uint64_t seed;
+    int64_t evals;
+} miser_cfg;
+
+static int uniform_ok(double lo, double hi) { return lo <= hi && isfinite(lo) && isfinite(hi) && isfinite(hi - lo); }
+
+/* from_iterator_using_welford over `count` points of the box [lo, hi], lib.rs:172-202 */
+static int miser_batch(miser_cfg *m, const double *lo, const double *hi, int64_t count, uint32_t node, int64_t gbase,
+                       int bessel, double *mean_out, double *var_out)
+{
+    int n = m->n;
+    double *x = (double *)malloc(sizeof(double) * (size_t)n);
+    double mean = 0.0, sum_of_squares = 0.0;
+    int64_t total = 0;
+    for (int64_t i = 0; i < count; ++i) {
+        for (int p = 0; 2 * p < n; ++p) {
+            uint32_t w[4];
+            philox_draw(m->seed, STREAM_MISER, node, gbase | i, (uint32_t)p, w);
+            x[2 * p] = orc_u01(w[0], w[1]) * (hi[2 * p] - lo[2 * p]) + lo[2 * p];
+            if (2 * p + 1 < n) x[2 * p + 1] = orc_u01(w[2], w[3]) * (hi[2 * p + 1] - lo[2 * p + 1]) + lo[2 * p + 1];
+        }
+        const double sample = orc_objective(m->integrand_id, x, n);
+        const double c = (double)(i + 1);
+        const double delta_mean = sample - mean;
+        mean = mean + delta_mean / c;
+        sum_of_squares = sum_of_squares + delta_mean * (sample - mean);
+        total += 1;
+    }
+    free(x);
+    m->evals += count;
+    if (total < 2) return ORC_ERR_INCORRECT_INPUT;
+    if (bessel) total -= 1;
+    *mean_out = mean;
+    *var_out = sum_of_squares / (double)total;
+    return ORC_OK;
+}
+
+static int to_usize(double v, int64_t *out) /* num_traits ToPrimitive::to_usize for f64 */
+{
+    if (!(v > -1.0 && v < 18446744073709551616.0)) return 0;
+    *out = v < 0.0 ? 0 : (int64_t)(v < 9.0e18 ? v : 9.0e18);
+    return 1;
+}
+
+static int miser_recurse(miser_cfg *m, double *from, double *to, uint32_t node, int depth_remaining, int64_t sample_count,
+                         double *mean_out, double *var_out)
+{
+    int n = m->n;
+    const int64_t minimum_sample_count = m->min_dim_count * n;         /* :319 */
+    const int64_t ctl = (int64_t)(2 * n) << 40;
+    for (int d = 0; d < n; ++d)
+        if (!uniform_ok(from[d], to[d])) return ORC_ERR_EXTERNAL;       /* samplers, :320-324 */
+    if (depth_remaining == 0 || sample_count < minimum_sample_count) { /* :335-349 */
+        const int64_t count = sample_count > minimum_sample_count ? sample_count : minimum_sample_count;
+        double volume = 1.0, mean, var;
+        for (int d = 0; d < n; ++d) volume = volume * (to[d] - from[d]);
+        int st = miser_batch(m, from, to, count, node, (int64_t)(2 * n + 1) << 40, 0, &mean, &var);
+        if (st) return st;
+        *mean_out = mean * volume;                                     /* scale_mean */
+        *var_out = var * volume * volume;
+        return ORC_OK;
+    }
+    if (sample_count < 2) sample_count = 2;                            /* :351 */
+    double best_variance = DBL_MAX, best_lower_variance = DBL_MAX, best_upper_variance = DBL_MAX; /* :356-358 */
+    uint32_t w[4];
+    philox_draw(m->seed, STREAM_MISER, node, ctl, 0u, w);
+    int best_dimension = (int)(orc_u01(w[0], w[1]) * (double)n);       /* uniform(0, n - 1), :359 */
+    if (best_dimension > n - 1) best_dimension = n - 1;
+    double best_mid = from[best_dimension] + (to[best_dimension] - from[best_dimension]) * 0.5; /* :360 */
+    if (!uniform_ok(-m->dither, m->dither)) return ORC_ERR_EXTERNAL;   /* :361 */
+    /* the GPU build draws every dither of a node before the first probe runs; without a shared rng stream the
+     * order is immaterial, but an invalid bisection of ANY dimension fails the node before probing */
+    double *mids = (double *)malloc(sizeof(double) * (size_t)n);
+    for (int d = 0; d < n; ++d) {
+        philox_draw(m->seed, STREAM_MISER, node, ctl | (int64_t)(1 + d), 0u, w);
+        const double r = orc_u01(w[0], w[1]) * (m->dither - (-m->dither)) + (-m->dither);
+        const double delta = to[d] - from[d];
+        mids[d] = from[d] + delta * (0.5 + r);                         /* :364-365 */
+        if (!uniform_ok(from[d], mids[d]) || !uniform_ok(mids[d], to[d])) { free(mids); return ORC_ERR_EXTERNAL; }
+    }
+    for (int d = 0; d < n; ++d) {
+        const double mid = mids[d], old_from = from[d], old_to = to[d];
+        double mean, variance_lower, variance_upper;
+        to[d] = mid;                                                   /* lower_d_sampler, :366 */
+        int st = miser_batch(m, from, to, sample_count, node, (int64_t)(2 * d) << 40, 1, &mean, &variance_lower);
+        to[d] = old_to;
+        if (!st) {
+            from[d] = mid;                                             /* upper_d_sampler, :367 */
+            st = miser_batch(m, from, to, sample_count, node, (int64_t)(2 * d + 1) << 40, 1, &mean, &variance_upper);
+            from[d] = old_from;
+        }
+        if (st) { free(mids); return st; }
+        const double total_variance = variance_lower + variance_upper;
+        if (total_variance < best_variance) {                          /* :396-402 */
+            best_variance = total_variance;
+            best_lower_variance = variance_lower;
+            best_upper_variance = variance_upper;
+            best_dimension = d;
+            best_mid = mid;
+        }
+    }
+    free(mids);
+    const double old_from = from[best_dimension], old_to = to[best_dimension];
+    const double beta = 1.0 / (1.0 + m->alpha);                        /* :407 */
+    const double la = pow(best_lower_variance, beta), ua = pow(best_upper_variance, beta);
+    const double sum = la + ua;
+    int64_t lower_count, upper_count;
+    if (!to_usize((double)sample_count * (la / sum), &lower_count)) return ORC_ERR_TYPE_CONVERSION; /* :413-415 */
+    if (!to_usize((double)sample_count * (ua / sum), &upper_count)) return ORC_ERR_TYPE_CONVERSION; /* :417-419 */
+    double lm, lv, um, uv;
+    to[best_dimension] = best_mid;                                     /* :422-431 */
+    int st = miser_recurse(m, from, to, 2 * node, depth_remaining - 1, lower_count, &lm, &lv);
+    to[best_dimension] = old_to;
+    if (st) return st;
+    from[best_dimension] = best_mid;                                   /* :433-440 */
+    st = miser_recurse(m, from, to, 2 * node + 1, depth_remaining - 1, upper_count, &um, &uv);
+    from[best_dimension] = old_from;
+    if (st) return st;
+    *mean_out = lm + um;                                               /* MeanVariance::add, :442 */
+    *var_out = lv + uv;
+    return ORC_OK;
+}
+
+int orc_miser_integrate(int integrand_id, int n, int64_t sample_count, int maximum_depth, int64_t min_dim_count,
+                        double alpha, double dither, const double *from, const double *to, uint64_t seed,
+                        double *mean_out, double *variance_out, int64_t *evals_out)
+{
+    if (n <= 0 || maximum_depth < 0 || maximum_depth > 30) return ORC_ERR_INCORRECT_INPUT;
+    miser_cfg m = {integrand_id, n, min_dim_count, alpha, dither, seed, 0};
+    double *f = (double *)malloc(sizeof(double) * (size_t)n), *t = (double *)malloc(sizeof(double) * (size_t)n);
+    memcpy(f, from, sizeof(double) * (size_t)n);
+    memcpy(t, to, sizeof(double) * (size_t)n);
+    int st = miser_recurse(&m, f, t, 1u, maximum_depth, sample_count, mean_out, variance_out);
+    if (evals_out) *evals_out = m.evals;
+    free(f); free(t);
+    return st;
 }
 
 /* ============================== all-cores variant =============================== */

@@ -173,6 +173,12 @@ int orc_mc_integrate(int integrand_id, int n, int64_t count, const double *from,
                      const double *replay_u, double *mean, double *variance);
 void orc_mc_draws(uint64_t seed, int64_t index, int n, double *u);
 
+/* ---- MISER (src/integrators/miser.rs:270-443), recursion exactly as miser_recurse :301-443; the draw counters are
+ * described in eqs_oracle.c.  evals: integrand evaluations spent (may be NULL).  returns a status. */
+int orc_miser_integrate(int integrand_id, int n, int64_t sample_count, int maximum_depth, int64_t min_dim_count,
+                        double alpha, double dither, const double *from, const double *to, uint64_t seed,
+                        double *mean, double *variance, int64_t *evals);
+
 double orc_time_pso_steps(orc_pso *s, int64_t iters);
 /* all-cores variant of a synchronous pass (threads over particles), bit-identical to orc_pso_step */
 int orc_pso_step_mt(orc_pso *s, int threads);

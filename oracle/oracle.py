@@ -156,6 +156,17 @@ def mc_integrate(integrand_id, lower, upper, sample_count=1000, seed=0, replay_u
     return int(st), m.value, v.value
 
 
+def miser_integrate(integrand_id, lower, upper, sample_count=1000, maximum_depth=5, min_dim_count=32, alpha=2.0,
+                    dither=0.05, seed=0):
+    """MISER::integrate_with_rng (reference miser.rs:270-443): returns (status, mean, variance, evals)."""
+    lo, plo = _d(lower); hi, phi = _d(upper)
+    m, v, e = C.c_double(0), C.c_double(0), C.c_int64(0)
+    st = lib().orc_miser_integrate(C.c_int(int(integrand_id)), C.c_int(int(lo.size)), C.c_int64(sample_count),
+                                   C.c_int(maximum_depth), C.c_int64(min_dim_count), C.c_double(alpha),
+                                   C.c_double(dither), plo, phi, C.c_uint64(seed), C.byref(m), C.byref(v), C.byref(e))
+    return int(st), m.value, v.value, int(e.value)
+
+
 class Pso:
     """Step-granular oracle ParticleSwarm (reference particle_swarm.rs:356-431)."""
 

@@ -96,6 +96,22 @@ pub struct eqs_mc_params {
 }
 
 #[repr(C)]
+#[derive(Clone, Copy)]
+pub struct eqs_miser_params {
+    pub n: i32,
+    pub integrand_id: i32,
+    pub sample_count: i64,
+    pub minimum_dimensional_sample_count: i64,
+    pub maximum_depth: i32,
+    pub reserved: i32,
+    pub alpha: c_double,
+    pub dither: c_double,
+    pub from: *const c_double,
+    pub to: *const c_double,
+    pub seed: u64,
+}
+
+#[repr(C)]
 #[derive(Clone, Copy, Default)]
 pub struct eqs_report {
     pub iters_run: i64,
@@ -172,4 +188,8 @@ extern "C" {
     pub fn eqs_mc_validate(p: *const eqs_mc_params) -> c_int;
     pub fn eqs_mc_integrate(ctx: *mut eqs_ctx, p: *const eqs_mc_params, mean: *mut c_double, variance: *mut c_double,
                             report: *mut eqs_report) -> c_int;
+
+    pub fn eqs_miser_validate(p: *const eqs_miser_params) -> c_int;
+    pub fn eqs_miser_integrate(ctx: *mut eqs_ctx, p: *const eqs_miser_params, mean: *mut c_double, variance: *mut c_double,
+                               report: *mut eqs_report) -> c_int;
 }

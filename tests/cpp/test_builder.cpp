@@ -73,6 +73,9 @@ static int gpu_tests()
         CHECK(g.is_ok() && std::fabs(g.unwrap() - 0.746824132812427025) <= 0.1);
         auto sc = MonteCarlo(Objective::SinCos).with_context(ctx).with_sample_count(1 << 20).integrate_with_seed({0.0, 0.0}, {1.0, 1.0}, 7);
         CHECK(sc.is_ok() && std::fabs(sc.unwrap().mean - 0.9248464799519) <= 1e-2);
+        // tests/integrators.rs:108-116
+        auto mi = eqsolver::integrators::MISER(Objective::SinCos).with_context(ctx).integrate_with_seed({0.0, 0.0}, {1.0, 1.0}, 1729);
+        CHECK(mi.is_ok() && std::fabs(mi.unwrap().mean - 0.9248464799519) <= 0.001);
         auto bad = MonteCarlo(Objective::Gaussian).with_context(ctx).integrate({1.0}, {0.0});
         CHECK(!bad.is_ok() && bad.unwrap_err().kind == SolverError::ExternalError);
     }

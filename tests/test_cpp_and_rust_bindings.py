@@ -40,7 +40,7 @@ def test_rust_extern_block_matches_header():
     assert rust == header_symbols()
     # struct field order of the #[repr(C)] mirrors == the C structs
     hdr = open(os.path.join(ROOT, "include", "eqsolver_b200.h")).read()
-    for name in ("eqs_pso_params", "eqs_ce_params", "eqs_mc_params", "eqs_report"):
+    for name in ("eqs_pso_params", "eqs_ce_params", "eqs_mc_params", "eqs_miser_params", "eqs_report"):
         c_body = re.search(r"typedef struct \{([^{}]*)\} %s;" % name, hdr).group(1)
         c_body = re.sub(r"/\*.*?\*/", "", c_body, flags=re.S)
         c_fields = []

@@ -191,3 +191,69 @@ def test_all_cores_pass_is_bit_identical_to_the_scalar_pass():
     c = O.Pso(O.ROSENBROCK, lower, upper, particle_count=N, tol=0.0, mode=O.SEQUENTIAL, seed=11)
     c.init(x0)
     assert c.step_mt(4) == -1      # the reference's sequential gbest semantics cannot be threaded
+
+
+def test_miser_oracle_against_pure_python_recursion():
+    """orc_miser_integrate (miser.rs:301-443) against a pure-Python restatement of the recursion, bit for bit, plus
+    the reference's own acceptance test (tests/integrators.rs:108-116: |mean - 0.924846| <= 0.001 at the defaults)."""
+    import math
+    seed, n, min_dim, alpha, dither = 1729, 2, 32, 2.0, 0.05
+    key = [seed & 0xFFFFFFFF, seed >> 32]
+    spent = [0]
+
+    def draw(node, gidx, j):
+        w = O.philox4x32_10([gidx & 0xFFFFFFFF, gidx >> 32, (4 << 28) | j, node], key)
+        return O.u01(int(w[0]), int(w[1])), O.u01(int(w[2]), int(w[3]))
+
+    def batch(lo, hi, count, node, gbase, bessel):
+        mean = ssq = 0.0
+        for i in range(count):
+            u0, u1 = draw(node, gbase | i, 0)
+            x0, x1 = u0 * (hi[0] - lo[0]) + lo[0], u1 * (hi[1] - lo[1]) + lo[1]
+            s = math.sin(math.cos(x1) + x0)
+            d = s - mean
+            mean = mean + d / float(i + 1)
+            ssq = ssq + d * (s - mean)
+        spent[0] += count
+        return mean, ssq / float(count - 1 if bessel else count)
+
+    def recurse(lo, hi, node, depth, count):
+        if depth == 0 or count < min_dim * n:
+            count = max(count, min_dim * n)
+            vol = 1.0
+            for d in range(n):
+                vol = vol * (hi[d] - lo[d])
+            m, v = batch(lo, hi, count, node, (2 * n + 1) << 40, False)
+            return m * vol, v * vol * vol
+        count = max(count, 2)
+        best = (1.7976931348623157e308,) * 3
+        bd = min(n - 1, int(draw(node, (2 * n) << 40, 0)[0] * n))
+        bmid = lo[bd] + (hi[bd] - lo[bd]) * 0.5
+        for d in range(n):
+            r = draw(node, ((2 * n) << 40) | (1 + d), 0)[0] * (dither - (-dither)) + (-dither)
+            mid = lo[d] + (hi[d] - lo[d]) * (0.5 + r)
+            h2 = list(hi); h2[d] = mid
+            l2 = list(lo); l2[d] = mid
+            vl = batch(lo, h2, count, node, (2 * d) << 40, True)[1]
+            vu = batch(l2, hi, count, node, (2 * d + 1) << 40, True)[1]
+            if vl + vu < best[0]:
+                best, bd, bmid = (vl + vu, vl, vu), d, mid
+        beta = 1.0 / (1.0 + alpha)
+        la, ua = best[1] ** beta, best[2] ** beta
+        nl, nu = int(float(count) * (la / (la + ua))), int(float(count) * (ua / (la + ua)))
+        h2 = list(hi); h2[bd] = bmid
+        l2 = list(lo); l2[bd] = bmid
+        a = recurse(lo, h2, 2 * node, depth - 1, nl)
+        b = recurse(l2, hi, 2 * node + 1, depth - 1, nu)
+        return a[0] + b[0], a[1] + b[1]
+
+    want = recurse([0.0, 0.0], [1.0, 1.0], 1, 3, 400)
+    st, mean, var, evals = O.miser_integrate(O.SINCOS, [0.0, 0.0], [1.0, 1.0], sample_count=400, maximum_depth=3, seed=seed)
+    assert st == 0 and evals == spent[0]
+    assert_bit_equal([mean, var], list(want))
+    st, mean, var, _ = O.miser_integrate(O.SINCOS, [0.0, 0.0], [1.0, 1.0], seed=1729)
+    assert st == 0 and abs(mean - 0.9248464799519) <= 0.001
+    assert O.miser_integrate(O.SPHERE, [0.0, 0.0], [1.0, -1.0])[0] == O.ERR_EXTERNAL
+    assert O.miser_integrate(O.SPHERE, [0.0, 0.0], [0.0, 0.0])[0] == O.ERR_TYPE_CONVERSION
+    assert O.miser_integrate(O.SPHERE, [0.0, 0.0], [1.0, 1.0], min_dim_count=0, sample_count=1, maximum_depth=0)[0] \
+        == O.ERR_INCORRECT_INPUT
