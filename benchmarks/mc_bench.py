@@ -44,6 +44,41 @@ def main():
         out["cpu_oracle_samples_per_s"] = cpu_count / (time.perf_counter() - t0)
         print(json.dumps(out))
 
+    # the reference's own integrator benchmark group, benchmarks/integrators.rs:67-78 "1D Heavy Integrators":
+    # MonteCarlo::new(f).integrate(0., 0.5) at the default 1000 samples, f = sum_{i<1000} (-1)^i x^i
+    def best_of(fn, reps=a.reps):
+        fn()
+        best = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+        return best
+    mc = E.MonteCarlo.new(E.Objective.SERIES).with_context(ctx)
+    group = {"group": "1D Heavy Integrators (benchmarks/integrators.rs:67-78)", "exact": 0.4054651081081644}
+    group["Monte Carlo"] = {"gpu_ms": 1e3 * best_of(lambda: mc.integrate(0.0, 0.5)),
+                            "cpu_oracle_ms": 1e3 * best_of(lambda: O.mc_integrate(O.SERIES, [0.0], [0.5], 1000, 1), 2),
+                            "mean": mc.integrate(0.0, 0.5)}
+    mi = E.MISER.new(E.Objective.SERIES).with_context(ctx)
+    group["MISER"] = {"gpu_ms": 1e3 * best_of(lambda: mi.integrate(0.0, 0.5)),
+                      "cpu_oracle_ms": 1e3 * best_of(lambda: O.miser_integrate(O.SERIES, [0.0], [0.5]), 2),
+                      "mean": mi.integrate(0.0, 0.5), "evals": mi.last_report.evals, "levels": mi.last_report.iters_run}
+    print(json.dumps(group))
+    # MISER at the reference test's shape (tests/integrators.rs:108-116) and at GPU-sized point counts
+    for count in (1000, 1 << 20, 1 << 24):
+        mi = E.MISER.new(E.Objective.SINCOS).with_sample_count(count).with_context(ctx)
+        t = best_of(lambda: mi.integrate_with_seed([0.0, 0.0], [1.0, 1.0], 3))
+        r = mi.integrate_with_seed([0.0, 0.0], [1.0, 1.0], 3)
+        row = {"miser": "sincos_2d", "sample_count": count, "wall_ms": 1e3 * t, "kernel_ms": mi.last_report.loop_ms,
+               "evals": mi.last_report.evals, "evals_per_s": mi.last_report.evals / t, "error": r.mean - 0.9248464799519,
+               "sigma": r.variance ** 0.5}
+        if count <= (1 << 20):
+            cc = min(count, 1 << 16)
+            t0 = time.perf_counter()
+            ev = O.miser_integrate(O.SINCOS, [0.0, 0.0], [1.0, 1.0], sample_count=cc, seed=3)[3]
+            row["cpu_oracle_evals_per_s"] = ev / (time.perf_counter() - t0)
+        print(json.dumps(row))
+
 
 if __name__ == "__main__":
     main()

@@ -1,0 +1,47 @@
+#!/usr/bin/env python3
+"""ParticleSwarm in SEQUENTIAL_EXACT mode (the reference's in-loop gbest semantics, particle_swarm.rs:399-427) next to
+the synchronous mode on one GPU: particle-evals/s and the repair overhead, C2 shape by default.
+
+    python benchmarks/seq_bench.py [--n 32] [--particles 1048576] [--objective ROSENBROCK] [--iters 40]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=32)
+    ap.add_argument("--particles", type=int, default=1 << 20)
+    ap.add_argument("--objective", default="ROSENBROCK")
+    ap.add_argument("--iters", type=int, default=40)
+    ap.add_argument("--lower", type=float, default=-5.0)
+    ap.add_argument("--upper", type=float, default=10.0)
+    a = ap.parse_args()
+    import eqsolver_b200 as E
+    ctx = E.Context(0)
+    out = {"workload": f"ParticleSwarm {a.objective.lower()} n={a.n}, {a.particles} particles, {a.iters} passes"}
+    for mode in (E.PsoMode.SYNCHRONOUS, E.PsoMode.SEQUENTIAL_EXACT):
+        ps = (E.ParticleSwarm.new(getattr(E.Objective, a.objective), [a.lower] * a.n, [a.upper] * a.n)
+              .with_particle_count(a.particles).with_tol(0.0).with_seed(1729).with_mode(mode).with_context(ctx))
+        run = ps.start(np.zeros(a.n))
+        run.step(3)
+        run.sync()
+        run.step(a.iters)
+        run.sync()
+        ms, launches = run.last_step_ms()
+        g, cost, it, stalled, imp = run.gbest()
+        out[mode.name.lower()] = {"evals_per_s": a.particles * a.iters / (ms * 1e-3), "ms_per_pass": ms / a.iters,
+                                  "launches_per_pass": launches / a.iters, "gbest_cost": cost}
+        run.close()
+    out["sequential_over_synchronous_time"] = out["sequential_exact"]["ms_per_pass"] / out["synchronous"]["ms_per_pass"]
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

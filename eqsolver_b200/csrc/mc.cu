@@ -127,7 +127,10 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(MC_BLOCK) mc
 
 // ---- MISER (miser.rs:301-443): all Welford batches (variance probes and leaves) of one recursion level ------------
 
-constexpr int MS_BLOCK = 256, MS_SPT = 4, MS_CHUNK = MS_BLOCK * MS_SPT;
+constexpr int MS_BLOCK = 256;
+// points per thread and chunk: a function of the batch size alone (small batches spread over more CTAs)
+__host__ __device__ inline int miser_spt(long long count) { return count <= 65536 ? 1 : 4; }
+__host__ __device__ inline long long miser_chunk(long long count) { return (long long)MS_BLOCK * miser_spt(count); }
 constexpr uint32_t STREAM_MISER = 4u;
 
 struct MiserBatch {      // `count` points uniform in the node's region, dimension d narrowed to one half (d < 0: leaf)
@@ -160,7 +163,7 @@ __device__ __forceinline__ Moments shfl_down(const Moments &m, int o)
     return b;
 }
 
-// one CTA per chunk of MS_CHUNK points (grid-stride); the partition into chunks, threads and merge order depends on
+// one CTA per chunk of miser_chunk(count) points (grid-stride); the partition into chunks, threads and merge order depends on
 // the batch sizes only, never on the grid, so a level is bit-reproducible
 template <class Obj> __global__ void __launch_bounds__(MS_BLOCK) miser_chunk_kernel(const MiserDev P)
 {
@@ -191,9 +194,10 @@ template <class Obj> __global__ void __launch_bounds__(MS_BLOCK) miser_chunk_ker
         }
         __syncthreads();
         Moments m{0.0, 0.0, 0.0};
-        const long long base = (chunk - B.chunk0) * MS_CHUNK;
+        const int spt = miser_spt(B.count);
+        const long long base = (chunk - B.chunk0) * ((long long)MS_BLOCK * spt);
 #pragma unroll 1
-        for (int k = 0; k < MS_SPT; ++k) {
+        for (int k = 0; k < spt; ++k) {
             const long long i = base + (long long)k * MS_BLOCK + tid;
             if (i >= B.count) break;
             ObjAcc acc;
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(MS_BLOCK) miser_merge_kernel(const MiserDev P)
     const int b = (int)(((long long)blockIdx.x * MS_BLOCK + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (b >= P.nbatch) return;
     const MiserBatch B = P.batch[b];
-    const long long nch = (B.count + MS_CHUNK - 1) / MS_CHUNK, per = (nch + 31) / 32;
+    const long long csz = miser_chunk(B.count), nch = (B.count + csz - 1) / csz, per = (nch + 31) / 32;
     Moments m{0.0, 0.0, 0.0};
     for (long long c = lane * per; c < nch && c < (lane + 1) * per; ++c) m = merge(m, P.part[B.chunk0 + c]);
 #pragma unroll
@@ -490,7 +494,7 @@ int eqs_miser_integrate(eqs_ctx *ctx, const eqs_miser_params *p, double *mean, d
             b.upper = upper;
             b.node_id = id;
             batches.push_back(b);
-            nchunks += (count + MS_CHUNK - 1) / MS_CHUNK;
+            nchunks += (count + miser_chunk(count) - 1) / miser_chunk(count);
             evals += count;
         };
         for (size_t li = 0; li < level.size(); ++li) {

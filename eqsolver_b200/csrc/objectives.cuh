@@ -153,6 +153,32 @@ template <> struct Objective<EQS_OBJ_SINCOS> { // (v[1].cos() + v[0]).sin(), n =
     __device__ __forceinline__ static double end(const ObjAcc &s, int) { return s.a; }
 };
 
+// integrand of the reference's integrator benchmark (benchmarks/integrators.rs:69-75):
+// sum += (-1f64).powi(i) * x.powi(i) for i in 0..1000; powi with a run-time exponent is compiler-rt's __powidf2
+__device__ __forceinline__ double powi_rt(double a, int b)
+{
+    double r = 1.0;
+    for (;;) {
+        if (b & 1) r *= a;
+        b >>= 1;
+        if (b == 0) break;
+        a *= a;
+    }
+    return r;
+}
+template <> struct Objective<EQS_OBJ_SERIES> {
+    static constexpr bool streaming = true;
+    __device__ __forceinline__ static void begin(ObjAcc &s, int) { s.a = 0.0; }
+    __device__ __forceinline__ static void feed(ObjAcc &s, double x, int)
+    {
+        double sum = 0.0;
+#pragma unroll 4 // four independent square-and-multiply chains in flight; the sum itself stays in order
+        for (int i = 0; i < 1000; ++i) sum += powi_rt(-1.0, i) * powi_rt(x, i);
+        s.a += sum;
+    }
+    __device__ __forceinline__ static double end(const ObjAcc &s, int) { return s.a; }
+};
+
 } // inline namespace
 } // namespace eqs
 
@@ -189,6 +215,7 @@ template <class F> inline bool dispatch_objective(int id, F &&f)
     case EQS_OBJ_ACKLEY: f.template operator()<Objective<EQS_OBJ_ACKLEY>>(); return true;
     case EQS_OBJ_THREE_CIRCLES: f.template operator()<Objective<EQS_OBJ_THREE_CIRCLES>>(); return true;
     case EQS_OBJ_HEAVY: f.template operator()<Objective<EQS_OBJ_HEAVY>>(); return true;
+    case EQS_OBJ_SERIES: f.template operator()<Objective<EQS_OBJ_SERIES>>(); return true;
     case EQS_OBJ_USER: f.template operator()<Objective<EQS_OBJ_USER>>(); return true;
     case EQS_OBJ_GAUSSIAN: f.template operator()<Objective<EQS_OBJ_GAUSSIAN>>(); return true;
     case EQS_OBJ_SINCOS: f.template operator()<Objective<EQS_OBJ_SINCOS>>(); return true;

@@ -40,6 +40,7 @@ class Objective(enum.IntEnum):
     USER = 6
     GAUSSIAN = 7       # exp(-sum x^2), tests/integrators.rs:11-13
     SINCOS = 8         # sin(cos(x1) + x0), tests/integrators.rs:15-17
+    SERIES = 9         # sum_{i<1000} (-1)^i x^i, benchmarks/integrators.rs:69-75
 
 
 class PsoMode(enum.IntEnum):

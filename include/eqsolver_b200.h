@@ -52,7 +52,8 @@ typedef enum {
     EQS_OBJ_USER = 6,          /* eqsolver_b200/csrc/user_objective.cuh, rebuilt by the user */
     EQS_OBJ_GAUSSIAN = 7,      /* exp(-sum x^2): the integrand of tests/integrators.rs:11-13 (n = 1 there) */
     EQS_OBJ_SINCOS = 8,        /* sin(cos(x1) + x0), n = 2: tests/integrators.rs:15-17 */
-    EQS_OBJ_COUNT = 9
+    EQS_OBJ_SERIES = 9,        /* sum_i (-1)^i x^i, i < 1000, summed over the dimensions: benchmarks/integrators.rs:69-75 */
+    EQS_OBJ_COUNT = 10
 } eqs_objective;
 
 typedef enum {

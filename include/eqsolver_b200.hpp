@@ -23,7 +23,7 @@ namespace eqsolver {
 constexpr double DEFAULT_TOL = 1e-6;      // lib.rs:13
 constexpr int64_t DEFAULT_ITERMAX = 50;   // lib.rs:16
 
-enum class Objective : int32_t { Sphere = 0, Rosenbrock, Rastrigin, Ackley, ThreeCircles, Heavy, User, Gaussian, SinCos };
+enum class Objective : int32_t { Sphere = 0, Rosenbrock, Rastrigin, Ackley, ThreeCircles, Heavy, User, Gaussian, SinCos, Series };
 
 // SolverError, lib.rs:19-44
 struct SolverError {

@@ -25,6 +25,20 @@ static const double ORC_PI = 3.14159265358979323846; /* std::f64::consts::PI */
 /* x.powi(2) lowers to x*x. */
 static double sq(double x) { return x * x; }
 
+/* f64::powi with a run-time exponent = compiler-rt's __powidf2: square-and-multiply from the low bit up */
+static double powi(double a, int b)
+{
+    const int recip = b < 0;
+    double r = 1.0;
+    for (;;) {
+        if (b & 1) r *= a;
+        b /= 2;
+        if (b == 0) break;
+        a *= a;
+    }
+    return recip ? 1.0 / r : r;
+}
+
 double orc_objective(int id, const double *x, int n)
 {
     switch (id) {
@@ -98,6 +112,15 @@ double orc_objective(int id, const double *x, int n)
     }
     case ORC_OBJ_SINCOS: /* tests/integrators.rs:15-17: (v[1].cos() + v[0]).sin() */
         return sin(cos(x[1]) + x[0]);
+    case ORC_OBJ_SERIES: { /* benchmarks/integrators.rs:69-75: sum += (-1f64).powi(i) * x.powi(i), i in 0..1000 */
+        double total = 0.0;
+        for (int d = 0; d < n; ++d) {
+            double sum = 0.0;
+            for (int i = 0; i < 1000; ++i) sum += powi(-1.0, i) * powi(x[d], i);
+            total += sum;
+        }
+        return total;
+    }
     default:
         return NAN;
     }

@@ -38,7 +38,8 @@ enum {
     ORC_OBJ_HEAVY = 5,          /* reference benchmarks/multi.rs:106-115,137 */
     ORC_OBJ_USER = 6,           /* twin of the shipped user-hook example (Zakharov); not in the reference */
     ORC_OBJ_GAUSSIAN = 7,       /* exp(-sum x^2): reference tests/integrators.rs:11-13 for n = 1 */
-    ORC_OBJ_SINCOS = 8          /* sin(cos(x1) + x0), n = 2: reference tests/integrators.rs:15-17 */
+    ORC_OBJ_SINCOS = 8,         /* sin(cos(x1) + x0), n = 2: reference tests/integrators.rs:15-17 */
+    ORC_OBJ_SERIES = 9          /* sum_{i<1000} (-1)^i x^i per dimension: reference benchmarks/integrators.rs:69-75 */
 };
 
 /* Status codes = SolverError variants, reference src/lib.rs:19-44. */

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 
-SPHERE, ROSENBROCK, RASTRIGIN, ACKLEY, THREE_CIRCLES, HEAVY, USER, GAUSSIAN, SINCOS = range(9)
+SPHERE, ROSENBROCK, RASTRIGIN, ACKLEY, THREE_CIRCLES, HEAVY, USER, GAUSSIAN, SINCOS, SERIES = range(10)
 SEQUENTIAL, SYNCHRONOUS = 0, 1
 DIV_REFERENCE_TEN, DIV_ELITE_COUNT = 0, 1
 OK, ERR_MAX_ITER, ERR_NAN, ERR_INCORRECT_INPUT, ERR_BAD_JACOBIAN, ERR_TYPE_CONVERSION, ERR_EXTERNAL = range(7)

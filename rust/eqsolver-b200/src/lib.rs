@@ -49,6 +49,8 @@ pub enum Objective {
     Gaussian = 7,
     /// sin(cos(x1) + x0): tests/integrators.rs:15-17
     SinCos = 8,
+    /// sum over i < 1000 of (-1)^i x^i: the integrand of eqsolver's benchmarks/integrators.rs:69-75
+    Series = 9,
 }
 
 /// One GPU: stream, device memory arena, NCCL communicator.  Cheap to clone (shared).

@@ -24,6 +24,7 @@ pub const EQS_OBJ_HEAVY: i32 = 5;
 pub const EQS_OBJ_USER: i32 = 6;
 pub const EQS_OBJ_GAUSSIAN: i32 = 7;
 pub const EQS_OBJ_SINCOS: i32 = 8;
+pub const EQS_OBJ_SERIES: i32 = 9;
 
 pub const EQS_PSO_SEQUENTIAL_EXACT: i32 = 0;
 pub const EQS_PSO_SYNCHRONOUS: i32 = 1;

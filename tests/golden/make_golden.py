@@ -92,7 +92,40 @@ def zakharov(x):
     return s1 + q + q * q
 
 
-OBJECTIVES = {0: sphere, 1: rosenbrock, 2: rastrigin, 3: ackley, 4: three_circles, 5: heavy, 6: zakharov}
+def gaussian(x):  # tests/integrators.rs:11-13, squares summed over the dimensions
+    s2 = 0.0
+    for w in x:
+        s2 += w * w
+    return math.exp(-s2)
+
+
+def sincos(x):  # tests/integrators.rs:15-17
+    return math.sin(math.cos(x[1]) + x[0])
+
+
+def powi(a, b):  # f64::powi with a run-time exponent (compiler-rt __powidf2), b >= 0
+    r = 1.0
+    while True:
+        if b & 1:
+            r *= a
+        b //= 2
+        if b == 0:
+            return r
+        a *= a
+
+
+def series(x):  # benchmarks/integrators.rs:69-75
+    total = 0.0
+    for w in x:
+        s = 0.0
+        for i in range(1000):
+            s += powi(-1.0, i) * powi(w, i)
+        total += s
+    return total
+
+
+OBJECTIVES = {0: sphere, 1: rosenbrock, 2: rastrigin, 3: ackley, 4: three_circles, 5: heavy, 6: zakharov,
+              7: gaussian, 8: sincos, 9: series}
 
 
 # ---------------------------------------------------------------- Philox4x32-10
@@ -230,6 +263,11 @@ def main():
         (5, [0.3] * 100, "benchmarks/multi.rs:129 init (Heavy)"),
         (6, [1.0, 1.0, 1.0], "zakharov (shipped user hook example)"),
         (6, [0.25, -0.5, 0.75, 1.5], "zakharov"),
+        (7, [0.5], "gaussian, tests/integrators.rs:11"),
+        (7, [0.25, -1.5, 0.75], "gaussian, 3-D"),
+        (8, [0.3, 0.9], "sin(cos y + x), tests/integrators.rs:15"),
+        (9, [0.25], "alternating power series, benchmarks/integrators.rs:69 (1/(1+x) = 0.8)"),
+        (9, [0.5, 0.125], "alternating power series, 2-D sum"),
     ]
     obj = [dict(objective=o, x=x, value=repr(OBJECTIVES[o](x)), bits=bits(OBJECTIVES[o](x)), note=note)
            for o, x, note in kat_points]

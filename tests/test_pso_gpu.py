@@ -18,7 +18,7 @@ def test_objective_kats(ctx):
     for e in golden("objective_kats.json"):
         got = ctx.objective_eval(e["objective"], e["x"])[0]
         want = from_bits(e["bits"])
-        if e["objective"] in (2, 3):  # cos/exp: libdevice vs glibc, <= a few ulp of the summands
+        if e["objective"] in (2, 3, 7, 8):  # cos/exp/sin: libdevice vs glibc, <= a few ulp of the summands
             assert abs(got - want) <= 1e-12 * max(1.0, abs(want)) + 1e-13, e["note"]
         else:
             assert_bit_equal([got], [want], e["note"])
