@@ -353,6 +353,13 @@ template <class Obj> __global__ void pso_x0_kernel(const PsoDev P)
     c->pass_done = 0;
     c->block_counter = 0;
     c->p2p_timeout = 0;
+    c->seq_start = 0;
+    c->seq_commit_lo = 1;
+    c->seq_commit_hi = 0;
+    c->seq_window = 0;
+    c->seq_target = 0;
+    c->seq_parity = 0;
+    c->seq_commit_buf = 0;
 }
 
 // :361-389 without the (order-dependent) gbest bookkeeping, which pso_ring_scan_kernel reconstructs
@@ -636,6 +643,121 @@ __global__ void __launch_bounds__(PSO_BLOCK) pso_commit_kernel(const PsoDev P, l
     }
 }
 
+// Sequential-exact mode on one rank, device-driven.  A round speculates only a WINDOW of particles [start, start + W)
+// against the current gbest: A = the committed (x, v), B = the other buffer pair, A -> B.  The last CTA finds the first
+// improving particle i* of the window (none: the whole window is final), moves gbest (:420-425), records [start, i*]
+// as final and advances start; the NEXT launch performs the pbest update (:417-419) of that range before it speculates.
+// When start reaches N the pass is over: iter + 1, stall test, and A / B swap roles -- nothing is copied.  A repair
+// therefore costs at most one window instead of the rest of the population, and no host round trip is needed: the
+// host only enqueues launches (no-ops once iter == seq_target).  With k improvements per pass, a fixed cost c_r per
+// round and c_p per particle, a pass costs (N/W + k/2) c_r + (N + k W/2) c_p, least at W = sqrt(2 N c_r / (k c_p)):
+// W is re-chosen after every pass from a running estimate of k (measured: profiles/r01_sweep.md).
+__global__ void pso_seq_arm_kernel(const PsoDev P, long long iters, long long wmin, long long wmax, long long w0, double wscale)
+{
+    PsoCtrl *c = P.ctrl;
+    c->seq_target = c->iter + iters;
+    c->seq_wmin = wmin;
+    c->seq_wmax = wmax;
+    c->seq_wscale = wscale;
+    if (c->seq_window == 0) { // first use after init
+        c->seq_window = w0;
+        c->seq_imp0 = c->improvements;
+        c->seq_kest = 4.0;
+    }
+    if (c->seq_window < wmin) c->seq_window = wmin;
+    if (c->seq_window > wmax) c->seq_window = wmax;
+}
+
+template <class Obj, bool REPLAY>
+__global__ void __launch_bounds__(PSO_BLOCK) pso_seqw_kernel(const PsoDev P)
+{
+    extern __shared__ double sG[];
+    __shared__ MinLoc s_red[32];
+    __shared__ int s_found;
+    PsoCtrl *ctrl = P.ctrl;
+    const long long clo = ctrl->seq_commit_lo, chi = ctrl->seq_commit_hi;
+    const int cbuf = ctrl->seq_commit_buf, parity = ctrl->seq_parity;
+    const bool active = !ctrl->stalled && ctrl->iter < ctrl->seq_target;
+    const long long start = ctrl->seq_start, W = ctrl->seq_window, N = P.nloc;
+    const uint32_t t = (uint32_t)ctrl->iter;
+    const double Gc = ctrl->Gc;
+    if (!active && clo > chi) return; // uniform over the grid: nothing pending, nothing to do
+    const long long stride = (long long)gridDim.x * blockDim.x, gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // particle li is always handled by thread li mod stride, so a particle's pending commit precedes its speculation
+    auto first_at = [&](long long lo) {
+        long long r = (gtid - lo) % stride;
+        if (r < 0) r += stride;
+        return lo + r;
+    };
+    if (clo <= chi) { // :417-419 for the particles the previous round made final
+        const double *src = cbuf ? P.x2 : P.x;
+        const int nq = (P.n + 3) >> 2;
+        for (long long li = first_at(clo); li <= chi; li += stride) {
+            const double c = P.cost[li];
+            if (c < P.pbc[li]) {
+                P.pbc[li] = c;
+                for (int q = 0; q < nq; ++q) {
+                    const long long off = goff(P, q, li);
+                    st256(P.pb + off, ld256(src + off));
+                }
+            }
+        }
+    }
+    MinLoc first{0.0, kNoIndex}; // min over the index only
+    const long long wend = start + W < N ? start + W : N;
+    if (active) {
+        load_gbest(P, sG);
+        const double *xa = parity ? P.x2 : P.x, *va = parity ? P.v2 : P.v;
+        double *xb = parity ? P.x : P.x2, *vb = parity ? P.v : P.v2;
+        for (long long li = first_at(start); li < wend; li += stride) {
+            const double cost = pso_move<Obj, REPLAY>(P, t, li, sG, xa, va, P.pb, xb, vb, true);
+            P.cost[li] = cost;
+            if (cost < Gc && li < first.i) first.i = li; // :417,:420 (cost < Gc implies cost < pbest cost)
+        }
+    }
+    MinLoc win;
+    if (!grid_minloc_last_block(P, first, s_red, win)) return;
+    if (threadIdx.x == 0) {
+        PsoCtrl *c = ctrl;
+        int found = 0;
+        if (active) {
+            found = win.i != kNoIndex;
+            const long long hi = found ? win.i : wend - 1;
+            c->seq_commit_lo = start;
+            c->seq_commit_hi = hi;
+            c->seq_commit_buf = parity ^ 1;
+            if (found) { // :420-425
+                ring_push(c, c->Gc);
+                c->Gc = __ldcg(P.cost + win.i);
+                c->improvements += 1;
+            }
+            if (hi + 1 >= N) { // the pass is complete
+                c->iter += 1;
+                c->stalled = stall_test(c, P.tol);
+                c->seq_start = 0;
+                c->seq_parity = parity ^ 1;
+                c->seq_kest = 0.5 * c->seq_kest + 0.5 * (double)(c->improvements - c->seq_imp0);
+                c->seq_imp0 = c->improvements;
+                const double w = sqrt(c->seq_wscale * (double)N / fmax(c->seq_kest, 0.02));
+                long long wn = w < 9.0e18 ? (long long)w : c->seq_wmax;
+                wn = wn < c->seq_wmin ? c->seq_wmin : wn;
+                c->seq_window = wn > c->seq_wmax ? c->seq_wmax : wn;
+            } else {
+                c->seq_start = hi + 1;
+            }
+        } else {
+            c->seq_commit_lo = 1;
+            c->seq_commit_hi = 0;
+        }
+        s_found = found;
+    }
+    __syncthreads();
+    if (s_found) { // gbest <- the improving particle's speculated position (buffer B)
+        const double *xb = parity ? P.x : P.x2;
+        for (int d = threadIdx.x; d < P.n; d += blockDim.x) P.G[d] = __ldcg(xb + goff(P, d >> 2, win.i) + (d & 3));
+    }
+}
+
 // K8: small populations (nloc <= PSO_SMALL_MAX, one rank).  The reference's own shapes -- 100 particles x 50 passes
 // (benchmarks/multi.rs:70-84), 1000 x 1000 (BASELINE config 1) -- fit on ONE SM, and a pass is a few microseconds, so
 // kernel launches and host round trips are the whole cost.  One CTA therefore runs `iters` passes back to back: same
@@ -895,6 +1017,10 @@ int PsoSolver::create(const eqs_pso_params *p)
     memset(h_ctrl_, 0, sizeof(PsoCtrl));
     EQS_CUDA(ctx_, cudaEventCreate(&ev0_));
     EQS_CUDA(ctx_, cudaEventCreate(&ev1_));
+    // sequential mode on one rank beyond the single-CTA kernel's reach: device-driven windowed rounds
+    // (EQS_PSO_SEQ_HOST=1 keeps the host-driven whole-suffix rounds, which ranks > 1 always use)
+    seq_windowed_ = p->mode == EQS_PSO_SEQUENTIAL_EXACT && d_.world == 1 && !manual_ && d_.nloc > PSO_SMALL_MAX &&
+                    !getenv("EQS_PSO_SEQ_HOST");
     return EQS_OK;
 }
 
@@ -1065,6 +1191,60 @@ int PsoSolver::sequential_pass()
     return EQS_OK;
 }
 
+// `iters` passes of the sequential mode as device-driven windowed rounds (pso_seqw_kernel).  The host enqueues launches
+// in batches and looks at the control block between batches; launches past the target are no-ops.
+int PsoSolver::sequential_windowed(int64_t iters)
+{
+    const bool replay = d_.replay != nullptr;
+    const size_t smem = (size_t)((d_.n + 3) / 4) * 4 * sizeof(double);
+    int rc = EQS_OK;
+    auto launch = [&](int count) {
+        dispatch_objective(p_.objective_id, [&]<class Obj>() {
+            auto run = [&](auto kernel) {
+                if (grid_seqw_ == 0) {
+                    rc = persistent_grid(ctx_, kernel, PSO_BLOCK, smem, PSO_BLOCK, d_.nloc, grid_seqw_);
+                    if (rc != EQS_OK) return;
+                }
+                for (int k = 0; k < count; ++k) kernel<<<grid_seqw_, PSO_BLOCK, smem, ctx_->stream>>>(d_);
+                launches_ += count;
+            };
+            if (replay) run(pso_seqw_kernel<Obj, true>);
+            else run(pso_seqw_kernel<Obj, false>);
+        });
+    };
+    launch(0); // sizes the grid
+    EQS_TRY(rc);
+    // a round costs about 11 us beyond its particles (launch, tail, last-CTA reduction; measured on B200) and a
+    // particle (40n + 16) B of HBM traffic at ~5.7 TB/s
+    const long long wave = (long long)grid_seqw_ * PSO_BLOCK;
+    long long wmin = std::min<long long>(8192, wave), wmax = std::max<long long>(d_.nloc, wmin), w0 = std::min(wave, wmax);
+    const double wscale = 2.0 * 11.0 * 5.7e6 / (40.0 * d_.n + 16.0);
+    if (const char *e = getenv("EQS_PSO_SEQ_WINDOW")) wmin = wmax = w0 = std::max<long long>(1, atoll(e));
+    EQS_TRY(fetch_ctrl());
+    if (h_ctrl_->stalled) return EQS_OK;
+    const long long target = h_ctrl_->iter + iters;
+    pso_seq_arm_kernel<<<1, 1, 0, ctx_->stream>>>(d_, (long long)iters, wmin, wmax, w0, wscale);
+    launches_++;
+    for (;;) {
+        const long long left = target - h_ctrl_->iter;
+        const bool pending = h_ctrl_->seq_commit_lo <= h_ctrl_->seq_commit_hi;
+        if (left <= 0 || h_ctrl_->stalled) {
+            if (pending) launch(1); // the last round's pbest update
+            EQS_TRY(rc);
+            break;
+        }
+        const int batch = (int)std::min<double>(96.0, std::max<double>(4.0, seq_rounds_per_pass_ * (double)left + 1.0));
+        const long long it0 = h_ctrl_->iter;
+        launch(batch);
+        EQS_TRY(rc);
+        EQS_CUDA(ctx_, cudaGetLastError());
+        EQS_TRY(fetch_ctrl());
+        const long long done = h_ctrl_->iter - it0;
+        if (done > 0) seq_rounds_per_pass_ = 0.5 * seq_rounds_per_pass_ + 0.5 * std::min(64.0, (double)batch / (double)done);
+    }
+    return EQS_OK;
+}
+
 int PsoSolver::step_local(const double *replay_step)
 {
     EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
@@ -1121,7 +1301,10 @@ int PsoSolver::step(int64_t iters, const double *replay_step)
         EQS_TRY(rc);
         EQS_CUDA(ctx_, cudaGetLastError());
     }
-    for (int64_t it = 0; it < (small ? 0 : iters); ++it) {
+    if (!small && seq_windowed_ && iters > 0) {
+        EQS_TRY(sequential_windowed(iters));
+    }
+    for (int64_t it = 0; it < ((small || seq_windowed_) ? 0 : iters); ++it) {
         if (p_.mode == EQS_PSO_SYNCHRONOUS) {
             in_sync_step_ = true;
             EQS_TRY(launch_step());
@@ -1171,9 +1354,15 @@ int PsoSolver::read_state(double *x, double *v, double *pb, double *pbc)
     // device layout -> the reference's particle-major Vec<Particle>, resolving the role / stale bits of synchronous mode
     std::vector<unsigned char> flag((size_t)std::max<long long>(L, 1), 0);
     if (d_.sync && L > 0) EQS_TRY(pull(d_.pbflag, flag.data(), (size_t)L));
+    // windowed sequential mode: the committed (x, v) may live in (x2, v2)
+    bool swapped = false;
+    if (seq_windowed_) {
+        EQS_TRY(fetch_ctrl());
+        swapped = h_ctrl_->seq_parity != 0;
+    }
     if (x || pb) {
         std::vector<double> A(m), B(m);
-        EQS_TRY(pull(d_.x, A.data(), m * sizeof(double)));
+        EQS_TRY(pull(swapped ? d_.x2 : d_.x, A.data(), m * sizeof(double)));
         EQS_TRY(pull(d_.pb, B.data(), m * sizeof(double)));
         for (long long i = 0; i < L; ++i) {
             const bool stale = flag[i] & 1, role = flag[i] & 2;
@@ -1186,7 +1375,7 @@ int PsoSolver::read_state(double *x, double *v, double *pb, double *pbc)
     }
     if (v) {
         std::vector<double> V(m);
-        EQS_TRY(pull(d_.v, V.data(), m * sizeof(double)));
+        EQS_TRY(pull(swapped ? d_.v2 : d_.v, V.data(), m * sizeof(double)));
         for (long long i = 0; i < L; ++i)
             for (int d = 0; d < n; ++d) v[i * n + d] = at(V, i, d);
     }

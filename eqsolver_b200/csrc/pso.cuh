@@ -24,6 +24,17 @@ struct PsoCtrl {
     int pass_done;                  // sequential mode: the speculate-and-repair pass is complete
     unsigned int block_counter;     // last-block-done ticket
     int nan_seen;
+    // sequential mode, windowed device-driven rounds (pso_seqw_kernel)
+    long long seq_start;            // first particle of the current pass that is not final yet
+    long long seq_commit_lo, seq_commit_hi; // particles whose pbest update (:417-419) the next launch performs
+    long long seq_window;           // particles speculated per round, re-chosen after every pass (pso_seqw_kernel)
+    long long seq_wmin, seq_wmax;
+    long long seq_imp0;             // `improvements` when the current pass began
+    double seq_kest;                // running estimate of gbest improvements per pass
+    double seq_wscale;              // 2 * (fixed cost of a round) / (cost of one particle), in particles
+    long long seq_target;           // launches are no-ops once iter reaches it
+    int seq_parity;                 // 0: the committed (x, v) live in x / v, 1: in x2 / v2
+    int seq_commit_buf;             // which of x (0) / x2 (1) holds the positions of the pending commit
 };
 
 struct PsoDev {
@@ -92,6 +103,9 @@ public:
     bool manual_ = false;
     bool fused_exchange_ = false; // synchronous step exchanges over peer memory inside the step kernel
     bool in_sync_step_ = false;
+    bool seq_windowed_ = false;   // sequential mode: device-driven windowed rounds (one rank, more than PSO_SMALL_MAX particles)
+    int grid_seqw_ = 0;
+    double seq_rounds_per_pass_ = 16.0;
     int max_grid_ = 0;
 
 private:
@@ -103,6 +117,7 @@ private:
     int launch_step();
     int launch_step_apply();
     int sequential_pass();
+    int sequential_windowed(int64_t iters);
     int fetch_ctrl();
 };
 

@@ -431,3 +431,55 @@ def test_seeded_and_replay_solves_are_public_api(ctx):
     assert np.array_equal(got.view(np.uint64), od.solve(x0).view(np.uint64))
     with pytest.raises(E.IncorrectInput):
         ps.solve_with_draws(x0, init, steps.reshape(-1)[:-1])
+
+
+@pytest.mark.parametrize("window", [None, "64", "1000", "100000"])
+@pytest.mark.parametrize("objective,exact", [(E.Objective.ROSENBROCK, True), (E.Objective.HEAVY, True),
+                                             (E.Objective.RASTRIGIN, False)])
+def test_sequential_windowed_rounds_match_the_oracle(ctx, monkeypatch, objective, exact, window):
+    """Sequential mode beyond the single-CTA kernel: device-driven windowed speculate-and-repair (pso_seqw_kernel).
+    Any window size must give the reference's sequential semantics: whole state after every pass, several passes
+    per step() call, buffers swapping roles between passes."""
+    if window is None:
+        monkeypatch.delenv("EQS_PSO_SEQ_WINDOW", raising=False)
+    else:
+        monkeypatch.setenv("EQS_PSO_SEQ_WINDOW", window)
+    n, N = (6, 2500) if objective == E.Objective.HEAVY else (9, 5003)
+    lo, hi = (-5.12, 5.12) if objective == E.Objective.RASTRIGIN else (-5.0, 10.0)
+    g, o = make(objective, n, N, E.PsoMode.SEQUENTIAL_EXACT, seed=77, lo=lo, hi=hi)
+    x0 = np.full(n, 3.0)
+    run = g.with_context(ctx).start(x0)
+    o.init(x0)
+    compare_state(run, o, exact, "init")
+    for t, k in enumerate([1, 1, 2, 3, 1]):
+        run.step(k)
+        for _ in range(k):
+            assert o.step() == 0
+        compare_state(run, o, exact, f"after step call {t}")
+        assert run.gbest()[4] > 0     # gbest did improve: the repair rounds were exercised
+
+
+def test_sequential_windowed_replay_stall_and_solve(ctx, monkeypatch):
+    monkeypatch.setenv("EQS_PSO_SEQ_WINDOW", "777")
+    n, N, iters = 4, 3001, 5
+    lower, upper, x0 = [-5.0] * n, [10.0] * n, np.full(n, 1.5)
+    rng = np.random.Generator(np.random.Philox(5))
+    init, steps = rng.random((N, 2, n)), rng.random((iters, N, n, 2))
+    ps = (E.ParticleSwarm.new(E.Objective.ROSENBROCK, lower, upper).with_particle_count(N).with_iter_max(iters)
+          .with_tol(0.0).with_context(ctx))
+    od = O.Pso(O.ROSENBROCK, lower, upper, particle_count=N, iter_max=iters, tol=0.0, mode=O.SEQUENTIAL,
+               replay_init=init, replay_step=steps)
+    assert_bit_equal(ps.solve_with_draws(x0, init, steps), od.solve(x0))
+    # whole solve with the stall test active: same pass count, same answer
+    monkeypatch.delenv("EQS_PSO_SEQ_WINDOW")
+    ps = (E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * 3, [1.0] * 3).with_particle_count(4000).with_iter_max(400)
+          .with_tol(1e-3).with_seed(9).with_context(ctx))
+    o = O.Pso(O.SPHERE, [-1.0] * 3, [1.0] * 3, particle_count=4000, iter_max=400, tol=1e-3, mode=O.SEQUENTIAL, seed=9)
+    got = ps.solve(np.full(3, 0.5))
+    assert_bit_equal(got, o.solve(np.full(3, 0.5)))
+    assert ps.last_report.iters_run == o.iters() and 0 < o.iters() < 400 and ps.last_report.stalled == 1
+    # the host-driven rounds (what ranks > 1 use) stay available and agree
+    monkeypatch.setenv("EQS_PSO_SEQ_HOST", "1")
+    ps2 = (E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * 3, [1.0] * 3).with_particle_count(4000).with_iter_max(400)
+           .with_tol(1e-3).with_seed(9).with_context(ctx))
+    assert_bit_equal(ps2.solve(np.full(3, 0.5)), got)
