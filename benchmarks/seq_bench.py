@@ -2,7 +2,7 @@
 """ParticleSwarm in SEQUENTIAL_EXACT mode (the reference's in-loop gbest semantics, particle_swarm.rs:399-427) next to
 the synchronous mode on one GPU: particle-evals/s and the repair overhead, C2 shape by default.
 
-    python benchmarks/seq_bench.py [--n 32] [--particles 1048576] [--objective ROSENBROCK] [--iters 40]
+    python benchmarks/seq_bench.py [--dim 32] [--particles 1048576] [--objective ROSENBROCK] [--iters 40]
 """
 import argparse
 import json
@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=32)
+    ap.add_argument("--dim", dest="n", type=int, default=32)
     ap.add_argument("--particles", type=int, default=1 << 20)
     ap.add_argument("--objective", default="ROSENBROCK")
     ap.add_argument("--iters", type=int, default=40)
