@@ -483,3 +483,44 @@ def test_sequential_windowed_replay_stall_and_solve(ctx, monkeypatch):
     ps2 = (E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * 3, [1.0] * 3).with_particle_count(4000).with_iter_max(400)
            .with_tol(1e-3).with_seed(9).with_context(ctx))
     assert_bit_equal(ps2.solve(np.full(3, 0.5)), got)
+
+
+def test_concurrent_solves_from_threads(ctx):
+    """the reference's solve(&self) is re-entrant, so the C ABI must be callable concurrently on distinct
+    contexts, and on distinct solver handles of one context (its stream serialises the launches)."""
+    import threading
+    jobs = [(E.Objective.ROSENBROCK, 6, 3000 + 17 * j, 11 + j) for j in range(6)]
+
+    def solve(c, job):
+        obj, n, N, seed = job
+        return (E.ParticleSwarm.new(obj, [-5.0] * n, [10.0] * n).with_particle_count(N).with_iter_max(12).with_tol(0.0)
+                .with_seed(seed).with_mode(E.PsoMode.SYNCHRONOUS if seed % 2 else E.PsoMode.SEQUENTIAL_EXACT)
+                .with_context(c).solve(np.full(n, 2.0)))
+
+    want = [solve(ctx, j) for j in jobs]
+    for shared in (False, True):
+        got, errs = [None] * len(jobs), []
+
+        def work(i):
+            try:
+                got[i] = solve(ctx if shared else E.Context(0), jobs[i])
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errs, errs
+        for a, b in zip(got, want):
+            assert_bit_equal(a, b, f"shared context = {shared}")
+    # MonteCarlo and MISER from threads as well
+    res = [None] * 4
+
+    def integ(i):
+        c = E.Context(0)
+        res[i] = (E.MonteCarlo.new(E.Objective.GAUSSIAN).with_sample_count(100000).with_context(c)
+                  .integrate_with_seed(0.0, 1.0, 5),
+                  E.MISER.new(E.Objective.SINCOS).with_context(c).integrate_with_seed([0.0, 0.0], [1.0, 1.0], 5))
+    th = [threading.Thread(target=integ, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert all(r == res[0] and r is not None for r in res)
