@@ -793,6 +793,28 @@ int orc_mc_integrate(int integrand_id, int n, int64_t count, const double *from,
 }
 
 
+/* Welford moments (count, mean, sum of squared deviations) of the points [first, first + count) only: one rank's
+ * share of a sharded MonteCarlo (the ranks' moments are then merged pairwise in rank order, csrc/mc.cu) */
+int orc_mc_moments(int integrand_id, int n, int64_t first, int64_t count, const double *from, const double *to,
+                   uint64_t seed, double *moments)
+{
+    double *x = (double *)malloc(sizeof(double) * (size_t)n), *u = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+    double mean = 0.0, sum_of_squares = 0.0;
+    for (int64_t i = 0; i < count; ++i) {
+        orc_mc_draws(seed, first + i, n, u);
+        for (int d = 0; d < n; ++d) x[d] = u[d] * (to[d] - from[d]) + from[d];
+        const double sample = orc_objective(integrand_id, x, n);
+        const double delta_mean = sample - mean;
+        mean = mean + delta_mean / (double)(i + 1);
+        sum_of_squares = sum_of_squares + delta_mean * (sample - mean);
+    }
+    free(x); free(u);
+    moments[0] = (double)count;
+    moments[1] = mean;
+    moments[2] = sum_of_squares;
+    return ORC_OK;
+}
+
 /* ============================== MISER ======================================================= */
 /* miser_recurse, src/integrators/miser.rs:301-443.  The reference threads one rng through the recursion; here
  * every draw has a counter: stream 4, word 3 = node id (root 1, children 2 id, 2 id + 1), index =

@@ -173,6 +173,9 @@ int orc_ce_active(const orc_ce *s); /* loop condition :255 */
 int orc_mc_integrate(int integrand_id, int n, int64_t count, const double *from, const double *to, uint64_t seed,
                      const double *replay_u, double *mean, double *variance);
 void orc_mc_draws(uint64_t seed, int64_t index, int n, double *u);
+/* one rank's share of a sharded MonteCarlo: moments = {count, mean, sum of squared deviations} of points [first, first+count) */
+int orc_mc_moments(int integrand_id, int n, int64_t first, int64_t count, const double *from, const double *to,
+                   uint64_t seed, double *moments);
 
 /* ---- MISER (src/integrators/miser.rs:270-443), recursion exactly as miser_recurse :301-443; the draw counters are
  * described in eqs_oracle.c.  evals: integrand evaluations spent (may be NULL).  returns a status. */

@@ -156,6 +156,15 @@ def mc_integrate(integrand_id, lower, upper, sample_count=1000, seed=0, replay_u
     return int(st), m.value, v.value
 
 
+def mc_moments(integrand_id, lower, upper, first, count, seed=0):
+    """One rank's share of a sharded MonteCarlo: (count, mean, sum of squared deviations) of points [first, first+count)."""
+    lo, plo = _d(lower); hi, phi = _d(upper)
+    m = np.empty(3)
+    lib().orc_mc_moments(C.c_int(int(integrand_id)), C.c_int(int(lo.size)), C.c_int64(first), C.c_int64(count), plo, phi,
+                         C.c_uint64(seed), m.ctypes.data_as(_dp))
+    return m
+
+
 def miser_integrate(integrand_id, lower, upper, sample_count=1000, maximum_depth=5, min_dim_count=32, alpha=2.0,
                     dither=0.05, seed=0):
     """MISER::integrate_with_rng (reference miser.rs:270-443): returns (status, mean, variance, evals)."""

@@ -101,6 +101,25 @@ def _worker(rank, world, port, results):
             mu, sg = shc.state(); rmu, rsg = refc.state()
             np.testing.assert_allclose(mu, rmu, rtol=1e-12, atol=1e-12)
             np.testing.assert_allclose(sg, rsg, rtol=1e-12, atol=1e-12)
+
+        # 4. MonteCarlo: points sharded over the ranks, Welford moments merged pairwise in rank order (csrc/mc.cu)
+        lower, upper, count = [0.0, -1.0, 0.5], [1.0, 1.0, 2.0], 1001
+        first, local = E.shard_range(count, world, rank)
+        parts = allgather(O.mc_moments(O.GAUSSIAN, lower, upper, first, local, seed=9))
+        cnt, mean, m2 = 0.0, 0.0, 0.0
+        for r in range(world):
+            nb, mb, sb = parts[r]
+            if nb == 0:
+                continue
+            if cnt == 0:
+                cnt, mean, m2 = nb, mb, sb
+                continue
+            tot, delta = cnt + nb, mb - mean
+            mean, m2, cnt = mean + delta * (nb / tot), m2 + sb + delta * delta * (cnt * nb / tot), tot
+        vol = np.prod(np.array(upper) - np.array(lower))
+        st, rmean, rvar = O.mc_integrate(O.GAUSSIAN, lower, upper, count, seed=9)
+        assert st == 0 and cnt == count
+        assert abs(mean * vol - rmean) <= 1e-13 * abs(rmean) and abs(m2 / (count - 1) * vol * vol - rvar) <= 1e-12 * rvar
         results[rank] = "ok"
     except Exception as e:  # surface the failure to the parent
         import traceback
