@@ -2,6 +2,8 @@
 // CrossEntropy entry points live in ce.cu.  No exception crosses the boundary.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <exception>
 #include <new>
 
 #include "common.cuh"
@@ -17,6 +19,25 @@ struct eqs_pso {
 };
 
 static thread_local std::string g_create_error;
+static thread_local char g_boundary_text[256] = "";
+
+namespace eqs {
+int boundary_exception() noexcept
+{
+    try {
+        throw;
+    } catch (const std::bad_alloc &) {
+        snprintf(g_boundary_text, sizeof(g_boundary_text), "out of host memory");
+    } catch (const std::exception &e) {
+        snprintf(g_boundary_text, sizeof(g_boundary_text), "C++ exception: %s", e.what());
+    } catch (...) {
+        snprintf(g_boundary_text, sizeof(g_boundary_text), "unknown C++ exception");
+    }
+    return EQS_ERR_EXTERNAL;
+}
+const char *boundary_exception_text() noexcept { return g_boundary_text; }
+} // namespace eqs
+
 
 namespace {
 
@@ -94,6 +115,7 @@ int eqs_abi_version(void) { return EQS_ABI_VERSION; }
 
 int eqs_ctx_create(int device, eqs_ctx **out)
 {
+    EQS_BOUNDARY_TRY
     if (!out) return EQS_ERR_INCORRECT_INPUT;
     *out = nullptr;
     int count = 0;
@@ -120,10 +142,12 @@ int eqs_ctx_create(int device, eqs_ctx **out)
     }
     *out = ctx;
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_ctx_destroy(eqs_ctx *ctx)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx) return EQS_OK;
     cudaSetDevice(ctx->c.device);
     comm_destroy(&ctx->c);
@@ -132,45 +156,56 @@ int eqs_ctx_destroy(eqs_ctx *ctx)
     if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 const char *eqs_last_error(const eqs_ctx *ctx) { return ctx ? ctx->c.error.c_str() : g_create_error.c_str(); }
 
 int eqs_ctx_sm_count(const eqs_ctx *ctx, int *out)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx || !out) return EQS_ERR_INCORRECT_INPUT;
     *out = ctx->c.sm_count;
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_comm_unique_id(void *out128)
 {
+    EQS_BOUNDARY_TRY
     if (!out128) return EQS_ERR_INCORRECT_INPUT;
     return comm_unique_id(out128, g_create_error);
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_ctx_comm_init(eqs_ctx *ctx, int rank, int world, const void *id128)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx || (world > 1 && !id128)) return EQS_ERR_INCORRECT_INPUT;
     return comm_init(&ctx->c, rank, world, id128);
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_ctx_rank(const eqs_ctx *ctx, int *rank, int *world)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx) return EQS_ERR_INCORRECT_INPUT;
     if (rank) *rank = ctx->c.rank;
     if (world) *world = ctx->c.world;
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_shard_range(int64_t count, int world, int rank, int64_t *first, int64_t *local)
 {
+    EQS_BOUNDARY_TRY
     if (count < 0 || world < 1 || rank < 0 || rank >= world) return EQS_ERR_INCORRECT_INPUT;
     const int64_t base = count / world, rem = count % world;
     const int64_t f = rank * base + std::min<int64_t>(rank, rem);
     if (first) *first = f;
     if (local) *local = base + (rank < rem ? 1 : 0);
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int64_t eqs_record_doubles(int32_t n) { return record_doubles(n); }
@@ -179,6 +214,7 @@ int64_t eqs_record_doubles(int32_t n) { return record_doubles(n); }
 
 int eqs_objective_eval(eqs_ctx *ctx, int32_t objective_id, const double *x, int32_t n, int64_t count, double *out)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx || !x || !out || n <= 0 || count < 0) return EQS_ERR_INCORRECT_INPUT;
     Ctx *c = &ctx->c;
     if ((objective_id == EQS_OBJ_THREE_CIRCLES || objective_id == EQS_OBJ_SINCOS) && n != 2)
@@ -200,10 +236,12 @@ int eqs_objective_eval(eqs_ctx *ctx, int32_t objective_id, const double *x, int3
     cudaFree(dout);
     if (st == EQS_OK && e != cudaSuccess) st = c->fail(EQS_ERR_EXTERNAL, "CUDA error: %s", cudaGetErrorString(e));
     return st;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_philox_blocks(eqs_ctx *ctx, const uint32_t *ctr, const uint32_t key[2], int64_t count, uint32_t *out)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx || !ctr || !key || !out || count < 0) return EQS_ERR_INCORRECT_INPUT;
     Ctx *c = &ctx->c;
     if (count == 0) return EQS_OK;
@@ -219,10 +257,12 @@ int eqs_philox_blocks(eqs_ctx *ctx, const uint32_t *ctr, const uint32_t key[2], 
     cudaFree(dout);
     if (e != cudaSuccess) return c->fail(EQS_ERR_EXTERNAL, "CUDA error: %s", cudaGetErrorString(e));
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_draws(eqs_ctx *ctx, int32_t kind, uint64_t seed, int64_t t, int64_t first, int64_t count, int32_t n, double *a, double *b)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx || !a || kind < 0 || kind > 2 || (kind != 2 && !b) || n <= 0 || count < 0) return EQS_ERR_INCORRECT_INPUT;
     Ctx *c = &ctx->c;
     if (count == 0) return EQS_OK;
@@ -239,10 +279,12 @@ int eqs_draws(eqs_ctx *ctx, int32_t kind, uint64_t seed, int64_t t, int64_t firs
     cudaFree(db);
     if (e != cudaSuccess) return c->fail(EQS_ERR_EXTERNAL, "CUDA error: %s", cudaGetErrorString(e));
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_device_cos(eqs_ctx *ctx, const double *x, int64_t count, double *out)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx || !x || !out || count < 0) return EQS_ERR_INCORRECT_INPUT;
     Ctx *c = &ctx->c;
     if (count == 0) return EQS_OK;
@@ -258,10 +300,12 @@ int eqs_device_cos(eqs_ctx *ctx, const double *x, int64_t count, double *out)
     cudaFree(dout);
     if (e != cudaSuccess) return c->fail(EQS_ERR_EXTERNAL, "CUDA error: %s", cudaGetErrorString(e));
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_measure_fp64(eqs_ctx *ctx, double *tflops)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx || !tflops) return EQS_ERR_INCORRECT_INPUT;
     Ctx *c = &ctx->c;
     EQS_CUDA(c, cudaSetDevice(c->device));
@@ -288,10 +332,12 @@ int eqs_measure_fp64(eqs_ctx *ctx, double *tflops)
     cudaFree(dout);
     *tflops = best;
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_measure_copy(eqs_ctx *ctx, int64_t bytes, double *gbps)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx || !gbps || bytes < 16) return EQS_ERR_INCORRECT_INPUT;
     Ctx *c = &ctx->c;
     EQS_CUDA(c, cudaSetDevice(c->device));
@@ -321,6 +367,7 @@ int eqs_measure_copy(eqs_ctx *ctx, int64_t bytes, double *gbps)
     cudaFree(b);
     *gbps = best;
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 // ---- ParticleSwarm -------------------------------------------------------------------------------------
@@ -329,6 +376,7 @@ int eqs_pso_validate(const eqs_pso_params *p) { return validate_pso_params(p, nu
 
 int eqs_pso_create(eqs_ctx *ctx, const eqs_pso_params *p, eqs_pso **out)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx || !out) return EQS_ERR_INCORRECT_INPUT;
     *out = nullptr;
     eqs_pso *h = new (std::nothrow) eqs_pso(&ctx->c);
@@ -340,12 +388,15 @@ int eqs_pso_create(eqs_ctx *ctx, const eqs_pso_params *p, eqs_pso **out)
     }
     *out = h;
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_destroy(eqs_pso *h)
 {
+    EQS_BOUNDARY_TRY
     delete h;
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 #define H_OR_FAIL(h)                                                                                             \
@@ -353,26 +404,33 @@ int eqs_pso_destroy(eqs_pso *h)
 
 int eqs_pso_init(eqs_pso *h, const double *x0)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     if (!x0) return h->s.ctx_->fail(EQS_ERR_INCORRECT_INPUT, "null x0");
     return h->s.init(x0);
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_step(eqs_pso *h, int64_t iters, const double *replay_step)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     if (iters < 0) return h->s.ctx_->fail(EQS_ERR_INCORRECT_INPUT, "negative iteration count");
     return h->s.step(iters, replay_step);
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_sync(eqs_pso *h)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     return h->s.sync();
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_last_step_ms(eqs_pso *h, double *ms, int64_t *kernel_launches)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     Ctx *c = h->s.ctx_;
     EQS_CUDA(c, cudaEventSynchronize(h->s.ev1_));
@@ -381,80 +439,103 @@ int eqs_pso_last_step_ms(eqs_pso *h, double *ms, int64_t *kernel_launches)
     if (ms) *ms = f;
     if (kernel_launches) *kernel_launches = h->s.last_launches_;
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_read_gbest(eqs_pso *h, double *g, double *cost, int64_t *iters_run, int32_t *stalled, int64_t *improvements)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     return h->s.read_gbest(g, cost, iters_run, stalled, improvements);
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_read_state(eqs_pso *h, double *x, double *v, double *pbest, double *pbest_cost)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     return h->s.read_state(x, v, pbest, pbest_cost);
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_read_ring(eqs_pso *h, double *ring, int64_t *ring_i)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     return h->s.read_ring(ring, ring_i);
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_local_range(eqs_pso *h, int64_t *first, int64_t *local)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     if (first) *first = h->s.d_.first;
     if (local) *local = h->s.d_.nloc;
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_init_local(eqs_pso *h, const double *x0, int32_t phase)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     if (phase < 0 || phase > 1 || (phase == 0 && !x0)) return h->s.ctx_->fail(EQS_ERR_INCORRECT_INPUT, "bad init phase");
     return h->s.init_local(x0, phase);
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_init_apply(eqs_pso *h)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     return h->s.init_apply();
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_step_local(eqs_pso *h, const double *replay_step)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     return h->s.step_local(replay_step);
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_step_apply(eqs_pso *h)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     return h->s.step_apply();
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_get_record(eqs_pso *h, double *record)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     if (!record) return EQS_ERR_INCORRECT_INPUT;
     return h->s.get_record(record);
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_set_records(eqs_pso *h, const double *records)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     if (!records) return EQS_ERR_INCORRECT_INPUT;
     return h->s.set_records(records);
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_pso_solve(eqs_ctx *ctx, const eqs_pso_params *p, const double *x0, double *out_x, eqs_report *report)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx) return EQS_ERR_INCORRECT_INPUT;
     if (!x0 || !out_x) return ctx->c.fail(EQS_ERR_INCORRECT_INPUT, "null x0 / out_x");
     PsoSolver s(&ctx->c);
     EQS_TRY(s.create(p));
     return s.solve(x0, out_x, report);
+    EQS_BOUNDARY_CATCH
 }
 
 } // extern "C"

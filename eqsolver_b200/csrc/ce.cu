@@ -914,6 +914,7 @@ int eqs_ce_validate(const eqs_ce_params *p) { return validate_ce_params(p, nullp
 
 int eqs_ce_create(eqs_ctx *ctx, const eqs_ce_params *p, const double *x0, eqs_ce **out)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx || !out) return EQS_ERR_INCORRECT_INPUT;
     *out = nullptr;
     eqs_ce *h = new (std::nothrow) eqs_ce(&ctx->c);
@@ -925,32 +926,40 @@ int eqs_ce_create(eqs_ctx *ctx, const eqs_ce_params *p, const double *x0, eqs_ce
     }
     *out = h;
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_ce_destroy(eqs_ce *h)
 {
+    EQS_BOUNDARY_TRY
     delete h;
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_ce_step(eqs_ce *h, int64_t iters, const double *replay_normals)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     if (iters < 0) return h->s.ctx_->fail(EQS_ERR_INCORRECT_INPUT, "negative iteration count");
     return h->s.step(iters, replay_normals);
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_ce_sync(eqs_ce *h)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     Ctx *c = h->s.ctx_;
     EQS_CUDA(c, cudaSetDevice(c->device));
     EQS_CUDA(c, cudaStreamSynchronize(c->stream));
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_ce_last_step_ms(eqs_ce *h, double *ms, int64_t *kernel_launches)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     Ctx *c = h->s.ctx_;
     EQS_CUDA(c, cudaEventSynchronize(h->s.ev1_));
@@ -959,16 +968,20 @@ int eqs_ce_last_step_ms(eqs_ce *h, double *ms, int64_t *kernel_launches)
     if (ms) *ms = f;
     if (kernel_launches) *kernel_launches = h->s.last_launches_;
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_ce_read_state(eqs_ce *h, double *mu, double *sigma, int64_t *iters_run, int32_t *active)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     return h->s.read_state(mu, sigma, iters_run, active);
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_ce_read_elites(eqs_ce *h, int64_t *idx, int64_t *count)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     CeSolver &s = h->s;
     Ctx *c = s.ctx_;
@@ -983,10 +996,12 @@ int eqs_ce_read_elites(eqs_ce *h, int64_t *idx, int64_t *count)
         if (s.small_path_) std::sort(idx, idx + ne);              // the contract is ascending sample order
     }
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_ce_read_costs(eqs_ce *h, double *costs)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     CeSolver &s = h->s;
     Ctx *c = s.ctx_;
@@ -995,24 +1010,29 @@ int eqs_ce_read_costs(eqs_ce *h, double *costs)
     if (s.d_.nloc > 0) EQS_CUDA(c, cudaMemcpyAsync(costs, s.d_.cost, s.d_.nloc * 8, cudaMemcpyDeviceToHost, c->stream));
     EQS_CUDA(c, cudaStreamSynchronize(c->stream));
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_ce_local_range(eqs_ce *h, int64_t *first, int64_t *local)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     if (first) *first = h->s.d_.first;
     if (local) *local = h->s.d_.nloc;
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_ce_phase(eqs_ce *h, int32_t phase, const double *replay_normals)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     CeSolver &s = h->s;
     Ctx *c = s.ctx_;
     EQS_CUDA(c, cudaSetDevice(c->device));
     if (phase == 0) EQS_TRY(s.prepare_replay(replay_normals, 1));
     return s.launch_phase(phase);
+    EQS_BOUNDARY_CATCH
 }
 
 int64_t eqs_ce_exchange_words(eqs_ce *h, int32_t phase)
@@ -1024,6 +1044,7 @@ int64_t eqs_ce_exchange_words(eqs_ce *h, int32_t phase)
 
 int eqs_ce_get_exchange(eqs_ce *h, int32_t phase, void *words)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     CeSolver &s = h->s;
     Ctx *c = s.ctx_;
@@ -1035,10 +1056,12 @@ int eqs_ce_get_exchange(eqs_ce *h, int32_t phase, void *words)
     EQS_CUDA(c, cudaMemcpyAsync(words, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     EQS_CUDA(c, cudaStreamSynchronize(c->stream));
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_ce_set_exchange(eqs_ce *h, int32_t phase, const void *words)
 {
+    EQS_BOUNDARY_TRY
     H_OR_FAIL(h);
     CeSolver &s = h->s;
     Ctx *c = s.ctx_;
@@ -1050,15 +1073,18 @@ int eqs_ce_set_exchange(eqs_ce *h, int32_t phase, const void *words)
     EQS_CUDA(c, cudaMemcpyAsync(dst, words, bytes, cudaMemcpyHostToDevice, c->stream));
     EQS_CUDA(c, cudaStreamSynchronize(c->stream));
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 int eqs_ce_solve(eqs_ctx *ctx, const eqs_ce_params *p, const double *x0, double *out_mu, eqs_report *report)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx) return EQS_ERR_INCORRECT_INPUT;
     if (!x0 || !out_mu) return ctx->c.fail(EQS_ERR_INCORRECT_INPUT, "null x0 / out_mu");
     CeSolver s(&ctx->c);
     EQS_TRY(s.create(p, x0));
     return s.solve(out_mu, report);
+    EQS_BOUNDARY_CATCH
 }
 
 } // extern "C"

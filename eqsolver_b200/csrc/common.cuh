@@ -10,7 +10,19 @@
 #include <cuda_runtime.h>
 #include "../../include/eqsolver_b200.h"
 
+// No C++ exception may cross the C ABI (include/eqsolver_b200.h): every extern "C" entry point with a body that can
+// allocate runs between these two; std::bad_alloc and friends come back as EQS_ERR_EXTERNAL.
+#define EQS_BOUNDARY_TRY try {
+#define EQS_BOUNDARY_CATCH                                                                                       \
+    }                                                                                                            \
+    catch (...) { return eqs::boundary_exception(); }
+
 namespace eqs {
+
+// inside a catch (...): the status for "a C++ exception reached the boundary"; the text is kept per thread
+int boundary_exception() noexcept;
+const char *boundary_exception_text() noexcept;
+
 
 // ---- exchange record (doubles) --------------------------------------------------------------------------
 // One record per rank and exchange: the only data that ever crosses NVLink for ParticleSwarm.

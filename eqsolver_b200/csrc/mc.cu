@@ -331,6 +331,7 @@ int eqs_mc_validate(const eqs_mc_params *p) { return validate_mc_params(p, nullp
 
 int eqs_mc_integrate(eqs_ctx *ctx, const eqs_mc_params *p, double *mean, double *variance, eqs_report *report)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx) return EQS_ERR_INCORRECT_INPUT;
     Ctx *c = &ctx->c;
     if (!mean || !variance) return c->fail(EQS_ERR_INCORRECT_INPUT, "null result pointers");
@@ -440,6 +441,7 @@ int eqs_mc_integrate(eqs_ctx *ctx, const eqs_mc_params *p, double *mean, double 
     cleanup();
 #undef MC_TRY
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 
@@ -447,6 +449,7 @@ int eqs_miser_validate(const eqs_miser_params *p) { return validate_miser_params
 
 int eqs_miser_integrate(eqs_ctx *ctx, const eqs_miser_params *p, double *mean, double *variance, eqs_report *report)
 {
+    EQS_BOUNDARY_TRY
     if (!ctx) return EQS_ERR_INCORRECT_INPUT;
     Ctx *c = &ctx->c;
     if (!mean || !variance) return c->fail(EQS_ERR_INCORRECT_INPUT, "null result pointers");
@@ -662,6 +665,10 @@ int eqs_miser_integrate(eqs_ctx *ctx, const eqs_miser_params *p, double *mean, d
             }
         }
         level.swap(next);
+        if (nodes.size() > (size_t)1 << 22) { // the host holds the recursion tree; 4M regions is far beyond any sane call
+            rc = c->fail(EQS_ERR_INCORRECT_INPUT, "MISER recursion spans more than 2^22 regions; lower maximum_depth");
+            break;
+        }
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
@@ -697,6 +704,7 @@ int eqs_miser_integrate(eqs_ctx *ctx, const eqs_miser_params *p, double *mean, d
         report->loop_ms = total_ms;
     }
     return EQS_OK;
+    EQS_BOUNDARY_CATCH
 }
 
 } // extern "C"
