@@ -1,10 +1,10 @@
 // pso.cuh -- device-side state of one ParticleSwarm shard and the host driver class.
 //
-// Data layout in HBM: structure of arrays, dimension-major, particle-contiguous
-//   x, v, pbest : [n][ld] f64   (ld = local particle count rounded up to 16 => 128-byte rows)
-//   pbest_cost  : [ld]   f64
-// replacing the reference's array of structs `Vec<Particle>` (particle_swarm.rs:14-22, 361-389), so that
-// thread i of a warp reads lane-contiguous 8/16-byte words for every dimension d.
+// Data layout in HBM: array of structures of arrays, 4 dimensions of one particle per 32-byte sector
+//   x, v, pbest : [ceil(n/4)][ld][4] f64   (ld = local particle count rounded up to 32)
+//   pbest_cost  : [ld] f64
+// replacing the reference's array of structs `Vec<Particle>` (particle_swarm.rs:14-22, 361-389): lane i of a warp
+// moves group q of particle i with one 256-bit access, a warp touches 1 KB of consecutive bytes.
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"
@@ -38,10 +38,10 @@ struct PsoCtrl {
 };
 
 struct PsoDev {
-    double *x, *v, *pb, *pbc;       // population, SoA [n][ld]; synchronous mode: x = buffer A, pb = buffer B (pso.cu)
+    double *x, *v, *pb, *pbc;       // population, [ceil(n/4)][ld][4]; synchronous mode: x = buffer A, pb = buffer B (pso.cu)
     double *cost;                   // [ld] costs of the last evaluation (init ring scan, sequential mode)
     unsigned char *pbflag;          // [ld] synchronous mode: bit 0 = stale (pbest == position), bit 1 = x lives in B
-    double *x2, *v2;                // sequential mode: speculative next state
+    double *x2, *v2;                // sequential mode: second (x, v) pair -- speculated state / role-swapping partner
     double *G;                      // [n] global_best_position
     PsoCtrl *ctrl;
     double *part_cost;              // [grid] per-block partial min-loc
