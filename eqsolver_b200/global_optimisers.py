@@ -379,6 +379,12 @@ class PsoRun:
         self.ctx.check(_ffi.lib().eqs_pso_read_state(self._h, _p(x), _p(v), _p(pb), _p(pbc)))
         return x, v, pb, pbc
 
+    def pbest_costs(self) -> np.ndarray:
+        """Only the pbest costs of this rank's particles (state() also moves 3 n-vectors per particle)."""
+        pbc = np.empty(self.local)
+        self.ctx.check(_ffi.lib().eqs_pso_read_state(self._h, None, None, None, _p(pbc)))
+        return pbc
+
     def ring(self):
         r = np.empty(_ffi.STALL_WINDOW); i = C.c_int64(0)
         self.ctx.check(_ffi.lib().eqs_pso_read_ring(self._h, _p(r), C.byref(i)))

@@ -275,3 +275,29 @@ def test_seeded_and_replay_solves_are_public_api(ctx):
              replay_normals=z)
     mu = o.solve()
     np.testing.assert_allclose(got, mu, rtol=1e-12, atol=1e-13)
+
+
+def test_full_size_c5_per_gpu_properties(ctx):
+    """BASELINE config 5 at its per-GPU size (Rosenbrock n=1024, 2^23 samples, 1 % elites): size-independent checks."""
+    n, N = 1024, 1 << 23
+    k = N // 100
+    x0, s0 = np.zeros(n), np.full(n, 2.0)
+    ce = (E.CrossEntropy.new(E.Objective.ROSENBROCK).with_sample_size(N).with_importance_selection_size(k)
+          .with_iter_max(6).with_std_dev(s0).with_mean_divisor(E.MeanDivisor.ELITE_COUNT).with_seed(1729)
+          .with_tol(0.0).with_context(ctx))
+    run = ce.start(x0)
+    run.step(1)
+    costs, el = run.costs(), run.elites()
+    assert el.size == k and np.all(np.diff(el) > 0)
+    mask = np.zeros(N, dtype=bool); mask[el] = True
+    assert costs[mask].max() <= costs[~mask].min()
+    assert costs[mask].max() == np.partition(costs, k - 1)[k - 1]
+    for j in np.random.default_rng(2).integers(0, N, 16):             # sampled costs against the oracle
+        x = x0 + s0 * O.ce_normals(1729, 0, int(j), n)
+        assert abs(costs[j] - O.objective(O.ROSENBROCK, x)) <= 1e-12 * costs[j]
+    X = np.stack([x0 + s0 * O.ce_normals(1729, 0, int(i), n) for i in el])   # refit on the host from the counters
+    mu, sg, it, _ = run.state()
+    close(mu, X.mean(axis=0), 5.0, "mu")
+    close(sg, X.std(axis=0, ddof=1), 5.0, "sigma")
+    assert it == 1
+    run.close()

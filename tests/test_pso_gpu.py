@@ -524,3 +524,27 @@ def test_concurrent_solves_from_threads(ctx):
     [t.start() for t in th]
     [t.join() for t in th]
     assert all(r == res[0] and r is not None for r in res)
+
+
+def test_full_size_c4_properties(ctx):
+    """BASELINE config 4 at its per-GPU size (Ackley n=256, 2^21 particles = 12.9 GB of state): size-independent
+    properties of the synchronous pass."""
+    n, N = 256, 1 << 21
+    ps = (E.ParticleSwarm.new(E.Objective.ACKLEY, [-32.768] * n, [32.768] * n).with_particle_count(N).with_tol(0.0)
+          .with_seed(1729).with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx))
+    run = ps.start(np.full(n, 30.0))
+    g, c_prev, _, _, _ = run.gbest()
+    pbc_prev = run.pbest_costs()
+    f0 = O.objective(O.ACKLEY, np.full(n, 30.0))
+    assert c_prev == min(pbc_prev.min(), f0)
+    for t in range(3):
+        run.step(1)
+        g, c, it, stalled, _ = run.gbest()
+        pbc = run.pbest_costs()
+        assert it == t + 1 and not stalled
+        assert c <= c_prev and np.all(pbc <= pbc_prev)              # gbest / pbest costs never increase
+        assert c <= pbc.min() and (c == pbc.min() or c == f0)       # gbest cost = the best cost seen
+        assert abs(O.objective(O.ACKLEY, g) - c) <= 1e-12 * c       # the gbest cost is f(gbest position)
+        assert np.all(np.isfinite(pbc))
+        c_prev, pbc_prev = c, pbc
+    run.close()
