@@ -148,6 +148,41 @@ def cpu_baseline_port(workload: str, budget_s: float):
                       f"{os.cpu_count()} host cores visible, 1 used (the reference is single-threaded)"}
 
 
+def also_measured(ctx, E):
+    """Informational side measurements at N=1, outside the timed region of the headline (a few seconds): the other
+    kernels of the path on their BASELINE configurations, device-resident, CUDA events on the library stream."""
+    out = {}
+    # C2 in the reference's sequential-gbest semantics (pso_seqw_kernel)
+    n, N = 32, 1 << 20
+    run = (E.ParticleSwarm.new(E.Objective.ROSENBROCK, [-5.0] * n, [10.0] * n).with_particle_count(N).with_tol(0.0)
+           .with_seed(SEED).with_mode(E.PsoMode.SEQUENTIAL_EXACT).with_context(ctx)).start(np.zeros(n))
+    run.step(3); run.sync(); run.step(40); run.sync()
+    ms, launches = run.last_step_ms()
+    out["c2_sequential_exact"] = {"value": N * 40 / (ms * 1e-3), "unit": "particle-evals/s", "ms_per_pass": ms / 40,
+                                  "launches_per_pass": launches / 40, "passes": 40}
+    run.close()
+    # C3: CrossEntropy Rastrigin n=64, 2^22 samples per pass, 1 % elites, divisor k
+    n, N = 64, 1 << 22
+    ce = (E.CrossEntropy.new(E.Objective.RASTRIGIN).with_sample_size(N).with_importance_selection_size(N // 100)
+          .with_iter_max(40).with_std_dev(np.full(n, 2.0)).with_mean_divisor(E.MeanDivisor.ELITE_COUNT).with_seed(SEED)
+          .with_tol(0.0).with_context(ctx))
+    crun = ce.start(np.full(n, 3.0))
+    crun.step(3); crun.sync(); crun.step(20); crun.sync()
+    ms, launches = crun.last_step_ms()
+    out["c3_cross_entropy"] = {"value": N * 20 / (ms * 1e-3), "unit": "sample-evals/s", "ms_per_pass": ms / 20,
+                               "launches_per_pass": launches / 20, "passes": 20,
+                               "bound": "FP64 pipe + issue (profiles/r01_ce_c3.json)"}
+    crun.close()
+    # MonteCarlo, the reference's 1-D test integrand at a GPU-sized point count
+    count = 1 << 28
+    mc = E.MonteCarlo.new(E.Objective.GAUSSIAN).with_sample_count(count).with_context(ctx)
+    mc.integrate_with_seed(0.0, 1.0, 1)
+    r = mc.integrate_with_seed(0.0, 1.0, 2)
+    out["monte_carlo_1d"] = {"value": count / (mc.last_report.loop_ms * 1e-3), "unit": "samples/s", "samples": count,
+                             "mean": r.mean, "exact": 0.746824132812427}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; cargo/rustc are absent) on host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -186,6 +221,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the informational side measurements (N=1 only)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -318,6 +354,8 @@ def main():
                      "algorithmic_bytes_per_eval": algorithmic_bytes_per_eval(n),
                      "frac_of_nominal_8000": achieved / 8000.0},
     }
+    if world == 1 and not args.no_also:
+        line["also"] = also_measured(ctx, E)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(args.workload, args.cpu_budget)
