@@ -53,11 +53,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     flags = list(NVCC_FLAGS)
     user = os.environ.get("EQS_USER_OBJECTIVE_HEADER")
     if user:
-        # the user's header shadows csrc/user_objective.cuh
-        shadow = os.path.join(OBJ_DIR, "user_include")
-        os.makedirs(shadow, exist_ok=True)
-        shutil.copyfile(user, os.path.join(shadow, "user_objective.cuh"))
-        flags += ["-I", shadow]
+        # objectives.cuh includes this file instead of csrc/user_objective.cuh
+        flags += [f'-DEQS_USER_OBJECTIVE_HEADER="{os.path.abspath(user)}"']
     flags += os.environ.get("EQS_NVCC_DEFINES", "").split()  # e.g. "-DEQS_PSO_UQ=3" for tuning sweeps
     if verbose:
         flags += ["-Xptxas", "-v"]

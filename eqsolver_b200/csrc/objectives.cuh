@@ -182,7 +182,12 @@ template <> struct Objective<EQS_OBJ_SERIES> {
 } // inline namespace
 } // namespace eqs
 
+// the user hook: csrc/user_objective.cuh, or the header named by the build (EQS_USER_OBJECTIVE_HEADER, build.py)
+#ifdef EQS_USER_OBJECTIVE_HEADER
+#include EQS_USER_OBJECTIVE_HEADER
+#else
 #include "user_objective.cuh"
+#endif
 
 namespace eqs {
 #if EQS_COS_TABLE

@@ -1,4 +1,6 @@
 """GPU: the CUDA ParticleSwarm path (through the C ABI) against the CPU oracle on identical draws."""
+import os
+
 import numpy as np
 import pytest
 
@@ -548,3 +550,47 @@ def test_full_size_c4_properties(ctx):
         assert np.all(np.isfinite(pbc))
         c_prev, pbc_prev = c, pbc
     run.close()
+
+
+def test_user_objective_hook(ctx, tmp_path):
+    """a user objective is a CUDA header named at build time (EQS_USER_OBJECTIVE_HEADER).  Build a
+    library variant whose api.cu carries a custom streaming functor and evaluate it through eqs_objective_eval."""
+    import ctypes as C
+    import subprocess
+    from eqsolver_b200 import _ffi, build as kbuild
+    hdr = tmp_path / "mine.cuh"
+    hdr.write_text('''#pragma once
+namespace eqs {
+struct UserObjective {  // sum (d + 1) * |x_d|^3, streaming form
+    static constexpr bool streaming = true;
+    __device__ static void begin(ObjAcc &s, int) { s.a = 0.0; }
+    __device__ static void feed(ObjAcc &s, double x, int d) { s.a += (double)(d + 1) * (fabs(x) * x * x); }
+    __device__ static double end(const ObjAcc &s, int) { return s.a; }
+};
+}
+''')
+    nvcc = kbuild._nvcc()
+    obj = tmp_path / "api.o"
+    subprocess.check_call([nvcc, *kbuild.NVCC_FLAGS, f'-DEQS_USER_OBJECTIVE_HEADER="{hdr}"', "-c",
+                           os.path.join(kbuild.CSRC, "api.cu"), "-o", str(obj)])
+    others = [os.path.join(kbuild.OBJ_DIR, s.replace(".cu", ".o")) for s in kbuild.SOURCES if s != "api.cu"]
+    for s, o in zip([s for s in kbuild.SOURCES if s != "api.cu"], others):
+        if not os.path.exists(o):   # a tree without build/: compile the stock object
+            subprocess.check_call([nvcc, *kbuild.NVCC_FLAGS, "-c", os.path.join(kbuild.CSRC, s), "-o", o])
+    lib = tmp_path / "libcustom.so"
+    subprocess.check_call([nvcc, "-shared", "-o", str(lib), str(obj), *others, "-gencode",
+                           "arch=compute_100a,code=sm_100a", "-ldl"])
+    L = C.CDLL(str(lib))
+    L.eqs_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.eqs_objective_eval.argtypes = _ffi.SYMBOLS["eqs_objective_eval"][1]
+    h = C.c_void_p()
+    assert L.eqs_ctx_create(0, C.byref(h)) == 0
+    x = np.random.default_rng(3).uniform(-2, 2, size=(33, 5))
+    out = np.empty(33)
+    assert L.eqs_objective_eval(h, int(E.Objective.USER), x.ctypes.data_as(_ffi.dp), 5, 33, out.ctypes.data_as(_ffi.dp)) == 0
+    want = np.zeros(33)
+    for d in range(5):
+        want = want + (d + 1.0) * (np.abs(x[:, d]) * x[:, d] * x[:, d])
+    assert_bit_equal(out, want)
+    L.eqs_ctx_destroy.argtypes = [C.c_void_p]
+    L.eqs_ctx_destroy(h)
