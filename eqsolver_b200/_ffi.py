@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libeqsolver_b200.so")
+# EQS_B200_LIBRARY: load a differently built variant of the same library (tuning sweeps, user-objective builds)
+LIB_PATH = os.environ.get("EQS_B200_LIBRARY") or os.path.join(_HERE, "lib", "libeqsolver_b200.so")
 
 dp = C.POINTER(C.c_double)
 i64p = C.POINTER(C.c_int64)

@@ -40,6 +40,13 @@ namespace {
 #ifndef EQS_PSO_UQ
 #define EQS_PSO_UQ 2
 #endif
+// cache-policy qualifiers of the 256-bit population accesses (tuning sweeps; empty = default policy)
+#ifndef EQS_PSO_LDHINT
+#define EQS_PSO_LDHINT ""
+#endif
+#ifndef EQS_PSO_STHINT
+#define EQS_PSO_STHINT ""
+#endif
 #ifndef EQS_PSO_MINB
 #define EQS_PSO_MINB 2
 #endif
@@ -55,13 +62,13 @@ struct D4 {
 __device__ __forceinline__ D4 ld256(const double *p)
 {
     D4 r;
-    asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.e[0]), "=d"(r.e[1]), "=d"(r.e[2]), "=d"(r.e[3]) : "l"(p));
+    asm("ld.global" EQS_PSO_LDHINT ".v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.e[0]), "=d"(r.e[1]), "=d"(r.e[2]), "=d"(r.e[3]) : "l"(p));
     return r;
 }
 
 __device__ __forceinline__ void st256(double *p, const D4 &v)
 {
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.e[0]), "d"(v.e[1]), "d"(v.e[2]), "d"(v.e[3]));
+    asm volatile("st.global" EQS_PSO_STHINT ".v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.e[0]), "d"(v.e[1]), "d"(v.e[2]), "d"(v.e[3]));
 }
 
 __device__ __forceinline__ long long goff(const PsoDev &P, int q, long long li) { return ((long long)q * P.ld + li) * 4; }
