@@ -333,6 +333,9 @@ def main():
     except Exception:
         pass
 
+    # the same access pattern with the arithmetic removed, measured now on this GPU (informational second ceiling)
+    pattern = ctx.measure_pattern(n, per_gpu) if n % 8 == 0 else None
+
     line = {
         "metric": "particle-evals/s", "value": value, "unit": "particle-evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -352,7 +355,11 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "pso_step_kernel",
                      "algorithmic_bytes_per_eval": algorithmic_bytes_per_eval(n),
-                     "frac_of_nominal_8000": achieved / 8000.0},
+                     "frac_of_nominal_8000": achieved / 8000.0,
+                     "pattern_ceiling": None if pattern is None else {
+                         "value": pattern, "unit": "GB/s", "frac": achieved / pattern,
+                         "what": "eqs_measure_pattern: this kernel's loads and stores (3 buffers read, 2 written in "
+                                 "place, 256-bit, same layout and grid) with no arithmetic, best of 11 launches"}},
     }
     if world == 1 and not args.no_also:
         line["also"] = also_measured(ctx, E)

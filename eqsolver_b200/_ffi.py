@@ -75,6 +75,7 @@ SYMBOLS = {
     "eqs_device_cos": (C.c_int, [_vp, dp, C.c_int64, dp]),
     "eqs_measure_fp64": (C.c_int, [_vp, dp]),
     "eqs_measure_copy": (C.c_int, [_vp, C.c_int64, dp]),
+    "eqs_measure_pattern": (C.c_int, [_vp, C.c_int32, C.c_int64, dp]),
     "eqs_pso_validate": (C.c_int, [C.POINTER(PsoParams)]),
     "eqs_pso_solve": (C.c_int, [_vp, C.POINTER(PsoParams), dp, dp, C.POINTER(Report)]),
     "eqs_pso_create": (C.c_int, [_vp, C.POINTER(PsoParams), C.POINTER(_vp)]),

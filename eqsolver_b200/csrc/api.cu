@@ -107,6 +107,44 @@ __global__ void __launch_bounds__(256) copy_kernel(const double2 *__restrict__ s
         dst[i] = src[i];
 }
 
+// the ParticleSwarm step's memory traffic with the arithmetic removed: a thread walks the 4-dimension groups of its
+// particle in the [groups][ld][4] layout, 256-bit loads of three buffers, 256-bit stores back into two of them
+// (in place, like x and v), two groups in flight -- the ceiling this access pattern can reach on the machine
+__device__ __forceinline__ void ld4(const double *p, double (&r)[4])
+{
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[0]), "=d"(r[1]), "=d"(r[2]), "=d"(r[3]) : "l"(p));
+}
+__device__ __forceinline__ void st4(double *p, const double (&r)[4])
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r[0]), "d"(r[1]), "d"(r[2]), "d"(r[3]));
+}
+__global__ void __launch_bounds__(256, 2) pattern_kernel(double *a, double *b, const double *c, long long ld, int groups)
+{
+    for (long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x; li < ld; li += (long long)gridDim.x * blockDim.x) {
+        for (int q = 0; q + 2 <= groups; q += 2) {
+            double x[2][4], v[2][4], p[2][4];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const long long off = ((long long)(q + k) * ld + li) * 4;
+                ld4(a + off, x[k]);
+                ld4(b + off, v[k]);
+                ld4(c + off, p[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const long long off = ((long long)(q + k) * ld + li) * 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[k][j] = v[k][j] + p[k][j];
+                    x[k][j] = x[k][j] + v[k][j];
+                }
+                st4(a + off, x[k]);
+                st4(b + off, v[k]);
+            }
+        }
+    }
+}
+
 } // namespace
 
 extern "C" {
@@ -365,6 +403,42 @@ int eqs_measure_copy(eqs_ctx *ctx, int64_t bytes, double *gbps)
     cudaEventDestroy(e1);
     cudaFree(a);
     cudaFree(b);
+    *gbps = best;
+    return EQS_OK;
+    EQS_BOUNDARY_CATCH
+}
+
+int eqs_measure_pattern(eqs_ctx *ctx, int32_t n, int64_t particles, double *gbps)
+{
+    EQS_BOUNDARY_TRY
+    if (!ctx || !gbps || n < 8 || (n & 7) || particles < 1) return EQS_ERR_INCORRECT_INPUT;
+    Ctx *c = &ctx->c;
+    EQS_CUDA(c, cudaSetDevice(c->device));
+    const long long ld = (particles + 31) / 32 * 32;
+    const int groups = n / 4;
+    const size_t bytes = (size_t)groups * ld * 4 * sizeof(double);
+    double *buf[3] = {nullptr, nullptr, nullptr};
+    for (auto &p : buf) {
+        EQS_CUDA(c, cudaMalloc(&p, bytes));
+        EQS_CUDA(c, cudaMemsetAsync(p, 0, bytes, c->stream));
+    }
+    cudaEvent_t e0, e1;
+    EQS_CUDA(c, cudaEventCreate(&e0));
+    EQS_CUDA(c, cudaEventCreate(&e1));
+    const int grid = (int)std::min<long long>(2LL * c->sm_count, (ld + 255) / 256);
+    double best = 0.0;
+    for (int rep = 0; rep < 12; ++rep) { // rep 0 warms up
+        cudaEventRecord(e0, c->stream);
+        pattern_kernel<<<grid, 256, 0, c->stream>>>(buf[0], buf[1], buf[2], ld, groups);
+        cudaEventRecord(e1, c->stream);
+        EQS_CUDA(c, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0) best = std::max(best, 5.0 * (double)bytes / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    for (auto p : buf) cudaFree(p);
     *gbps = best;
     return EQS_OK;
     EQS_BOUNDARY_CATCH

@@ -188,6 +188,12 @@ class Context:
         self.check(_ffi.lib().eqs_measure_copy(self._h, nbytes, C.byref(v)))
         return v.value
 
+    def measure_pattern(self, n: int = 32, particles: int = 1 << 20) -> float:
+        """GB/s of the ParticleSwarm step's access pattern with the arithmetic removed (its own ceiling)."""
+        v = C.c_double(0)
+        self.check(_ffi.lib().eqs_measure_pattern(self._h, n, particles, C.byref(v)))
+        return v.value
+
 
 def unique_id() -> bytes:
     buf = C.create_string_buffer(128)

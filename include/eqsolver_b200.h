@@ -156,6 +156,9 @@ int eqs_device_cos(eqs_ctx *ctx, const double *x, int64_t count, double *out);
 /* measured machine ceilings for the roofline: DFMA issue rate (TFLOP/s) and copy bandwidth (GB/s) */
 int eqs_measure_fp64(eqs_ctx *ctx, double *tflops);
 int eqs_measure_copy(eqs_ctx *ctx, int64_t bytes, double *gbps);
+/* the ParticleSwarm step's access pattern with the arithmetic removed (3 buffers read, 2 of them written in place,
+ * 256-bit accesses in the [n/4][particles][4] layout; n a multiple of 8): GB/s over the 5 streams */
+int eqs_measure_pattern(eqs_ctx *ctx, int32_t n, int64_t particles, double *gbps);
 
 /* ---- ParticleSwarm ------------------------------------------------------------------------- */
 /* ParticleSwarm::new validation, particle_swarm.rs:124-139: EQS_ERR_EXTERNAL when some lower > upper

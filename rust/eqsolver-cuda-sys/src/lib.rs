@@ -144,6 +144,7 @@ extern "C" {
                      a: *mut c_double, b: *mut c_double) -> c_int;
     pub fn eqs_device_cos(ctx: *mut eqs_ctx, x: *const c_double, count: i64, out: *mut c_double) -> c_int;
     pub fn eqs_measure_fp64(ctx: *mut eqs_ctx, tflops: *mut c_double) -> c_int;
+    pub fn eqs_measure_pattern(ctx: *mut eqs_ctx, n: i32, particles: i64, gbps: *mut c_double) -> c_int;
     pub fn eqs_measure_copy(ctx: *mut eqs_ctx, bytes: i64, gbps: *mut c_double) -> c_int;
 
     pub fn eqs_pso_validate(p: *const eqs_pso_params) -> c_int;
