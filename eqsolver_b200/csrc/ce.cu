@@ -96,6 +96,37 @@ __device__ __forceinline__ void ce_sample_coords(const CeDev &P, uint32_t t, lon
     }
 }
 
+// the same coordinates fed to a streaming objective, four (two Philox blocks) at a time where the functor has a
+// feed_vec: its per-coordinate operations and their order are unchanged (objectives.cuh)
+template <class Obj, bool REPLAY>
+__device__ __forceinline__ double ce_sample_cost(const CeDev &P, uint32_t t, long long gi, const double *smu, const double *ssig)
+{
+    const int n = P.n;
+    ObjAcc acc;
+    Obj::begin(acc, n);
+    if constexpr (REPLAY) {
+        const double *z = P.replay + (((long long)t - P.replay_t0) * P.ntotal + gi) * n;
+        for (int d = 0; d < n; ++d) Obj::feed(acc, smu[d] + ssig[d] * z[d], d);
+    } else {
+        int d = 0;
+        for (; d + 4 <= n; d += 4) {
+            double z[4], x[4];
+            normal_pair(philox_draw(P.key, STREAM_CE, t, gi, (uint32_t)(d >> 1)), z[0], z[1]);
+            normal_pair(philox_draw(P.key, STREAM_CE, t, gi, (uint32_t)(d >> 1) + 1u), z[2], z[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = smu[d + j] + ssig[d + j] * z[j];
+            objective_feed_vec<Obj, 4>(acc, x, d);
+        }
+        for (; d < n; d += 2) {
+            double z0, z1;
+            normal_pair(philox_draw(P.key, STREAM_CE, t, gi, (uint32_t)(d >> 1)), z0, z1);
+            Obj::feed(acc, smu[d] + ssig[d] * z0, d);
+            if (d + 1 < n) Obj::feed(acc, smu[d + 1] + ssig[d + 1] * z1, d + 1);
+        }
+    }
+    return Obj::end(acc, n);
+}
+
 __device__ __forceinline__ void load_mu_sigma(const CeDev &P, double *smu, double *ssig)
 {
     for (int d = threadIdx.x; d < P.n; d += blockDim.x) {
@@ -120,10 +151,7 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK) ce
         const long long gi = P.first + li;
         double cost;
         if constexpr (Obj::streaming) {
-            ObjAcc acc;
-            Obj::begin(acc, P.n);
-            ce_sample_coords<REPLAY>(P, t, gi, smu, ssig, [&](double x, int d) { Obj::feed(acc, x, d); });
-            cost = Obj::end(acc, P.n);
+            cost = ce_sample_cost<Obj, REPLAY>(P, t, gi, smu, ssig);
         } else {
             ce_sample_coords<REPLAY>(P, t, gi, smu, ssig, [&](double x, int d) { P.xs[(long long)d * P.ld + li] = x; });
             cost = Obj::eval(StridedView{P.xs + li, P.ld}, P.n);

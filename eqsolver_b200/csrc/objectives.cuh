@@ -29,6 +29,10 @@ inline namespace cos_literal {
 #endif
 
 __device__ __forceinline__ double obj_cos(double y) { return eqs_cos_t<(EQS_COS_TABLE != 0)>(y); }
+template <int M> __device__ __forceinline__ void obj_cos_vec(const double (&y)[M], double (&out)[M])
+{
+    eqs_cos_vec<(EQS_COS_TABLE != 0), M>(y, out);
+}
 
 struct ObjAcc {
     double a, b, p;
@@ -78,6 +82,16 @@ template <> struct Objective<EQS_OBJ_RASTRIGIN> {
     static constexpr bool streaming = true;
     __device__ __forceinline__ static void begin(ObjAcc &s, int n) { s.a = 10.0 * (double)n; }
     __device__ __forceinline__ static void feed(ObjAcc &s, double x, int) { s.a += x * x - 10.0 * obj_cos(kTwoPi * x); }
+    // M consecutive coordinates at once: same operations per coordinate, accumulated in coordinate order
+    template <int M> __device__ __forceinline__ static void feed_vec(ObjAcc &s, const double (&x)[M], int)
+    {
+        double y[M], c[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) y[j] = kTwoPi * x[j];
+        obj_cos_vec<M>(y, c);
+#pragma unroll
+        for (int j = 0; j < M; ++j) s.a += x[j] * x[j] - 10.0 * c[j];
+    }
     __device__ __forceinline__ static double end(const ObjAcc &s, int) { return s.a; }
 };
 
@@ -88,6 +102,18 @@ template <> struct Objective<EQS_OBJ_ACKLEY> {
     {
         s.a += x * x;
         s.b += obj_cos(kTwoPi * x);
+    }
+    template <int M> __device__ __forceinline__ static void feed_vec(ObjAcc &s, const double (&x)[M], int)
+    {
+        double y[M], c[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) y[j] = kTwoPi * x[j];
+        obj_cos_vec<M>(y, c);
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            s.a += x[j] * x[j];
+            s.b += c[j];
+        }
     }
     __device__ __forceinline__ static double end(const ObjAcc &s, int n)
     {
@@ -196,6 +222,17 @@ inline namespace cos_table {
 inline namespace cos_literal {
 #endif
 template <> struct Objective<EQS_OBJ_USER> : public UserObjective {};
+
+// M consecutive coordinates d0 .. d0+M-1 of a streaming functor: its feed_vec when it has one, else feed in order
+template <class Obj, int M> __device__ __forceinline__ void objective_feed_vec(ObjAcc &acc, const double (&x)[M], int d0)
+{
+    if constexpr (requires(ObjAcc &a) { Obj::template feed_vec<M>(a, x, d0); }) {
+        Obj::template feed_vec<M>(acc, x, d0);
+    } else {
+#pragma unroll
+        for (int j = 0; j < M; ++j) Obj::feed(acc, x[j], d0 + j);
+    }
+}
 
 // evaluate any functor through a view (eqs_objective_eval, f(x0), random-access functors)
 template <class Obj, class X> __device__ __forceinline__ double objective_on(const X &x, int n)

@@ -122,9 +122,10 @@ __device__ __forceinline__ void pso_group_math(const PsoDev &P, uint32_t t, long
             double rp, rg;
             step_draw<REPLAY>(P, t, gi, d, rp, rg);
             pso_update(P, x.e[j], v.e[j], pb.e[j], sG[d], rp, rg);
-            if constexpr (Obj::streaming) Obj::feed(acc, x.e[j], d);
+            if constexpr (Obj::streaming && !FULL) Obj::feed(acc, x.e[j], d);
         }
     }
+    if constexpr (Obj::streaming && FULL) objective_feed_vec<Obj, 4>(acc, x.e, 4 * q); // the group's 4 coordinates at once
 }
 
 // K consecutive groups of one particle: all loads first (3K independent 32-byte requests), then math, then stores
