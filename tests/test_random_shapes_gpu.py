@@ -1,0 +1,116 @@
+"""GPU: a seeded sweep over random shapes (dimension, population, objective, mode, seed) against the CPU oracle -- the
+ragged corners (n not a multiple of 4, populations around the tile / window / single-CTA limits) that fixed-size tests
+only sample."""
+import numpy as np
+import pytest
+
+import eqsolver_b200 as E
+from conftest import assert_bit_equal
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+EXACT = [E.Objective.SPHERE, E.Objective.ROSENBROCK, E.Objective.USER, E.Objective.HEAVY]
+
+
+def _pick_population(rng):
+    edge = [1, 2, 31, 32, 33, 255, 256, 257, 2047, 2048, 2049, 4096, 4097]
+    return int(rng.choice(edge)) if rng.random() < 0.5 else int(rng.integers(1, 7000))
+
+
+def test_particle_swarm_random_shapes(ctx):
+    rng = np.random.default_rng(20261019)
+    for case in range(400):
+        obj = EXACT[int(rng.integers(0, len(EXACT)))]
+        n = int(rng.integers(1, 41)) if obj != E.Objective.HEAVY else int(rng.integers(1, 13))
+        N = _pick_population(rng)
+        mode = E.PsoMode.SYNCHRONOUS if rng.random() < 0.5 else E.PsoMode.SEQUENTIAL_EXACT
+        seed = int(rng.integers(0, 2 ** 40))
+        lo, hi = -float(rng.uniform(0.5, 6.0)), float(rng.uniform(0.5, 12.0))
+        x0 = rng.uniform(lo, hi, n)
+        what = f"case {case}: {obj.name} n={n} N={N} {mode.name} seed={seed}"
+        g = (E.ParticleSwarm.new(obj, [lo] * n, [hi] * n).with_particle_count(N).with_tol(0.0).with_seed(seed)
+             .with_mode(mode).with_context(ctx))
+        o = O.Pso(int(obj), [lo] * n, [hi] * n, particle_count=N, tol=0.0, mode=int(mode), seed=seed)
+        run = g.start(x0)
+        o.init(x0)
+        for k in (1, 2):
+            run.step(k)
+            for _ in range(k):
+                assert o.step() == 0
+        for a, b, name in zip(run.state(), o.state(), ("x", "v", "pbest", "pbest cost")):
+            assert_bit_equal(a, b, f"{what}: {name}")
+        gb, gc, it, _, _ = run.gbest()
+        assert_bit_equal(gb, o.gbest(), what + ": gbest")
+        assert gc == o.gbest_cost() and it == o.iters() == 3, what
+        assert_bit_equal(run.ring()[0], o.ring()[0], what + ": ring")
+        assert run.ring()[1] == o.ring()[1], what
+        run.close()
+
+
+def test_cross_entropy_random_shapes(ctx):
+    rng = np.random.default_rng(7)
+    for case in range(150):
+        obj = [E.Objective.SPHERE, E.Objective.ROSENBROCK, E.Objective.USER][int(rng.integers(0, 3))]
+        n = int(rng.integers(1, 33))
+        N = max(2, _pick_population(rng))
+        k = int(rng.integers(2, min(N, 300) + 1))
+        seed = int(rng.integers(0, 2 ** 40))
+        div = E.MeanDivisor.ELITE_COUNT if rng.random() < 0.7 else E.MeanDivisor.REFERENCE_TEN
+        x0, s0 = rng.uniform(-2, 2, n), rng.uniform(0.5, 2.0, n)
+        what = f"case {case}: {obj.name} n={n} N={N} k={k} {div.name} seed={seed}"
+        ce = (E.CrossEntropy.new(obj).with_sample_size(N).with_importance_selection_size(k).with_iter_max(4)
+              .with_std_dev(s0).with_mean_divisor(div).with_seed(seed).with_tol(0.0).with_context(ctx))
+        o = O.Ce(int(obj), x0, sample_size=N, elite_count=k, iter_max=4, std_dev=s0, mean_divisor=int(div), seed=seed,
+                 tol=0.0)
+        run = ce.start(x0)
+        for t in range(2):
+            run.step(1)
+            assert o.step() == 0
+            assert sorted(run.elites().tolist()) == sorted(o.elites().tolist()), what + f": elite set, pass {t}"
+            mu, sg, _, _ = run.state()
+            omu, osg = o.state()
+            scale = float(np.abs(omu).max() + np.abs(osg).max() + 1.0)
+            np.testing.assert_allclose(mu, omu, rtol=1e-11, atol=1e-12 * scale, err_msg=what)
+            np.testing.assert_allclose(sg, osg, rtol=1e-11, atol=1e-12 * scale, err_msg=what)
+        run.close()
+
+
+def test_integrators_random_shapes(ctx):
+    rng = np.random.default_rng(11)
+    for case in range(100):
+        integrand = [E.Objective.SPHERE, E.Objective.ROSENBROCK, E.Objective.GAUSSIAN][int(rng.integers(0, 3))]
+        n = int(rng.integers(1, 10))
+        count = int(rng.choice([2, 3, 255, 256, 257, 1000, 65536, 65537])) if rng.random() < 0.5 else int(rng.integers(2, 90000))
+        lower = rng.uniform(-2, 0, n)
+        upper = lower + rng.uniform(0.1, 3.0, n)
+        seed = int(rng.integers(0, 2 ** 40))
+        what = f"case {case}: {integrand.name} n={n} count={count} seed={seed}"
+        r = E.MonteCarlo.new(integrand).with_sample_count(count).with_context(ctx).integrate_with_seed(lower, upper, seed)
+        st, mean, var = O.mc_integrate(int(integrand), lower, upper, count, seed)
+        assert st == 0, what
+        assert abs(r.mean - mean) <= 1e-12 * max(1.0, abs(mean)), what
+        assert abs(r.variance - var) <= 1e-9 * max(1e-300, abs(var)), what
+    for case in range(60):
+        integrand = [E.Objective.SPHERE, E.Objective.GAUSSIAN, E.Objective.ROSENBROCK][int(rng.integers(0, 3))]
+        n = int(rng.integers(1, 5))
+        kw = dict(sample_count=int(rng.integers(10, 30000)), maximum_depth=int(rng.integers(0, 7)),
+                  min_dim_count=int(rng.integers(1, 64)), alpha=float(rng.uniform(0.5, 3.0)),
+                  dither=float(rng.uniform(0.0, 0.3)))
+        lower = rng.uniform(-1, 0, n)
+        upper = lower + rng.uniform(0.5, 2.0, n)
+        seed = int(rng.integers(0, 2 ** 40))
+        what = f"MISER case {case}: {integrand.name} n={n} {kw} seed={seed}"
+        mi = (E.MISER.new(integrand).with_sample_count(kw["sample_count"]).with_maximum_depth(kw["maximum_depth"])
+              .with_minimum_dimensional_sample_count(kw["min_dim_count"]).with_alpha(kw["alpha"]).with_dither(kw["dither"])
+              .with_context(ctx))
+        st, mean, var, evals = O.miser_integrate(int(integrand), lower, upper, seed=seed, **kw)
+        if st != 0:   # e.g. 1-D Rosenbrock is constant: 0/0 points -> TypeConversionError, like the reference
+            with pytest.raises({O.ERR_TYPE_CONVERSION: E.TypeConversionError, O.ERR_EXTERNAL: E.ExternalError,
+                                O.ERR_INCORRECT_INPUT: E.IncorrectInput}[st]):
+                mi.integrate_with_seed(lower, upper, seed)
+            continue
+        got = mi.integrate_with_seed(lower, upper, seed)
+        assert mi.last_report.evals == evals, what
+        assert abs(got.mean - mean) <= 1e-12 * max(1.0, abs(mean)), what
+        assert abs(got.variance - var) <= 1e-9 * max(1e-300, abs(var)), what
