@@ -114,3 +114,58 @@ def test_integrators_random_shapes(ctx):
         assert mi.last_report.evals == evals, what
         assert abs(got.mean - mean) <= 1e-12 * max(1.0, abs(mean)), what
         assert abs(got.variance - var) <= 1e-9 * max(1e-300, abs(var)), what
+
+
+def test_sharded_particle_swarm_random_shapes(ctx):
+    """The multi-rank protocol (virtual ranks on one GPU, records moved by the harness) on random shapes, including
+    worlds with more ranks than particles: every rank's gbest / ring equals the unsharded oracle bit for bit, and the
+    concatenated shards are its population."""
+    rng = np.random.default_rng(5)
+    for case in range(40):
+        obj = EXACT[int(rng.integers(0, 3))]
+        n = int(rng.integers(1, 20))
+        world = int(rng.integers(2, 7))
+        N = int(rng.choice([1, 2, world - 1, world, world + 1, 63, 64, 65, 257])) if rng.random() < 0.5 else int(rng.integers(1, 1500))
+        N = max(N, 1)
+        seed = int(rng.integers(0, 2 ** 40))
+        lower, upper = [-5.0] * n, [10.0] * n
+        x0 = rng.uniform(-5, 10, n)
+        what = f"case {case}: {obj.name} n={n} N={N} world={world} seed={seed}"
+        base = lambda: (E.ParticleSwarm.new(obj, lower, upper).with_particle_count(N).with_tol(0.0).with_seed(seed)
+                        .with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx))
+        o = O.Pso(int(obj), lower, upper, particle_count=N, tol=0.0, mode=O.SYNCHRONOUS, seed=seed)
+        o.init(x0)
+        ranks = [base().with_virtual_rank(r, world).start() for r in range(world)]
+        assert sum(r.local for r in ranks) == N, what
+
+        def gather():
+            recs = np.stack([r.get_record() for r in ranks])
+            for r in ranks:
+                r.set_records(recs)
+
+        for phase in (0, 1):
+            for r in ranks:
+                r.init_local(x0, phase)
+            gather()
+        for r in ranks:
+            r.init_apply()
+        for t in range(4):
+            for r in ranks:
+                g, c, it, _, _ = r.gbest()
+                assert_bit_equal(g, o.gbest(), what + f": gbest pass {t}")
+                assert c == o.gbest_cost() and it == o.iters(), what
+                assert_bit_equal(r.ring()[0], o.ring()[0], what + ": ring")
+                assert r.ring()[1] == o.ring()[1], what
+            if t == 3:
+                break
+            assert o.step() == 0
+            for r in ranks:
+                r.step_local()
+            gather()
+            for r in ranks:
+                r.step_apply()
+        parts = [r.state() for r in ranks if r.local > 0]
+        for j, name in enumerate(("x", "v", "pbest", "pbest cost")):
+            assert_bit_equal(np.concatenate([p[j] for p in parts]), o.state()[j], what + ": " + name)
+        for r in ranks:
+            r.close()
