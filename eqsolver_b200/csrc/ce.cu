@@ -544,8 +544,8 @@ int validate_ce_params(const eqs_ce_params *p, std::string *why)
         return st;
     };
     if (!p) return bad(EQS_ERR_INCORRECT_INPUT, "null parameters");
-    if (p->n <= 0 || p->n >= (1 << 28)) return bad(EQS_ERR_INCORRECT_INPUT, "dimension n out of range");
-    if (p->sample_size <= 0) return bad(EQS_ERR_INCORRECT_INPUT, "sample size must be positive");
+    if (p->n <= 0 || p->n > 12800) return bad(EQS_ERR_INCORRECT_INPUT, "dimension n out of range (1..12800: mu, sigma tile in shared memory)");
+    if (p->sample_size <= 0 || p->sample_size > (1LL << 40)) return bad(EQS_ERR_INCORRECT_INPUT, "sample size out of range (1..2^40)");
     // the reference does not validate k: k < 2 divides by zero (:295) and k > N silently averages N samples (:284)
     if (p->elite_count < 2 || p->elite_count > p->sample_size)
         return bad(EQS_ERR_INCORRECT_INPUT, "importance selection size must satisfy 2 <= k <= sample size");

@@ -901,8 +901,9 @@ int validate_pso_params(const eqs_pso_params *p, std::string *why)
     };
     if (!p) return bad(EQS_ERR_INCORRECT_INPUT, "null parameters");
     if (p->n <= 0) return bad(EQS_ERR_INCORRECT_INPUT, "dimension n must be positive");
-    if (p->n >= (1 << 28)) return bad(EQS_ERR_INCORRECT_INPUT, "dimension n must be below 2^28");
+    if (p->n > 12800) return bad(EQS_ERR_INCORRECT_INPUT, "dimension n out of range (1..12800: gbest tile in shared memory)");
     if (p->particle_count < 0 || p->iter_max < 0) return bad(EQS_ERR_INCORRECT_INPUT, "negative count");
+    if (p->particle_count > (1LL << 40)) return bad(EQS_ERR_INCORRECT_INPUT, "particle count out of range (0..2^40)");
     if (p->objective_id < 0 || p->objective_id >= EQS_OBJ_COUNT) return bad(EQS_ERR_INCORRECT_INPUT, "unknown objective id");
     if ((p->objective_id == EQS_OBJ_THREE_CIRCLES || p->objective_id == EQS_OBJ_SINCOS) && p->n != 2)
         return bad(EQS_ERR_INCORRECT_INPUT, "this objective needs n = 2");

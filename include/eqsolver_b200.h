@@ -77,11 +77,11 @@ typedef struct eqs_ce eqs_ce;
 
 /* ParticleSwarm fields (particle_swarm.rs:90-105) + what a closure-free, seedable, sharded build needs. */
 typedef struct {
-    int32_t n;                /* dimension D */
+    int32_t n;                /* dimension D, 1..12800 (gbest tile in shared memory) */
     int32_t objective_id;     /* eqs_objective, replaces `f` */
     int32_t mode;             /* eqs_pso_mode */
     int32_t exchange;         /* eqs_exchange */
-    int64_t particle_count;   /* GLOBAL particle count, with_particle_count :305-333 (default 100) */
+    int64_t particle_count;   /* GLOBAL particle count, with_particle_count :305-333 (default 100), at most 2^40 */
     int64_t iter_max;         /* with_iter_max (default 50, lib.rs:16) */
     double tol;               /* with_tol (default 1e-6, lib.rs:13) */
     double w, c1, c2;         /* inertia / cognitive / social, defaults 0.5 / 1 / 1 (:8-10) */
@@ -101,7 +101,7 @@ typedef struct {
     int32_t objective_id;
     int32_t mean_divisor;     /* eqs_ce_divisor */
     int32_t exchange;         /* eqs_exchange */
-    int64_t sample_size;      /* GLOBAL, with_sample_size (default 100, :8) */
+    int64_t sample_size;      /* GLOBAL, with_sample_size (default 100, :8), at most 2^40 */
     int64_t elite_count;      /* with_importance_selection_size (default 10, :9); 2 <= k <= N */
     int64_t iter_max;         /* the loop runs at most iter_max-1 times (:253-255) */
     double tol;

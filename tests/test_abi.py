@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 from conftest import ROOT
@@ -65,3 +66,66 @@ def test_no_cpu_fallback():
     import eqsolver_b200 as E
     with pytest.raises(E.ExternalError, match="no CUDA device"):
         E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0], [1.0]).solve([0.0])
+
+
+def test_validate_entry_points_survive_garbage():
+    """The host-only *_validate entry points (what `new` / the builders call before any GPU work) on a seeded stream of
+    hostile parameter blocks: null pointers, NaN / infinite / inverted bounds, zero and negative sizes, huge counts.
+    They must answer with a status (never crash), and agree with the reference's rules where those are decidable."""
+    import ctypes as C
+    from eqsolver_b200 import _ffi
+    L = _ffi.lib()
+    rng = np.random.default_rng(99)
+    specials = [0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e308, -1e308, 5e-324]
+    ints = [0, 1, 2, -1, 3, 7, 100, 12800, 12801, 2 ** 31 - 1, -2 ** 31]
+    bigs = [0, 1, 2, -1, 10, 2 ** 40, 2 ** 40 + 1, 2 ** 62, -2 ** 62]
+    statuses = set(range(7))
+    for case in range(600):
+        n = int(rng.choice(ints))
+        m = max(1, min(abs(n), 64))
+        lo = np.array([rng.choice(specials) if rng.random() < 0.3 else rng.uniform(-5, 5) for _ in range(m)])
+        hi = np.array([rng.choice(specials) if rng.random() < 0.3 else rng.uniform(-5, 5) for _ in range(m)])
+        plo = None if rng.random() < 0.1 else lo.ctypes.data_as(_ffi.dp)
+        phi = None if rng.random() < 0.1 else hi.ctypes.data_as(_ffi.dp)
+        obj = int(rng.integers(-2, 13))
+        p = _ffi.PsoParams()
+        p.n, p.objective_id, p.mode, p.exchange = n, obj, int(rng.integers(-1, 4)), int(rng.integers(-1, 4))
+        p.particle_count, p.iter_max = int(rng.choice(bigs)), int(rng.choice(bigs))
+        p.tol, p.w, p.c1, p.c2 = (float(rng.choice(specials)) for _ in range(4))
+        p.lower, p.upper = plo, phi
+        p.virtual_rank, p.virtual_world = int(rng.integers(-2, 5)), int(rng.integers(-2, 5))
+        st = L.eqs_pso_validate(C.byref(p)) if 0 < n <= 64 or plo is None or phi is None or n <= 0 or n > 12800 else None
+        if st is not None:
+            assert st in statuses
+            if st == _ffi.OK:   # what the reference's `new` requires (particle_swarm.rs:124-139)
+                assert np.all(lo[:n] <= hi[:n]) and np.all(np.isfinite(lo[:n])) and np.all(np.isfinite(hi[:n]))
+        c = _ffi.CeParams()
+        sd = np.array([rng.choice(specials) if rng.random() < 0.3 else rng.uniform(0.1, 3) for _ in range(m)])
+        c.n, c.objective_id, c.mean_divisor, c.exchange = n, obj, int(rng.integers(-1, 3)), int(rng.integers(-1, 4))
+        c.sample_size, c.elite_count, c.iter_max = int(rng.choice(bigs)), int(rng.choice(bigs)), int(rng.choice(bigs))
+        c.tol = float(rng.choice(specials))
+        c.std_dev = None if rng.random() < 0.3 or not (0 < n <= 64) else sd.ctypes.data_as(_ffi.dp)
+        c.virtual_rank, c.virtual_world = int(rng.integers(-2, 5)), int(rng.integers(-2, 5))
+        st = L.eqs_ce_validate(C.byref(c))
+        assert st in statuses
+        if st == _ffi.OK:
+            assert 2 <= c.elite_count <= c.sample_size and 0 < n <= 12800
+        if 0 < n <= 64 or plo is None or phi is None or n <= 0 or n > 12800:
+            q = _ffi.McParams()
+            q.n, q.integrand_id, q.sample_count = n, obj, int(rng.choice(bigs))
+            q.from_, q.to = plo, phi
+            st = L.eqs_mc_validate(C.byref(q))
+            assert st in statuses
+            if st == _ffi.OK:
+                assert q.sample_count >= 2 and np.all(lo[:n] <= hi[:n])
+            r = _ffi.MiserParams()
+            r.n, r.integrand_id, r.sample_count = n, obj, int(rng.choice(bigs))
+            r.minimum_dimensional_sample_count, r.maximum_depth = int(rng.choice(bigs)), int(rng.choice(ints))
+            r.alpha, r.dither = float(rng.choice(specials)), float(rng.choice(specials))
+            r.from_, r.to = plo, phi
+            st = L.eqs_miser_validate(C.byref(r))
+            assert st in statuses
+            if st == _ffi.OK:
+                assert 0 <= r.maximum_depth <= 30 and 0 <= r.sample_count <= 2 ** 40
+    assert L.eqs_pso_validate(None) != _ffi.OK and L.eqs_ce_validate(None) != _ffi.OK
+    assert L.eqs_mc_validate(None) != _ffi.OK and L.eqs_miser_validate(None) != _ffi.OK
