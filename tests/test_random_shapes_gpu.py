@@ -169,3 +169,112 @@ def test_sharded_particle_swarm_random_shapes(ctx):
             assert_bit_equal(np.concatenate([p[j] for p in parts]), o.state()[j], what + ": " + name)
         for r in ranks:
             r.close()
+
+
+def _same_numbers(a, b, what):
+    """Bit equality, except that any NaN equals any NaN (x86 and the GPU differ in the payload of a generated NaN)."""
+    a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+    b = np.ascontiguousarray(b, dtype=np.float64).ravel()
+    assert a.shape == b.shape, what
+    both_nan = np.isnan(a) & np.isnan(b)
+    bad = np.flatnonzero((a.view(np.uint64) != b.view(np.uint64)) & ~both_nan)
+    assert bad.size == 0, f"{what}: {bad.size} of {a.size} differ, first at {bad[0]}: {a[bad[0]]!r} vs {b[bad[0]]!r}"
+
+
+def test_hostile_numerics_match_the_oracle(ctx):
+    """NaN / infinite / huge coefficients, tolerances and start points: the GPU path must do what the reference's
+    arithmetic does with them (NaN never wins a `<`, infinities propagate), never hang or crash."""
+    rng = np.random.default_rng(123)
+    specials = [0.0, -0.0, -1.0, 2.5, 1e308, -1e308, np.inf, -np.inf, np.nan, 5e-324]
+    for case in range(200):
+        obj = [E.Objective.SPHERE, E.Objective.ROSENBROCK][int(rng.integers(0, 2))]
+        n, N = int(rng.integers(1, 9)), int(rng.choice([1, 7, 100, 1500, 3000]))
+        mode = E.PsoMode.SYNCHRONOUS if rng.random() < 0.5 else E.PsoMode.SEQUENTIAL_EXACT
+        w, c1, c2, tol = (float(rng.choice(specials)) if rng.random() < 0.5 else float(rng.uniform(0, 1.5)) for _ in range(4))
+        x0 = np.array([float(rng.choice(specials)) if rng.random() < 0.3 else float(rng.uniform(-3, 3)) for _ in range(n)])
+        seed = int(rng.integers(0, 2 ** 32))
+        what = f"case {case}: {obj.name} n={n} N={N} {mode.name} w={w} c1={c1} c2={c2} tol={tol} x0={x0.tolist()} seed={seed}"
+        g = (E.ParticleSwarm.new(obj, [-2.0] * n, [3.0] * n).with_particle_count(N).with_iter_max(4).with_tol(tol)
+             .with_inertia_weight(w).with_cognitive_coefficient(c1).with_social_coefficient(c2).with_seed(seed)
+             .with_mode(mode).with_context(ctx))
+        o = O.Pso(int(obj), [-2.0] * n, [3.0] * n, particle_count=N, iter_max=4, tol=tol, w=w, c1=c1, c2=c2,
+                  mode=int(mode), seed=seed)
+        run = g.start(x0)
+        o.init(x0)
+        for _ in range(3):
+            run.step(1)
+            o.step()
+        for a, b, name in zip(run.state(), o.state(), ("x", "v", "pbest", "pbest cost")):
+            _same_numbers(a, b, f"{what}: {name}")
+        gb, gc, it, stalled, _ = run.gbest()
+        _same_numbers(gb, o.gbest(), what + ": gbest")
+        _same_numbers([gc], [o.gbest_cost()], what + ": gbest cost")
+        assert it == o.iters(), what
+        _same_numbers(run.ring()[0], o.ring()[0], what + ": ring")
+        run.close()
+        _same_numbers(g.solve(x0), o.solve(x0), what + ": solve")
+
+
+def test_cross_entropy_hostile_numerics_match_the_oracle(ctx):
+    """Zero / infinite / NaN standard deviations and start points: where the reference panics (NaN cost in the sort,
+    non-finite sigma in Normal::new) the GPU path returns NotANumber, otherwise it follows the oracle."""
+    rng = np.random.default_rng(321)
+    specials = [0.0, -0.0, -1.0, 1e308, np.inf, -np.inf, np.nan, 5e-324, 1e-300]
+    for case in range(120):
+        obj = [E.Objective.SPHERE, E.Objective.ROSENBROCK][int(rng.integers(0, 2))]
+        n, N = int(rng.integers(1, 7)), int(rng.choice([2, 11, 100, 1024, 1500]))
+        k = int(rng.integers(2, min(N, 40) + 1))
+        s0 = np.array([float(rng.choice(specials)) if rng.random() < 0.3 else float(rng.uniform(0.2, 2)) for _ in range(n)])
+        x0 = np.array([float(rng.choice(specials)) if rng.random() < 0.2 else float(rng.uniform(-3, 3)) for _ in range(n)])
+        tol = float(rng.choice([0.0, 1e-6, np.nan, np.inf, -1.0]))
+        seed = int(rng.integers(0, 2 ** 32))
+        what = f"case {case}: {obj.name} n={n} N={N} k={k} sigma={s0.tolist()} x0={x0.tolist()} tol={tol} seed={seed}"
+        ce = (E.CrossEntropy.new(obj).with_sample_size(N).with_importance_selection_size(k).with_iter_max(5)
+              .with_std_dev(s0).with_mean_divisor(E.MeanDivisor.ELITE_COUNT).with_seed(seed).with_tol(tol).with_context(ctx))
+        o = O.Ce(int(obj), x0, sample_size=N, elite_count=k, iter_max=5, std_dev=s0, mean_divisor=O.DIV_ELITE_COUNT,
+                 seed=seed, tol=tol)
+        try:
+            want = o.solve()
+        except FloatingPointError:
+            with pytest.raises(E.NotANumber):
+                ce.solve(x0)
+            continue
+        got = ce.solve(x0)
+        ok = (np.isnan(got) & np.isnan(want)) | np.isclose(got, want, rtol=1e-10, atol=1e-10) | (got == want)
+        assert ok.all(), f"{what}: {got} vs {want}"
+
+
+def test_miser_hostile_parameters_match_the_oracle(ctx):
+    """alpha / dither from {0, negative, huge, inf, NaN}, degenerate boxes, tiny budgets: same status as the recursive
+    oracle (ExternalError, TypeConversionError, IncorrectInput) or the same numbers."""
+    rng = np.random.default_rng(777)
+    specials = [0.0, -0.0, -1.0, -0.5, 0.49, 0.5, 0.51, 1.0, 1e308, np.inf, -np.inf, np.nan]
+    errors = {O.ERR_TYPE_CONVERSION: E.TypeConversionError, O.ERR_EXTERNAL: E.ExternalError,
+              O.ERR_INCORRECT_INPUT: E.IncorrectInput}
+    seen = set()
+    for case in range(150):
+        integrand = [E.Objective.SPHERE, E.Objective.GAUSSIAN, E.Objective.ROSENBROCK][int(rng.integers(0, 3))]
+        n = int(rng.integers(1, 4))
+        alpha = float(rng.choice(specials)) if rng.random() < 0.5 else float(rng.uniform(0.5, 3))
+        dither = float(rng.choice(specials)) if rng.random() < 0.5 else float(rng.uniform(0, 0.3))
+        kw = dict(sample_count=int(rng.choice([0, 1, 2, 50, 700, 5000])), maximum_depth=int(rng.integers(0, 5)),
+                  min_dim_count=int(rng.choice([0, 1, 2, 32])), alpha=alpha, dither=dither)
+        lower = rng.uniform(-1, 0, n)
+        upper = lower + (0.0 if rng.random() < 0.15 else rng.uniform(0.5, 2.0, n))
+        seed = int(rng.integers(0, 2 ** 32))
+        what = f"case {case}: {integrand.name} n={n} {kw} box={lower.tolist()}..{np.broadcast_to(upper, (n,)).tolist()} seed={seed}"
+        upper = np.broadcast_to(upper, (n,)).copy()
+        mi = (E.MISER.new(integrand).with_sample_count(kw["sample_count"]).with_maximum_depth(kw["maximum_depth"])
+              .with_minimum_dimensional_sample_count(kw["min_dim_count"]).with_alpha(alpha).with_dither(dither)
+              .with_context(ctx))
+        st, mean, var, evals = O.miser_integrate(int(integrand), lower, upper, seed=seed, **kw)
+        seen.add(st)
+        if st != 0:
+            with pytest.raises(errors[st]):
+                mi.integrate_with_seed(lower, upper, seed)
+            continue
+        got = mi.integrate_with_seed(lower, upper, seed)
+        assert mi.last_report.evals == evals, what
+        assert (np.isnan(got.mean) and np.isnan(mean)) or abs(got.mean - mean) <= 1e-12 * max(1.0, abs(mean)), what
+        assert (np.isnan(got.variance) and np.isnan(var)) or abs(got.variance - var) <= 1e-9 * max(1e-300, abs(var)), what
+    assert {0, O.ERR_EXTERNAL, O.ERR_TYPE_CONVERSION} <= seen   # the sweep did reach the error paths
