@@ -278,3 +278,45 @@ def test_miser_hostile_parameters_match_the_oracle(ctx):
         assert (np.isnan(got.mean) and np.isnan(mean)) or abs(got.mean - mean) <= 1e-12 * max(1.0, abs(mean)), what
         assert (np.isnan(got.variance) and np.isnan(var)) or abs(got.variance - var) <= 1e-9 * max(1e-300, abs(var)), what
     assert {0, O.ERR_EXTERNAL, O.ERR_TYPE_CONVERSION} <= seen   # the sweep did reach the error paths
+
+
+def test_sharded_cross_entropy_random_shapes(ctx):
+    """The CrossEntropy exchange protocol (virtual ranks on one GPU: histograms for the distributed select, moment
+    sums in rank order) on random shapes incl. worlds larger than the sample count and ties at the k-th cost."""
+    rng = np.random.default_rng(2024)
+    for case in range(30):
+        obj = [E.Objective.SPHERE, E.Objective.ROSENBROCK][int(rng.integers(0, 2))]
+        n = int(rng.integers(1, 12))
+        world = int(rng.integers(2, 6))
+        N = int(rng.choice([2, 3, world, world + 1, 64, 65, 1025])) if rng.random() < 0.5 else int(rng.integers(2, 3000))
+        N = max(N, 2)
+        k = int(rng.integers(2, min(N, 200) + 1))
+        seed = int(rng.integers(0, 2 ** 40))
+        x0, s0 = rng.uniform(-2, 2, n), rng.uniform(0.5, 2.0, n)
+        what = f"case {case}: {obj.name} n={n} N={N} k={k} world={world} seed={seed}"
+        base = lambda: (E.CrossEntropy.new(obj).with_sample_size(N).with_importance_selection_size(k).with_iter_max(4)
+                        .with_std_dev(s0).with_mean_divisor(E.MeanDivisor.ELITE_COUNT).with_seed(seed).with_tol(0.0)
+                        .with_context(ctx))
+        o = O.Ce(int(obj), x0, sample_size=N, elite_count=k, iter_max=4, std_dev=s0, mean_divisor=O.DIV_ELITE_COUNT,
+                 seed=seed, tol=0.0)
+        ranks = [base().with_virtual_rank(r, world).start(x0) for r in range(world)]
+        assert sum(r.local for r in ranks) == N, what
+        for t in range(2):
+            assert o.step() == 0
+            for ph in range(E.CeRun.N_PHASES):
+                for r in ranks:
+                    r.phase(ph)
+                if ranks[0].exchange_words(ph):
+                    words = np.stack([r.get_exchange(ph) for r in ranks])
+                    for r in ranks:
+                        r.set_exchange(ph, words)
+            el = np.sort(np.concatenate([r.elites() for r in ranks]))
+            assert el.tolist() == np.sort(o.elites()).tolist(), what + f": elite set, pass {t}"
+            omu, osg = o.state()
+            scale = float(np.abs(omu).max() + np.abs(osg).max() + 1.0)
+            for r in ranks:
+                mu, sg, it, act = r.state()
+                np.testing.assert_allclose(mu, omu, rtol=1e-11, atol=1e-12 * scale, err_msg=what)
+                np.testing.assert_allclose(sg, osg, rtol=1e-11, atol=1e-12 * scale, err_msg=what)
+        for r in ranks:
+            r.close()
