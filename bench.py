@@ -200,12 +200,24 @@ def run_reference(args):
     t = o.time_steps(args.steps)
     value = N * args.steps / t
     sample = (f"each step = one sequential-gbest pass over {N} particles of the workload (bounded sample of "
-              f"{per_gpu} per GPU), 1 thread")
+              f"{per_gpu} per GPU), 1 thread: the reference's solve() is single-threaded and its in-loop gbest update "
+              f"is sequential, so one thread is all it can use")
+    # beside it, what every host core gives when the pass is made synchronous and threaded over the particles
+    # (NOT the reference's algorithm; SURVEY 8d's fair per-box figure)
+    cores = os.cpu_count() or 1
+    om = O.Pso(getattr(O, obj), [lo] * n, [hi] * n, particle_count=N, iter_max=10 ** 9, tol=0.0, mode=O.SYNCHRONOUS,
+               seed=SEED)
+    om.init(np.full(n, x0v))
+    om.time_steps_mt(1, cores)
+    steps_m = max(2, min(args.steps, 20))
+    all_cores = {"value": N * steps_m / om.time_steps_mt(steps_m, cores), "unit": "particle-evals/s", "cores": cores,
+                 "kind": "port", "sample": f"{steps_m} synchronous passes over the same {N} particles, {cores} threads"}
     line = {"impl": "reference", "metric": "particle-evals/s", "value": value, "unit": "particle-evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "n": n, "particles_per_gpu": per_gpu, "mode": "sequential (reference)"},
-            "cpu_baseline": {"value": value, "unit": "particle-evals/s", "cores": 1, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "particle-evals/s", "cores": 1, "kind": "port", "sample": sample,
+                             "all_cores": all_cores},
             "e2e": {"value": value, "unit": "particle-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "C restatement of eqsolver's algorithm (oracle/eqs_oracle.c), not the Rust crate: no cargo/rustc here"}
