@@ -1,6 +1,8 @@
 """GPU: a seeded sweep over random shapes (dimension, population, objective, mode, seed) against the CPU oracle -- the
 ragged corners (n not a multiple of 4, populations around the tile / window / single-CTA limits) that fixed-size tests
 only sample."""
+import os
+
 import numpy as np
 import pytest
 
@@ -9,6 +11,9 @@ from conftest import assert_bit_equal
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
+
+# EQS_SWEEP_SEED=k shifts every seed below: the same sweeps over other random shapes (bug hunting beyond the fixed set)
+SWEEP = int(os.environ.get("EQS_SWEEP_SEED", "0"))
 
 EXACT = [E.Objective.SPHERE, E.Objective.ROSENBROCK, E.Objective.USER, E.Objective.HEAVY]
 
@@ -19,7 +24,7 @@ def _pick_population(rng):
 
 
 def test_particle_swarm_random_shapes(ctx):
-    rng = np.random.default_rng(20261019)
+    rng = np.random.default_rng(20261019 + SWEEP)
     for case in range(400):
         obj = EXACT[int(rng.integers(0, len(EXACT)))]
         n = int(rng.integers(1, 41)) if obj != E.Objective.HEAVY else int(rng.integers(1, 13))
@@ -49,7 +54,7 @@ def test_particle_swarm_random_shapes(ctx):
 
 
 def test_cross_entropy_random_shapes(ctx):
-    rng = np.random.default_rng(7)
+    rng = np.random.default_rng(7 + SWEEP)
     for case in range(150):
         obj = [E.Objective.SPHERE, E.Objective.ROSENBROCK, E.Objective.USER][int(rng.integers(0, 3))]
         n = int(rng.integers(1, 33))
@@ -77,7 +82,7 @@ def test_cross_entropy_random_shapes(ctx):
 
 
 def test_integrators_random_shapes(ctx):
-    rng = np.random.default_rng(11)
+    rng = np.random.default_rng(11 + SWEEP)
     for case in range(100):
         integrand = [E.Objective.SPHERE, E.Objective.ROSENBROCK, E.Objective.GAUSSIAN][int(rng.integers(0, 3))]
         n = int(rng.integers(1, 10))
@@ -120,7 +125,7 @@ def test_sharded_particle_swarm_random_shapes(ctx):
     """The multi-rank protocol (virtual ranks on one GPU, records moved by the harness) on random shapes, including
     worlds with more ranks than particles: every rank's gbest / ring equals the unsharded oracle bit for bit, and the
     concatenated shards are its population."""
-    rng = np.random.default_rng(5)
+    rng = np.random.default_rng(5 + SWEEP)
     for case in range(40):
         obj = EXACT[int(rng.integers(0, 3))]
         n = int(rng.integers(1, 20))
@@ -184,7 +189,7 @@ def _same_numbers(a, b, what):
 def test_hostile_numerics_match_the_oracle(ctx):
     """NaN / infinite / huge coefficients, tolerances and start points: the GPU path must do what the reference's
     arithmetic does with them (NaN never wins a `<`, infinities propagate), never hang or crash."""
-    rng = np.random.default_rng(123)
+    rng = np.random.default_rng(123 + SWEEP)
     specials = [0.0, -0.0, -1.0, 2.5, 1e308, -1e308, np.inf, -np.inf, np.nan, 5e-324]
     for case in range(200):
         obj = [E.Objective.SPHERE, E.Objective.ROSENBROCK][int(rng.integers(0, 2))]
@@ -218,7 +223,7 @@ def test_hostile_numerics_match_the_oracle(ctx):
 def test_cross_entropy_hostile_numerics_match_the_oracle(ctx):
     """Zero / infinite / NaN standard deviations and start points: where the reference panics (NaN cost in the sort,
     non-finite sigma in Normal::new) the GPU path returns NotANumber, otherwise it follows the oracle."""
-    rng = np.random.default_rng(321)
+    rng = np.random.default_rng(321 + SWEEP)
     specials = [0.0, -0.0, -1.0, 1e308, np.inf, -np.inf, np.nan, 5e-324, 1e-300]
     for case in range(120):
         obj = [E.Objective.SPHERE, E.Objective.ROSENBROCK][int(rng.integers(0, 2))]
@@ -247,7 +252,7 @@ def test_cross_entropy_hostile_numerics_match_the_oracle(ctx):
 def test_miser_hostile_parameters_match_the_oracle(ctx):
     """alpha / dither from {0, negative, huge, inf, NaN}, degenerate boxes, tiny budgets: same status as the recursive
     oracle (ExternalError, TypeConversionError, IncorrectInput) or the same numbers."""
-    rng = np.random.default_rng(777)
+    rng = np.random.default_rng(777 + SWEEP)
     specials = [0.0, -0.0, -1.0, -0.5, 0.49, 0.5, 0.51, 1.0, 1e308, np.inf, -np.inf, np.nan]
     errors = {O.ERR_TYPE_CONVERSION: E.TypeConversionError, O.ERR_EXTERNAL: E.ExternalError,
               O.ERR_INCORRECT_INPUT: E.IncorrectInput}
@@ -283,7 +288,7 @@ def test_miser_hostile_parameters_match_the_oracle(ctx):
 def test_sharded_cross_entropy_random_shapes(ctx):
     """The CrossEntropy exchange protocol (virtual ranks on one GPU: histograms for the distributed select, moment
     sums in rank order) on random shapes incl. worlds larger than the sample count and ties at the k-th cost."""
-    rng = np.random.default_rng(2024)
+    rng = np.random.default_rng(2024 + SWEEP)
     for case in range(30):
         obj = [E.Objective.SPHERE, E.Objective.ROSENBROCK][int(rng.integers(0, 2))]
         n = int(rng.integers(1, 12))
