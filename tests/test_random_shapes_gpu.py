@@ -33,7 +33,13 @@ def test_particle_swarm_random_shapes(ctx):
         seed = int(rng.integers(0, 2 ** 40))
         lo, hi = -float(rng.uniform(0.5, 6.0)), float(rng.uniform(0.5, 12.0))
         x0 = rng.uniform(lo, hi, n)
-        what = f"case {case}: {obj.name} n={n} N={N} {mode.name} seed={seed}"
+        # sequential mode beyond the single-CTA kernel: force small windows half of the time (many rounds per pass)
+        window = str(int(rng.integers(16, 3000))) if rng.random() < 0.5 else None
+        if window is None:
+            os.environ.pop("EQS_PSO_SEQ_WINDOW", None)
+        else:
+            os.environ["EQS_PSO_SEQ_WINDOW"] = window
+        what = f"case {case}: {obj.name} n={n} N={N} {mode.name} seed={seed} window={window}"
         g = (E.ParticleSwarm.new(obj, [lo] * n, [hi] * n).with_particle_count(N).with_tol(0.0).with_seed(seed)
              .with_mode(mode).with_context(ctx))
         o = O.Pso(int(obj), [lo] * n, [hi] * n, particle_count=N, tol=0.0, mode=int(mode), seed=seed)
@@ -51,6 +57,7 @@ def test_particle_swarm_random_shapes(ctx):
         assert_bit_equal(run.ring()[0], o.ring()[0], what + ": ring")
         assert run.ring()[1] == o.ring()[1], what
         run.close()
+    os.environ.pop("EQS_PSO_SEQ_WINDOW", None)
 
 
 def test_cross_entropy_random_shapes(ctx):
