@@ -594,3 +594,31 @@ struct UserObjective {  // sum (d + 1) * |x_d|^3, streaming form
     assert_bit_equal(out, want)
     L.eqs_ctx_destroy.argtypes = [C.c_void_p]
     L.eqs_ctx_destroy(h)
+
+
+def test_whole_c4_population_on_one_gpu(ctx):
+    """Sized for 180 GB: BASELINE config 4's WHOLE population (2^24 particles x 256 dimensions, 103 GB of state) on one
+    GPU -- 64-bit indexing everywhere, same invariants as the per-GPU shard."""
+    import torch
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 125 * 2 ** 30:
+        pytest.skip("needs ~105 GB of free device memory")
+    n, N = 256, 1 << 24
+    x0 = np.full(n, 30.0)
+    ps = (E.ParticleSwarm.new(E.Objective.ACKLEY, [-32.768] * n, [32.768] * n).with_particle_count(N).with_tol(0.0)
+          .with_seed(1729).with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx))
+    run = ps.start(x0)
+    f0 = O.objective(O.ACKLEY, x0)
+    pbc_prev = run.pbest_costs()
+    assert pbc_prev.size == N and np.isfinite(pbc_prev).all()
+    # spot-check the far end of the index space against the oracle's arithmetic (draws keyed by the 64-bit index)
+    for i in (0, N // 2 + 12345, N - 1):
+        pos_u, _ = O.pso_init_draws(1729, i, n)
+        assert abs(pbc_prev[i] - O.objective(O.ACKLEY, pos_u * 65.536 + -32.768)) <= 1e-12 * pbc_prev[i]
+    run.step(3)
+    g, c, it, stalled, _ = run.gbest()
+    pbc = run.pbest_costs()
+    assert it == 3 and not stalled and np.all(pbc <= pbc_prev)
+    assert c <= pbc.min() and (c == pbc.min() or c == f0)
+    assert abs(O.objective(O.ACKLEY, g) - c) <= 1e-12 * c
+    run.close()
