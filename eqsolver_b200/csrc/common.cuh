@@ -51,6 +51,7 @@ struct Ctx {
     std::mutex cache_mutex;          // solvers sharing a context may be created / destroyed from different threads
     static constexpr size_t kPinnedBytes = 1024;
 
+    static constexpr size_t kArenaCacheMax = (size_t)2 << 30;
     cudaError_t acquire_arena(size_t bytes, void **out, size_t *got)
     {
         std::lock_guard<std::mutex> lock(cache_mutex);
@@ -68,7 +69,9 @@ struct Ctx {
     {
         if (!p) return;
         std::lock_guard<std::mutex> lock(cache_mutex);
-        if (bytes > cached_arena_bytes) {
+        // keep at most one arena, and only a modest one: the cache exists to take cudaMalloc / cudaFree out of
+        // repeated small and medium solves, not to sit on tens of GB after one large solve
+        if (bytes > cached_arena_bytes && bytes <= kArenaCacheMax) {
             if (cached_arena) cudaFree(cached_arena);
             cached_arena = p;
             cached_arena_bytes = bytes;
