@@ -111,6 +111,9 @@ struct Ctx {
         vsnprintf(buf, sizeof buf, fmt, ap);
         va_end(ap);
         error = buf;
+        // a failed runtime call (e.g. cudaMalloc -> cudaErrorMemoryAllocation) stays recorded until it is read; clear
+        // it, or the launch check of the NEXT, unrelated call on this thread reports it again
+        (void)cudaGetLastError();
         return status;
     }
 };

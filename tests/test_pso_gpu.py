@@ -622,3 +622,19 @@ def test_whole_c4_population_on_one_gpu(ctx):
     assert c <= pbc.min() and (c == pbc.min() or c == f0)
     assert abs(O.objective(O.ACKLEY, g) - c) <= 1e-12 * c
     run.close()
+
+
+def test_out_of_device_memory_is_an_error_not_a_crash(ctx):
+    """A population that cannot fit (6.6 TB of state) comes back as ExternalError with the CUDA message, and the
+    context stays usable."""
+    n = 32
+    big = (E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * n, [1.0] * n).with_particle_count(1 << 33)
+           .with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx))
+    with pytest.raises(E.ExternalError, match="(?i)memory"):
+        big.solve(np.zeros(n))
+    with pytest.raises(E.ExternalError, match="(?i)memory"):
+        (E.CrossEntropy.new(E.Objective.SPHERE).with_sample_size(1 << 38).with_importance_selection_size(1 << 36)
+         .with_context(ctx).solve(np.zeros(n)))
+    ok = (E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * n, [1.0] * n).with_particle_count(500).with_seed(1)
+          .with_context(ctx).solve(np.zeros(n)))
+    assert ok.shape == (n,) and np.isfinite(ok).all()
