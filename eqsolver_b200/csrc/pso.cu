@@ -1117,7 +1117,12 @@ int PsoSolver::init_local(const double *x0, int phase)
     return launch_ring_scan();
 }
 
-int PsoSolver::init_apply() { return launch_init_apply(); }
+int PsoSolver::init_apply()
+{
+    EQS_TRY(launch_init_apply());
+    initialised_ = true;
+    return EQS_OK;
+}
 
 int PsoSolver::init(const double *x0)
 {
@@ -1256,6 +1261,7 @@ int PsoSolver::sequential_windowed(int64_t iters)
 
 int PsoSolver::step_local(const double *replay_step)
 {
+    if (!initialised_) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "the population has not been initialised (eqs_pso_init)");
     EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
     if (p_.mode != EQS_PSO_SYNCHRONOUS) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "split-phase stepping is synchronous-mode only");
     if (replay_step) {
@@ -1274,6 +1280,7 @@ int PsoSolver::step_apply() { return launch_step_apply(); }
 
 int PsoSolver::step(int64_t iters, const double *replay_step)
 {
+    if (!initialised_) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "the population has not been initialised (eqs_pso_init)");
     EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
     if (manual_) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "exchange = MANUAL: use the split-phase calls");
     if (replay_step) {
@@ -1338,6 +1345,7 @@ int PsoSolver::sync()
 
 int PsoSolver::read_gbest(double *g, double *cost, int64_t *iters, int32_t *stalled, int64_t *improvements)
 {
+    if (!initialised_) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "the population has not been initialised (eqs_pso_init)");
     EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
     if (g) EQS_CUDA(ctx_, cudaMemcpyAsync(g, d_.G, d_.n * sizeof(double), cudaMemcpyDeviceToHost, ctx_->stream));
     EQS_TRY(fetch_ctrl());
@@ -1350,6 +1358,7 @@ int PsoSolver::read_gbest(double *g, double *cost, int64_t *iters, int32_t *stal
 
 int PsoSolver::read_state(double *x, double *v, double *pb, double *pbc)
 {
+    if (!initialised_) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "the population has not been initialised (eqs_pso_init)");
     EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
     const int n = d_.n, nq = (n + 3) / 4;
     const long long L = d_.nloc, ld = d_.ld;

@@ -103,6 +103,7 @@ public:
     bool manual_ = false;
     bool fused_exchange_ = false; // synchronous step exchanges over peer memory inside the step kernel
     bool in_sync_step_ = false;
+    bool initialised_ = false;    // init() / init_apply() has run: stepping or reading before that is refused
     bool seq_windowed_ = false;   // sequential mode: device-driven windowed rounds (one rank, more than PSO_SMALL_MAX particles)
     int grid_seqw_ = 0;
     double seq_rounds_per_pass_ = 16.0;

@@ -638,3 +638,15 @@ def test_out_of_device_memory_is_an_error_not_a_crash(ctx):
     ok = (E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * n, [1.0] * n).with_particle_count(500).with_seed(1)
           .with_context(ctx).solve(np.zeros(n)))
     assert ok.shape == (n,) and np.isfinite(ok).all()
+
+
+def test_stepping_before_init_is_refused(ctx):
+    run = (E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * 3, [1.0] * 3).with_particle_count(5000)
+           .with_context(ctx).start())          # created, not initialised
+    for call in (lambda: run.step(1), run.gbest, run.state):
+        with pytest.raises(E.IncorrectInput, match="initialised"):
+            call()
+    run.init(np.zeros(3))
+    run.step(2)
+    assert run.gbest()[2] == 2
+    run.close()
