@@ -129,3 +129,40 @@ def test_validate_entry_points_survive_garbage():
                 assert 0 <= r.maximum_depth <= 30 and 0 <= r.sample_count <= 2 ** 40
     assert L.eqs_pso_validate(None) != _ffi.OK and L.eqs_ce_validate(None) != _ffi.OK
     assert L.eqs_mc_validate(None) != _ffi.OK and L.eqs_miser_validate(None) != _ffi.OK
+
+
+def test_null_handles_are_refused_not_dereferenced():
+    """Every entry point taking a handle answers EQS_ERR_INCORRECT_INPUT for NULL (destroy(NULL) is a no-op)."""
+    from eqsolver_b200 import _ffi
+    L = _ffi.lib()
+    null = C.c_void_p()
+    calls = {
+        'eqs_pso_init': (null, None), 'eqs_pso_step': (null, 1, None), 'eqs_pso_sync': (null,),
+        'eqs_pso_read_gbest': (null, None, None, None, None, None), 'eqs_pso_read_state': (null, None, None, None, None),
+        'eqs_ce_step': (null, 1, None), 'eqs_ce_sync': (null,), 'eqs_ce_read_state': (null, None, None, None, None),
+        'eqs_ce_phase': (null, 0, None), 'eqs_ctx_sm_count': (null, None), 'eqs_ctx_rank': (null, None, None),
+        'eqs_objective_eval': (null, 0, None, 1, 1, None), 'eqs_mc_integrate': (null, None, None, None, None),
+        'eqs_miser_integrate': (null, None, None, None, None), 'eqs_pso_solve': (null, None, None, None, None),
+        'eqs_ce_solve': (null, None, None, None, None), 'eqs_pso_create': (null, None, None),
+        'eqs_ce_create': (null, None, None, None), 'eqs_measure_copy': (null, 100, None),
+        'eqs_measure_pattern': (null, 32, 100, None), 'eqs_measure_fp64': (null, None),
+        'eqs_device_cos': (null, None, 1, None), 'eqs_pso_last_step_ms': (null, None, None),
+        'eqs_pso_read_ring': (null, None, None), 'eqs_pso_local_range': (null, None, None),
+        'eqs_pso_init_local': (null, None, 0), 'eqs_pso_init_apply': (null,), 'eqs_pso_step_local': (null, None),
+        'eqs_pso_step_apply': (null,), 'eqs_pso_get_record': (null, None), 'eqs_pso_set_records': (null, None),
+        'eqs_ce_last_step_ms': (null, None, None), 'eqs_ce_read_elites': (null, None, None),
+        'eqs_ce_read_costs': (null, None), 'eqs_ce_local_range': (null, None, None),
+        'eqs_ce_get_exchange': (null, 0, None), 'eqs_ce_set_exchange': (null, 0, None),
+        'eqs_philox_blocks': (null, None, None, 1, None), 'eqs_draws': (null, 0, 0, 0, 0, 1, 1, None, None),
+        'eqs_ctx_comm_init': (null, 0, 1, None), 'eqs_comm_unique_id': (None,), 'eqs_shard_range': (10, 0, 0, None, None),
+    }
+    for name, args in calls.items():
+        assert getattr(L, name)(*args) == _ffi.ERR_INCORRECT_INPUT, name
+    for name in ('eqs_ctx_destroy', 'eqs_pso_destroy', 'eqs_ce_destroy'):
+        assert getattr(L, name)(null) == _ffi.OK, name
+    assert L.eqs_ce_exchange_words(null, 0) == 0
+    # and every handle-taking symbol of the header is in the table above (or is a destroy / validate / pure function)
+    pure = {'eqs_abi_version', 'eqs_last_error', 'eqs_record_doubles', 'eqs_ce_exchange_words', 'eqs_ctx_create',
+            'eqs_ctx_destroy', 'eqs_pso_destroy', 'eqs_ce_destroy', 'eqs_pso_validate', 'eqs_ce_validate',
+            'eqs_mc_validate', 'eqs_miser_validate'}
+    assert set(_ffi.SYMBOLS) - pure == set(calls), sorted(set(_ffi.SYMBOLS) - pure - set(calls))
