@@ -1057,6 +1057,7 @@ int eqs_ce_phase(eqs_ce *h, int32_t phase, const double *replay_normals)
     H_OR_FAIL(h);
     CeSolver &s = h->s;
     Ctx *c = s.ctx_;
+    if (phase < 0 || phase >= CE_PHASES) return c->fail(EQS_ERR_INCORRECT_INPUT, "phase out of range (0..%d)", CE_PHASES - 1);
     EQS_CUDA(c, cudaSetDevice(c->device));
     if (phase == 0) EQS_TRY(s.prepare_replay(replay_normals, 1));
     return s.launch_phase(phase);

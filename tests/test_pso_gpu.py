@@ -650,3 +650,49 @@ def test_stepping_before_init_is_refused(ctx):
     run.step(2)
     assert run.gbest()[2] == 2
     run.close()
+
+
+def test_null_data_pointers_with_live_handles(ctx):
+    """Live context / solver handles but NULL data pointers: a status, never a fault."""
+    import ctypes as C
+    from eqsolver_b200 import _ffi
+    L = _ffi.lib()
+    ok_or_bad = {_ffi.OK, _ffi.ERR_INCORRECT_INPUT}
+    ps = E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * 3, [1.0] * 3).with_particle_count(3000).with_context(ctx)
+    run = ps.start(np.zeros(3))
+    h = run._h
+    assert L.eqs_pso_init(h, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_pso_read_gbest(h, None, None, None, None, None) in ok_or_bad
+    assert L.eqs_pso_read_state(h, None, None, None, None) in ok_or_bad
+    assert L.eqs_pso_read_ring(h, None, None) in ok_or_bad
+    assert L.eqs_pso_last_step_ms(h, None, None) in ok_or_bad | {_ffi.ERR_EXTERNAL}   # no step timed yet
+    assert L.eqs_pso_local_range(h, None, None) in ok_or_bad
+    assert L.eqs_pso_get_record(h, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_pso_set_records(h, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_pso_step(h, -5, None) in ok_or_bad and L.eqs_pso_step(h, 0, None) == _ffi.OK
+    run.step(1)
+    assert run.gbest()[2] == 1
+    run.close()
+    ce = (E.CrossEntropy.new(E.Objective.SPHERE).with_sample_size(2000).with_importance_selection_size(20)
+          .with_context(ctx).start(np.zeros(3)))
+    hc = ce._h
+    assert L.eqs_ce_read_state(hc, None, None, None, None) in ok_or_bad
+    assert L.eqs_ce_read_elites(hc, None, None) in ok_or_bad
+    assert L.eqs_ce_read_costs(hc, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_ce_get_exchange(hc, 1, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_ce_set_exchange(hc, 1, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_ce_phase(hc, 99, None) == _ffi.ERR_INCORRECT_INPUT and L.eqs_ce_phase(hc, -1, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_ce_step(hc, -3, None) in ok_or_bad
+    ce.step(1)
+    ce.close()
+    c = ctx._h
+    assert L.eqs_objective_eval(c, 0, None, 3, 5, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_device_cos(c, None, 5, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_philox_blocks(c, None, None, 4, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_draws(c, 0, 1, 0, 0, 4, 3, None, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_pso_solve(c, None, None, None, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_ce_solve(c, None, None, None, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_mc_integrate(c, None, None, None, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_miser_integrate(c, None, None, None, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_measure_copy(c, 1 << 20, None) == _ffi.ERR_INCORRECT_INPUT
+    assert L.eqs_ctx_comm_init(c, 0, 2, None) != _ffi.OK
