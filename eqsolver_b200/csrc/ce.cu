@@ -725,7 +725,7 @@ public:
         if (phase == 0) {
             dispatch_objective(p_.objective_id, [&]<class Obj>() {
                 auto run = [&](auto kernel) {
-                    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (smem > kSmemOptIn) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     if (sample_grid_ == 0) {
                         int nb = 0;
                         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, CE_BLOCK, smem);
@@ -760,7 +760,7 @@ public:
                 launches_++;
             }
             auto gen = [&](auto kernel) {
-                if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (smem > kSmemOptIn) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 kernel<<<grid_for(D.kcap), CE_BLOCK, smem, s>>>(D);
                 launches_++;
             };
@@ -824,7 +824,7 @@ public:
             int rc = EQS_OK;
             dispatch_objective(p_.objective_id, [&]<class Obj>() {
                 auto run = [&](auto kernel) {
-                    if (small_smem > 48 * 1024 &&
+                    if (small_smem > kSmemOptIn &&
                         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem) != cudaSuccess)
                         rc = ctx_->fail(EQS_ERR_EXTERNAL, "cannot reserve %zu bytes of shared memory", small_smem);
                     if (rc != EQS_OK) return;

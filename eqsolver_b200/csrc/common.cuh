@@ -158,6 +158,11 @@ constexpr size_t MB_BYTES = MB_REC + 2ull * MB_MAX_WORLD * MB_REC_CAP * sizeof(d
 // returns false when the context has no peer mailboxes (single rank, IPC unavailable, or EQS_P2P=0)
 bool comm_p2p(Ctx *ctx, char **mailbox, char *const **d_peers);
 
+// Dynamic shared memory beyond this many bytes is requested with cudaFuncAttributeMaxDynamicSharedMemorySize.  The
+// limit without the opt-in is 48 KB for STATIC + dynamic together, so the threshold leaves room for the kernels' static
+// arrays (a few KB): asking at exactly 48 KB of dynamic memory fails the launch with cudaErrorInvalidValue.
+constexpr size_t kSmemOptIn = 32 * 1024;
+
 // ---- device helpers ------------------------------------------------------------------------------------
 __device__ __forceinline__ double sanitize_cost(double c) { return (c != c) ? __longlong_as_double(0x7ff0000000000000LL) : c; }
 

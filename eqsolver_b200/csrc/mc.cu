@@ -399,7 +399,7 @@ int eqs_mc_integrate(eqs_ctx *ctx, const eqs_mc_params *p, double *mean, double 
     dispatch_objective(p->integrand_id, [&]<class Obj>() {
         if constexpr (Obj::streaming) {
             auto run = [&](auto kernel) {
-                if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (smem > kSmemOptIn) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 kernel<<<grid, MC_BLOCK, smem, s>>>(D);
             };
             if (d_replay) run(mc_kernel<Obj, true>);
@@ -585,7 +585,7 @@ int eqs_miser_integrate(eqs_ctx *ctx, const eqs_miser_params *p, double *mean, d
                 dispatch_objective(p->integrand_id, [&]<class Obj>() {
                     if constexpr (Obj::streaming) {
                         auto kernel = miser_chunk_kernel<Obj>;
-                        if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        if (smem > kSmemOptIn) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                         kernel<<<grid, MS_BLOCK, smem, s>>>(D);
                     }
                 });

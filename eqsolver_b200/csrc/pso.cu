@@ -870,7 +870,7 @@ template <class K> int persistent_grid(Ctx *ctx, K kernel, int block, size_t sme
                                        long long units, int &grid)
 {
     int nb = 0;
-    if (smem > 48 * 1024) EQS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > kSmemOptIn) EQS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     EQS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, block, smem));
     if (nb < 1) return ctx->fail(EQS_ERR_EXTERNAL, "kernel does not fit on an SM (smem %zu)", smem);
     const long long need = std::max(1LL, (units + units_per_block_iter - 1) / units_per_block_iter);
@@ -1304,7 +1304,7 @@ int PsoSolver::step(int64_t iters, const double *replay_step)
         int rc = EQS_OK;
         dispatch_objective(p_.objective_id, [&]<class Obj>() {
             auto run = [&](auto kernel) {
-                if (smem > 48 * 1024 &&
+                if (smem > kSmemOptIn &&
                     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                     rc = ctx_->fail(EQS_ERR_EXTERNAL, "cannot reserve %zu bytes of shared memory", smem);
                 if (rc != EQS_OK) return;
