@@ -696,3 +696,25 @@ def test_null_data_pointers_with_live_handles(ctx):
     assert L.eqs_miser_integrate(c, None, None, None, None) == _ffi.ERR_INCORRECT_INPUT
     assert L.eqs_measure_copy(c, 1 << 20, None) == _ffi.ERR_INCORRECT_INPUT
     assert L.eqs_ctx_comm_init(c, 0, 2, None) != _ffi.OK
+
+
+def test_dynamic_shared_memory_just_below_48k(ctx):
+    """Regression (found by the seed sweep): 47-48 KB of dynamic shared memory plus the kernels' static arrays exceeds
+    the 48 KB a launch gets without the opt-in attribute."""
+    n = 6100                                    # gbest tile 48 800 B
+    lower, upper, x0 = [-2.0] * n, [2.0] * n, np.full(n, 0.5)
+    for mode in (E.PsoMode.SYNCHRONOUS, E.PsoMode.SEQUENTIAL_EXACT):
+        for N in (64, 3000):                    # single-CTA kernel / grid kernels
+            g, o = make(E.Objective.ROSENBROCK, n, N, mode, seed=3, lo=-2.0, hi=2.0)
+            run = g.with_context(ctx).start(x0); o.init(x0)
+            run.step(2); [o.step() for _ in range(2)]
+            compare_state(run, o, True, f"n={n} N={N} {mode.name}")
+            run.close()
+    ce = (E.CrossEntropy.new(E.Objective.ROSENBROCK).with_sample_size(646).with_importance_selection_size(286)
+          .with_iter_max(3).with_std_dev(np.full(19, 1.5)).with_mean_divisor(E.MeanDivisor.ELITE_COUNT).with_seed(5)
+          .with_tol(0.0).with_context(ctx))        # single-CTA CE kernel: (2*19 + 646 + 286*19) * 8 = 48 944 B
+    oc = O.Ce(O.ROSENBROCK, np.zeros(19), sample_size=646, elite_count=286, iter_max=3, std_dev=np.full(19, 1.5),
+              mean_divisor=O.DIV_ELITE_COUNT, seed=5, tol=0.0)
+    np.testing.assert_allclose(ce.solve(np.zeros(19)), oc.solve(), rtol=1e-10, atol=1e-12)
+    r = E.MonteCarlo.new(E.Objective.SPHERE).with_sample_count(5000).with_context(ctx).integrate_with_seed([0.0] * 3050, [1.0] * 3050, 1)
+    assert abs(r.mean - 3050 / 3.0) < 5.0       # 2 * 3050 * 8 = 48 800 B of box data in shared memory
