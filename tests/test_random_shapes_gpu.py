@@ -337,3 +337,33 @@ def test_sharded_cross_entropy_random_shapes(ctx):
                 np.testing.assert_allclose(sg, osg, rtol=1e-11, atol=1e-12 * scale, err_msg=what)
         for r in ranks:
             r.close()
+
+
+def test_particle_swarm_larger_random_shapes(ctx):
+    """A few populations beyond one wave of the grid (75 776 particles): natural multi-window sequential rounds,
+    several grid-stride iterations per thread in the synchronous kernel, ragged dimensions."""
+    os.environ.pop("EQS_PSO_SEQ_WINDOW", None)
+    rng = np.random.default_rng(99 + SWEEP)
+    for case in range(8):
+        obj = EXACT[int(rng.integers(0, 3))]
+        n = int(rng.integers(1, 40))
+        N = int(rng.integers(76_000, 400_000))
+        mode = E.PsoMode.SYNCHRONOUS if case % 2 else E.PsoMode.SEQUENTIAL_EXACT
+        seed = int(rng.integers(0, 2 ** 40))
+        x0 = rng.uniform(-3, 3, n)
+        what = f"case {case}: {obj.name} n={n} N={N} {mode.name} seed={seed}"
+        g = (E.ParticleSwarm.new(obj, [-5.0] * n, [10.0] * n).with_particle_count(N).with_tol(0.0).with_seed(seed)
+             .with_mode(mode).with_context(ctx))
+        o = O.Pso(int(obj), [-5.0] * n, [10.0] * n, particle_count=N, tol=0.0, mode=int(mode), seed=seed)
+        run = g.start(x0)
+        o.init(x0)
+        run.step(3)
+        for _ in range(3):
+            assert o.step() == 0
+        for a, b, name in zip(run.state(), o.state(), ("x", "v", "pbest", "pbest cost")):
+            assert_bit_equal(a, b, f"{what}: {name}")
+        gb, gc, it, _, imp = run.gbest()
+        assert_bit_equal(gb, o.gbest(), what + ": gbest")
+        assert gc == o.gbest_cost() and it == 3, what
+        assert_bit_equal(run.ring()[0], o.ring()[0], what + ": ring")
+        run.close()
