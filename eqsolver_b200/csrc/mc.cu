@@ -75,10 +75,22 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(MC_BLOCK) mc
             if constexpr (REPLAY) {
                 for (int d = 0; d < n; ++d) coord(P.replay[gi * n + d], d);
             } else {
-                for (int p = 0; 2 * p < n; ++p) {
-                    const uint4 w = philox_draw(P.key, STREAM_MC, 0u, gi, (uint32_t)p);
-                    coord(u01(w.x, w.y), 2 * p);
-                    if (2 * p + 1 < n) coord(u01(w.z, w.w), 2 * p + 1);
+                int d = 0;
+                if constexpr (Obj::streaming) { // four coordinates (two Philox blocks) at a time: objectives.cuh feed_vec
+                    for (; d + 4 <= n; d += 4) {
+                        const uint4 w0 = philox_draw(P.key, STREAM_MC, 0u, gi, (uint32_t)(d >> 1));
+                        const uint4 w1 = philox_draw(P.key, STREAM_MC, 0u, gi, (uint32_t)(d >> 1) + 1u);
+                        const double u[4] = {u01(w0.x, w0.y), u01(w0.z, w0.w), u01(w1.x, w1.y), u01(w1.z, w1.w)};
+                        double x[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) x[j] = u[j] * s_box[n + d + j] + s_box[d + j];
+                        objective_feed_vec<Obj, 4>(acc, x, d);
+                    }
+                }
+                for (; d < n; d += 2) {
+                    const uint4 w = philox_draw(P.key, STREAM_MC, 0u, gi, (uint32_t)(d >> 1));
+                    coord(u01(w.x, w.y), d);
+                    if (d + 1 < n) coord(u01(w.z, w.w), d + 1);
                 }
             }
             if constexpr (Obj::streaming) sample = Obj::end(acc, n);
@@ -202,10 +214,20 @@ template <class Obj> __global__ void __launch_bounds__(MS_BLOCK) miser_chunk_ker
             if (i >= B.count) break;
             ObjAcc acc;
             Obj::begin(acc, n);
-            for (int pr = 0; 2 * pr < n; ++pr) {
-                const uint4 w = philox_draw(P.key, STREAM_MISER, B.node_id, B.gbase | i, (uint32_t)pr);
-                Obj::feed(acc, u01(w.x, w.y) * s_box[n + 2 * pr] + s_box[2 * pr], 2 * pr);
-                if (2 * pr + 1 < n) Obj::feed(acc, u01(w.z, w.w) * s_box[n + 2 * pr + 1] + s_box[2 * pr + 1], 2 * pr + 1);
+            int d = 0;
+            for (; d + 4 <= n; d += 4) {
+                const uint4 w0 = philox_draw(P.key, STREAM_MISER, B.node_id, B.gbase | i, (uint32_t)(d >> 1));
+                const uint4 w1 = philox_draw(P.key, STREAM_MISER, B.node_id, B.gbase | i, (uint32_t)(d >> 1) + 1u);
+                const double u[4] = {u01(w0.x, w0.y), u01(w0.z, w0.w), u01(w1.x, w1.y), u01(w1.z, w1.w)};
+                double x[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = u[j] * s_box[n + d + j] + s_box[d + j];
+                objective_feed_vec<Obj, 4>(acc, x, d);
+            }
+            for (; d < n; d += 2) {
+                const uint4 w = philox_draw(P.key, STREAM_MISER, B.node_id, B.gbase | i, (uint32_t)(d >> 1));
+                Obj::feed(acc, u01(w.x, w.y) * s_box[n + d] + s_box[d], d);
+                if (d + 1 < n) Obj::feed(acc, u01(w.z, w.w) * s_box[n + d + 1] + s_box[d + 1], d + 1);
             }
             const double sample = Obj::end(acc, n);
             m.n += 1.0; // Welford, lib.rs:184-186
