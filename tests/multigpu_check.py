@@ -128,6 +128,57 @@ def main():
         assert st == 0 and abs(r.mean - mean) <= 1e-12 * abs(mean) and abs(r.variance - var) <= 1e-10 * abs(var)
         same_everywhere([r.mean, r.variance], "MC result")
 
+    # ---- seeded random shapes over the real exchanges (every rank draws the same shapes) -------------------------
+    rng = np.random.default_rng(31 + int(os.environ.get("EQS_SWEEP_SEED", "0")))
+    exact = [E.Objective.SPHERE, E.Objective.ROSENBROCK, E.Objective.USER]
+    for case in range(24):
+        obj = exact[int(rng.integers(0, 3))]
+        n = int(rng.integers(1, 30))
+        N = int(rng.choice([1, world - 1, world, world + 1, 255, 2049])) if rng.random() < 0.4 else int(rng.integers(1, 9000))
+        N = max(N, 1)
+        mode = E.PsoMode.SYNCHRONOUS if rng.random() < 0.7 else E.PsoMode.SEQUENTIAL_EXACT
+        seed = int(rng.integers(0, 2 ** 40))
+        x0 = rng.uniform(-4, 8, n)
+        what = f"random case {case}: {obj.name} n={n} N={N} {mode.name} seed={seed} rank {rank}"
+        run = (E.ParticleSwarm.new(obj, [-5.0] * n, [10.0] * n).with_particle_count(N).with_tol(0.0).with_seed(seed)
+               .with_mode(mode).with_context(ctx)).start(x0)
+        o = O.Pso(int(obj), [-5.0] * n, [10.0] * n, particle_count=N, tol=0.0, mode=int(mode), seed=seed)
+        o.init(x0)
+        run.step(3)
+        for _ in range(3):
+            o.step()
+        g, c, it, _, _ = run.gbest()
+        assert np.array_equal(g.view(np.uint64), o.gbest().view(np.uint64)) and c == o.gbest_cost() and it == 3, what
+        assert np.array_equal(run.ring()[0].view(np.uint64), o.ring()[0].view(np.uint64)) and run.ring()[1] == o.ring()[1], what
+        first, local_n = E.shard_range(N, world, rank)
+        if local_n > 0:
+            for a, b in zip(run.state(), o.state()):
+                b = np.ascontiguousarray(b[first:first + local_n])
+                assert np.array_equal(np.ascontiguousarray(a).view(np.uint64), b.view(np.uint64)), what
+        run.close()
+    for case in range(8):
+        obj = exact[int(rng.integers(0, 2))]
+        n = int(rng.integers(1, 20))
+        N = int(rng.integers(max(2, world), 20000))
+        k = int(rng.integers(2, min(N, 400) + 1))
+        seed = int(rng.integers(0, 2 ** 40))
+        x0c, s0c = rng.uniform(-2, 2, n), rng.uniform(0.5, 2.0, n)
+        what = f"random CE case {case}: {obj.name} n={n} N={N} k={k} seed={seed} rank {rank}"
+        crun = (E.CrossEntropy.new(obj).with_sample_size(N).with_importance_selection_size(k).with_iter_max(4)
+                .with_std_dev(s0c).with_mean_divisor(E.MeanDivisor.ELITE_COUNT).with_seed(seed).with_tol(0.0)
+                .with_context(ctx)).start(x0c)
+        oc = O.Ce(int(obj), x0c, sample_size=N, elite_count=k, iter_max=4, std_dev=s0c, mean_divisor=O.DIV_ELITE_COUNT,
+                  seed=seed, tol=0.0)
+        for t in range(2):
+            crun.step(1)
+            assert oc.step() == 0
+            mu, sg, _, _ = crun.state()
+            omu, osg = oc.state()
+            scale = float(np.abs(omu).max() + np.abs(osg).max() + 1.0)
+            np.testing.assert_allclose(mu, omu, rtol=1e-11, atol=1e-12 * scale, err_msg=what)
+            np.testing.assert_allclose(sg, osg, rtol=1e-11, atol=1e-12 * scale, err_msg=what)
+        crun.close()
+
     dist.barrier()
     if rank == 0:
         print(f"multigpu_check OK on {world} GPUs")
