@@ -23,6 +23,13 @@ namespace eqs {
 namespace {
 
 constexpr int CE_BLOCK = 256;
+// tuning knobs of ce_sample_kernel (profiles/r01_sweep.md): coordinates per trip of the dimension loop, min CTAs per SM
+#ifndef EQS_CE_DIMS
+#define EQS_CE_DIMS 4
+#endif
+#ifndef EQS_CE_MINBLOCKS
+#define EQS_CE_MINBLOCKS 1
+#endif
 constexpr int CE_BINS = 2048;
 constexpr int CE_PASSES = 6;
 constexpr int CE_TILE = 1024;  // samples per block in flag / compact (256 threads x 4, blocked)
@@ -109,13 +116,15 @@ __device__ __forceinline__ double ce_sample_cost(const CeDev &P, uint32_t t, lon
         for (int d = 0; d < n; ++d) Obj::feed(acc, smu[d] + ssig[d] * z[d], d);
     } else {
         int d = 0;
-        for (; d + 4 <= n; d += 4) {
-            double z[4], x[4];
-            normal_pair(philox_draw(P.key, STREAM_CE, t, gi, (uint32_t)(d >> 1)), z[0], z[1]);
-            normal_pair(philox_draw(P.key, STREAM_CE, t, gi, (uint32_t)(d >> 1) + 1u), z[2], z[3]);
+        constexpr int V = EQS_CE_DIMS; // coordinates per trip: V/2 Philox blocks and Box-Muller pairs in flight
+        for (; d + V <= n; d += V) {
+            double z[V], x[V];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = smu[d + j] + ssig[d + j] * z[j];
-            objective_feed_vec<Obj, 4>(acc, x, d);
+            for (int j = 0; j < V; j += 2)
+                normal_pair(philox_draw(P.key, STREAM_CE, t, gi, (uint32_t)((d + j) >> 1)), z[j], z[j + 1]);
+#pragma unroll
+            for (int j = 0; j < V; ++j) x[j] = smu[d + j] + ssig[d + j] * z[j];
+            objective_feed_vec<Obj, V>(acc, x, d);
         }
         for (; d < n; d += 2) {
             double z0, z1;
@@ -137,7 +146,7 @@ __device__ __forceinline__ void load_mu_sigma(const CeDev &P, double *smu, doubl
 }
 
 // K4: one thread per sample; nothing but the 8-byte cost goes to HBM
-template <class Obj, bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK) ce_sample_kernel(const CeDev P)
+template <class Obj, bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK, EQS_CE_MINBLOCKS) ce_sample_kernel(const CeDev P)
 {
     extern __shared__ double s_ms[];
     CeCtrl *c = P.ctrl;

@@ -71,11 +71,11 @@ __device__ __forceinline__ double u01(uint32_t w_lo, uint32_t w_hi)
 // Stands in for rand_distr's StandardNormal (cross_entropy.rs:270).
 __device__ __forceinline__ void normal_pair(uint4 w, double &z0, double &z1)
 {
-    const double u1 = u01(w.x, w.y);
-    const double u2 = u01(w.z, w.w);
-    const double r = sqrt(-2.0 * log_unit(1.0 - u1));
+    // 1 - u1 = 2 - (1.mantissa): the same value as 1.0 - u01(w.x, w.y) (both differences are exact) in one DADD
+    const double u1c = __dsub_rn(2.0, __hiloint2double((int)((w.y & 0xFFFFFu) | 0x3FF00000u), (int)w.x));
+    const double r = sqrt_boxmuller(-2.0 * log_unit(u1c));
     double s, c;
-    sincospi_unit(2.0 * u2, s, c);
+    sincos2pi_mantissa(__hiloint2double((int)((w.w & 0xFFFFFu) | 0x3FF00000u), (int)w.z), s, c); // u2 = this - 1
     z0 = r * c;
     z1 = r * s;
 }
