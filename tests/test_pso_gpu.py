@@ -64,6 +64,18 @@ def test_draws_match_oracle_bit_exact(ctx):
     np.testing.assert_allclose(z, want, rtol=0, atol=4e-15)  # log/sincospi: libdevice vs glibc
 
 
+def test_box_muller_normals_stay_within_ulps_of_the_oracle(ctx):
+    """devmath.cuh's log / sqrt / sincos against glibc through the whole Box-Muller transform, on 64k normals: the root
+    is correctly rounded and the log and the sine / cosine are within 1-2 ulp, so a normal is within a few ulp of 1."""
+    seed, n, count = 977, 16, 4096
+    (z,) = ctx.draws(2, seed, 5, 2 ** 35, count, n)
+    want = np.stack([O.ce_normals(seed, 5, 2 ** 35 + i, n) for i in range(count)])
+    assert np.isfinite(z).all()
+    err = np.abs(z - want)
+    assert (err <= 8.0 * np.maximum(np.spacing(np.abs(want)), np.spacing(1.0))).all(), err.max()  # a CPU model of the formulas sees <= 3
+    assert (z == want).mean() > 0.5  # most of them agree to the last bit
+
+
 def make(objective, n, N, mode, seed, lo=-5.0, hi=10.0, tol=0.0, iter_max=50):
     lower, upper = [lo] * n, [hi] * n
     g = (E.ParticleSwarm.new(objective, lower, upper).with_particle_count(N).with_iter_max(iter_max).with_tol(tol)
