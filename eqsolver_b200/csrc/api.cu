@@ -36,10 +36,13 @@ int boundary_exception() noexcept
     return EQS_ERR_EXTERNAL;
 }
 const char *boundary_exception_text() noexcept { return g_boundary_text; }
+void boundary_exception_clear() noexcept { g_boundary_text[0] = 0; }
 } // namespace eqs
 
 
 namespace {
+
+constexpr int64_t kDiagMaxCount = (int64_t)1 << 36; // values per call of a diagnostic entry point (grid and size_t arithmetic stay in range)
 
 template <class Obj> __global__ void objective_eval_kernel(const double *x, int n, long long count, double *out)
 {
@@ -197,7 +200,21 @@ int eqs_ctx_destroy(eqs_ctx *ctx)
     EQS_BOUNDARY_CATCH
 }
 
-const char *eqs_last_error(const eqs_ctx *ctx) { return ctx ? ctx->c.error.c_str() : g_create_error.c_str(); }
+const char *eqs_last_error(const eqs_ctx *ctx)
+{
+    // a C++ exception caught at the boundary (out of host memory ...) never reached Ctx::fail: its text is per thread
+    if (boundary_exception_text()[0]) return boundary_exception_text();
+    if (!ctx) return g_create_error.c_str();
+    // hand out a per-thread copy: another thread may fail on the same context while the caller reads the message
+    static thread_local std::string copy;
+    try {
+        std::lock_guard<std::mutex> lock(ctx->c.error_mutex);
+        copy = ctx->c.error;
+    } catch (...) {
+        return "out of host memory";
+    }
+    return copy.c_str();
+}
 
 int eqs_ctx_sm_count(const eqs_ctx *ctx, int *out)
 {
@@ -259,21 +276,19 @@ int eqs_objective_eval(eqs_ctx *ctx, int32_t objective_id, const double *x, int3
         return c->fail(EQS_ERR_INCORRECT_INPUT, "this objective needs n = 2");
     if (count == 0) return EQS_OK;
     EQS_CUDA(c, cudaSetDevice(c->device));
-    double *dx = nullptr, *dout = nullptr;
-    EQS_CUDA(c, cudaMalloc(&dx, sizeof(double) * n * count));
-    EQS_CUDA(c, cudaMalloc(&dout, sizeof(double) * count));
+    if (count > kDiagMaxCount / n) return c->fail(EQS_ERR_INCORRECT_INPUT, "count * n is limited to 2^36 values");
+    DevBuf<double> dx, dout;
+    EQS_CUDA(c, dx.alloc((size_t)n * count));
+    EQS_CUDA(c, dout.alloc((size_t)count));
     EQS_CUDA(c, cudaMemcpyAsync(dx, x, sizeof(double) * n * count, cudaMemcpyHostToDevice, c->stream));
+    double *const px = dx, *const po = dout;
     const bool known = dispatch_objective(objective_id, [&]<class Obj>() {
-        objective_eval_kernel<Obj><<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(dx, n, count, dout);
+        objective_eval_kernel<Obj><<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(px, n, count, po);
     });
-    int st = EQS_OK;
-    if (!known) st = c->fail(EQS_ERR_INCORRECT_INPUT, "unknown objective id %d", objective_id);
-    cudaError_t e = cudaMemcpyAsync(out, dout, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(dx);
-    cudaFree(dout);
-    if (st == EQS_OK && e != cudaSuccess) st = c->fail(EQS_ERR_EXTERNAL, "CUDA error: %s", cudaGetErrorString(e));
-    return st;
+    if (!known) return c->fail(EQS_ERR_INCORRECT_INPUT, "unknown objective id %d", objective_id);
+    EQS_CUDA(c, cudaMemcpyAsync(out, dout, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
+    EQS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EQS_OK;
     EQS_BOUNDARY_CATCH
 }
 
@@ -284,16 +299,15 @@ int eqs_philox_blocks(eqs_ctx *ctx, const uint32_t *ctr, const uint32_t key[2], 
     Ctx *c = &ctx->c;
     if (count == 0) return EQS_OK;
     EQS_CUDA(c, cudaSetDevice(c->device));
-    uint32_t *dc = nullptr, *dout = nullptr;
-    EQS_CUDA(c, cudaMalloc(&dc, 16 * count));
-    EQS_CUDA(c, cudaMalloc(&dout, 16 * count));
+    if (count > kDiagMaxCount / 4) return c->fail(EQS_ERR_INCORRECT_INPUT, "count is limited to 2^34 blocks");
+    DevBuf<uint32_t> dc, dout;
+    EQS_CUDA(c, dc.alloc(4 * (size_t)count));
+    EQS_CUDA(c, dout.alloc(4 * (size_t)count));
     EQS_CUDA(c, cudaMemcpyAsync(dc, ctr, 16 * count, cudaMemcpyHostToDevice, c->stream));
     philox_blocks_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(dc, philox_key(key[0], key[1]), count, dout);
-    cudaError_t e = cudaMemcpyAsync(out, dout, 16 * count, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(dc);
-    cudaFree(dout);
-    if (e != cudaSuccess) return c->fail(EQS_ERR_EXTERNAL, "CUDA error: %s", cudaGetErrorString(e));
+    EQS_CUDA(c, cudaGetLastError());
+    EQS_CUDA(c, cudaMemcpyAsync(out, dout, 16 * count, cudaMemcpyDeviceToHost, c->stream));
+    EQS_CUDA(c, cudaStreamSynchronize(c->stream));
     return EQS_OK;
     EQS_BOUNDARY_CATCH
 }
@@ -305,17 +319,16 @@ int eqs_draws(eqs_ctx *ctx, int32_t kind, uint64_t seed, int64_t t, int64_t firs
     Ctx *c = &ctx->c;
     if (count == 0) return EQS_OK;
     EQS_CUDA(c, cudaSetDevice(c->device));
-    double *da = nullptr, *db = nullptr;
+    if (count > kDiagMaxCount / n) return c->fail(EQS_ERR_INCORRECT_INPUT, "count * n is limited to 2^36 values");
+    DevBuf<double> da, db;
     const size_t bytes = sizeof(double) * n * count;
-    EQS_CUDA(c, cudaMalloc(&da, bytes));
-    EQS_CUDA(c, cudaMalloc(&db, bytes));
+    EQS_CUDA(c, da.alloc((size_t)n * count));
+    EQS_CUDA(c, db.alloc((size_t)n * count));
     draws_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(kind, philox_key(seed), (uint32_t)t, first, count, n, da, db);
-    cudaError_t e = cudaMemcpyAsync(a, da, bytes, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess && kind != 2) e = cudaMemcpyAsync(b, db, bytes, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(da);
-    cudaFree(db);
-    if (e != cudaSuccess) return c->fail(EQS_ERR_EXTERNAL, "CUDA error: %s", cudaGetErrorString(e));
+    EQS_CUDA(c, cudaGetLastError());
+    EQS_CUDA(c, cudaMemcpyAsync(a, da, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (kind != 2) EQS_CUDA(c, cudaMemcpyAsync(b, db, bytes, cudaMemcpyDeviceToHost, c->stream));
+    EQS_CUDA(c, cudaStreamSynchronize(c->stream));
     return EQS_OK;
     EQS_BOUNDARY_CATCH
 }
@@ -327,16 +340,15 @@ int eqs_device_cos(eqs_ctx *ctx, const double *x, int64_t count, double *out)
     Ctx *c = &ctx->c;
     if (count == 0) return EQS_OK;
     EQS_CUDA(c, cudaSetDevice(c->device));
-    double *dx = nullptr, *dout = nullptr;
-    EQS_CUDA(c, cudaMalloc(&dx, sizeof(double) * count));
-    EQS_CUDA(c, cudaMalloc(&dout, sizeof(double) * count));
+    if (count > kDiagMaxCount) return c->fail(EQS_ERR_INCORRECT_INPUT, "count is limited to 2^36 values");
+    DevBuf<double> dx, dout;
+    EQS_CUDA(c, dx.alloc((size_t)count));
+    EQS_CUDA(c, dout.alloc((size_t)count));
     EQS_CUDA(c, cudaMemcpyAsync(dx, x, sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));
     cos_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(dx, count, dout);
-    cudaError_t e = cudaMemcpyAsync(out, dout, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(dx);
-    cudaFree(dout);
-    if (e != cudaSuccess) return c->fail(EQS_ERR_EXTERNAL, "CUDA error: %s", cudaGetErrorString(e));
+    EQS_CUDA(c, cudaGetLastError());
+    EQS_CUDA(c, cudaMemcpyAsync(out, dout, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
+    EQS_CUDA(c, cudaStreamSynchronize(c->stream));
     return EQS_OK;
     EQS_BOUNDARY_CATCH
 }
@@ -347,11 +359,11 @@ int eqs_measure_fp64(eqs_ctx *ctx, double *tflops)
     if (!ctx || !tflops) return EQS_ERR_INCORRECT_INPUT;
     Ctx *c = &ctx->c;
     EQS_CUDA(c, cudaSetDevice(c->device));
-    double *dout = nullptr;
-    EQS_CUDA(c, cudaMalloc(&dout, 8));
-    cudaEvent_t e0, e1;
-    EQS_CUDA(c, cudaEventCreate(&e0));
-    EQS_CUDA(c, cudaEventCreate(&e1));
+    DevBuf<double> dout;
+    EQS_CUDA(c, dout.alloc(1));
+    Event e0, e1;
+    EQS_CUDA(c, e0.create());
+    EQS_CUDA(c, e1.create());
     const int grid = c->sm_count * 8, iters = 2048;
     dfma_kernel<<<grid, 256, 0, c->stream>>>(dout, 64, 1.0000001, 1e-9); // warm-up
     double best = 0.0;
@@ -365,9 +377,6 @@ int eqs_measure_fp64(eqs_ctx *ctx, double *tflops)
         const double flops = 2.0 * 8 * 16 * (double)iters * 256.0 * grid;
         best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(dout);
     *tflops = best;
     return EQS_OK;
     EQS_BOUNDARY_CATCH
@@ -380,13 +389,13 @@ int eqs_measure_copy(eqs_ctx *ctx, int64_t bytes, double *gbps)
     Ctx *c = &ctx->c;
     EQS_CUDA(c, cudaSetDevice(c->device));
     const long long n2 = bytes / 16;
-    double2 *a = nullptr, *b = nullptr;
-    EQS_CUDA(c, cudaMalloc(&a, n2 * 16));
-    EQS_CUDA(c, cudaMalloc(&b, n2 * 16));
+    DevBuf<double2> a, b;
+    EQS_CUDA(c, a.alloc((size_t)n2));
+    EQS_CUDA(c, b.alloc((size_t)n2));
     EQS_CUDA(c, cudaMemsetAsync(a, 0, n2 * 16, c->stream));
-    cudaEvent_t e0, e1;
-    EQS_CUDA(c, cudaEventCreate(&e0));
-    EQS_CUDA(c, cudaEventCreate(&e1));
+    Event e0, e1;
+    EQS_CUDA(c, e0.create());
+    EQS_CUDA(c, e1.create());
     const int grid = c->sm_count * 8;
     copy_kernel<<<grid, 256, 0, c->stream>>>(a, b, n2);
     double best = 0.0;
@@ -399,10 +408,6 @@ int eqs_measure_copy(eqs_ctx *ctx, int64_t bytes, double *gbps)
         cudaEventElapsedTime(&ms, e0, e1);
         best = std::max(best, 2.0 * n2 * 16 / (ms * 1e-3) / 1e9);
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(a);
-    cudaFree(b);
     *gbps = best;
     return EQS_OK;
     EQS_BOUNDARY_CATCH
@@ -417,14 +422,14 @@ int eqs_measure_pattern(eqs_ctx *ctx, int32_t n, int64_t particles, double *gbps
     const long long ld = (particles + 31) / 32 * 32;
     const int groups = n / 4;
     const size_t bytes = (size_t)groups * ld * 4 * sizeof(double);
-    double *buf[3] = {nullptr, nullptr, nullptr};
+    DevBuf<double> buf[3];
     for (auto &p : buf) {
-        EQS_CUDA(c, cudaMalloc(&p, bytes));
+        EQS_CUDA(c, p.alloc(bytes / sizeof(double)));
         EQS_CUDA(c, cudaMemsetAsync(p, 0, bytes, c->stream));
     }
-    cudaEvent_t e0, e1;
-    EQS_CUDA(c, cudaEventCreate(&e0));
-    EQS_CUDA(c, cudaEventCreate(&e1));
+    Event e0, e1;
+    EQS_CUDA(c, e0.create());
+    EQS_CUDA(c, e1.create());
     const int grid = (int)std::min<long long>(2LL * c->sm_count, (ld + 255) / 256);
     double best = 0.0;
     for (int rep = 0; rep < 12; ++rep) { // rep 0 warms up
@@ -436,9 +441,6 @@ int eqs_measure_pattern(eqs_ctx *ctx, int32_t n, int64_t particles, double *gbps
         cudaEventElapsedTime(&ms, e0, e1);
         if (rep > 0) best = std::max(best, 5.0 * (double)bytes / (ms * 1e-3) / 1e9);
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    for (auto p : buf) cudaFree(p);
     *gbps = best;
     return EQS_OK;
     EQS_BOUNDARY_CATCH

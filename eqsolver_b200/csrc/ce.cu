@@ -881,9 +881,9 @@ public:
     // CrossEntropy::solve, cross_entropy.rs:245-306
     int solve(double *out_mu, eqs_report *rep)
     {
-        cudaEvent_t e0, e1;
-        EQS_CUDA(ctx_, cudaEventCreate(&e0));
-        EQS_CUDA(ctx_, cudaEventCreate(&e1));
+        Event e0, e1;
+        EQS_CUDA(ctx_, e0.create());
+        EQS_CUDA(ctx_, e1.create());
         const int64_t l0 = launches_;
         cudaEventRecord(e0, ctx_->stream);
         int st = EQS_OK;
@@ -913,8 +913,6 @@ public:
             rep->init_ms = 0.0;
             rep->loop_ms = ms;
         }
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
         return st;
     }
 

@@ -54,7 +54,8 @@ NcclApi &nccl()
             if (api.handle) break;
         }
         if (!api.handle) {
-            api.error = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
+            const char *why = dlerror(); // a second call would return NULL: dlerror() clears the message it hands out
+            api.error = std::string("cannot load libnccl.so.2: ") + (why ? why : "?");
             return;
         }
         auto sym = [&](const char *s) {

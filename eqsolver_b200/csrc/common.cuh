@@ -12,7 +12,9 @@
 
 // No C++ exception may cross the C ABI (include/eqsolver_b200.h): every extern "C" entry point with a body that can
 // allocate runs between these two; std::bad_alloc and friends come back as EQS_ERR_EXTERNAL.
-#define EQS_BOUNDARY_TRY try {
+#define EQS_BOUNDARY_TRY                                                                                         \
+    try {                                                                                                        \
+        eqs::boundary_exception_clear();
 #define EQS_BOUNDARY_CATCH                                                                                       \
     }                                                                                                            \
     catch (...) { return eqs::boundary_exception(); }
@@ -21,7 +23,8 @@ namespace eqs {
 
 // inside a catch (...): the status for "a C++ exception reached the boundary"; the text is kept per thread
 int boundary_exception() noexcept;
-const char *boundary_exception_text() noexcept;
+const char *boundary_exception_text() noexcept; // "" unless the last failure on this thread was such an exception
+void boundary_exception_clear() noexcept;
 
 
 // ---- exchange record (doubles) --------------------------------------------------------------------------
@@ -40,6 +43,8 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     Comm *comm = nullptr;
     int rank = 0, world = 1;
+    // message behind the last non-zero status; solvers sharing the context may fail on different threads at once
+    mutable std::mutex error_mutex;
     mutable std::string error;
 
     // Allocation caches.  The reference's benchmark shape (benchmarks/multi.rs:70-100) constructs a solver and runs a
@@ -110,7 +115,11 @@ struct Ctx {
         va_start(ap, fmt);
         vsnprintf(buf, sizeof buf, fmt, ap);
         va_end(ap);
-        error = buf;
+        {
+            std::lock_guard<std::mutex> lock(error_mutex);
+            error = buf;
+        }
+        boundary_exception_clear();
         // a failed runtime call (e.g. cudaMalloc -> cudaErrorMemoryAllocation) stays recorded until it is read; clear
         // it, or the launch check of the NEXT, unrelated call on this thread reports it again
         (void)cudaGetLastError();
@@ -140,6 +149,32 @@ namespace eqs {
         int _s = (expr);                                                                                         \
         if (_s != EQS_OK) return _s;                                                                             \
     } while (0)
+
+// device scratch and CUDA events owned by one call: released on every way out of the function
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf()
+    {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t count) { return cudaMalloc(&p, count * sizeof(T)); }
+    operator T *() const { return p; }
+};
+struct Event {
+    cudaEvent_t e = nullptr;
+    Event() = default;
+    Event(const Event &) = delete;
+    Event &operator=(const Event &) = delete;
+    ~Event()
+    {
+        if (e) cudaEventDestroy(e);
+    }
+    cudaError_t create() { return cudaEventCreate(&e); }
+    operator cudaEvent_t() const { return e; }
+};
 
 // comm.cu
 int comm_unique_id(void *out128, std::string &err);

@@ -497,9 +497,9 @@ int eqs_miser_integrate(eqs_ctx *ctx, const eqs_miser_params *p, double *mean, d
     long long evals = 0, launches = 0;
     int levels = 0;
     float total_ms = 0.f;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    EQS_CUDA(c, cudaEventCreate(&e0));
-    EQS_CUDA(c, cudaEventCreate(&e1));
+    Event e0, e1;
+    EQS_CUDA(c, e0.create());
+    EQS_CUDA(c, e1.create());
     int rc = EQS_OK;
 
     while (!level.empty() && rc == EQS_OK) {
@@ -692,8 +692,6 @@ int eqs_miser_integrate(eqs_ctx *ctx, const eqs_miser_params *p, double *mean, d
             break;
         }
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (rc != EQS_OK) return rc;
 
     // ---- results in the recursion's own order: a node's error first, then lower, then upper (`?`, :422-440) ------

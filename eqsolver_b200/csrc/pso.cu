@@ -1429,10 +1429,10 @@ int PsoSolver::set_records(const double *recs)
 // ParticleSwarm::solve, particle_swarm.rs:356-431
 int PsoSolver::solve(const double *x0, double *out_x, eqs_report *rep)
 {
-    cudaEvent_t e0, e1, e2;
-    EQS_CUDA(ctx_, cudaEventCreate(&e0));
-    EQS_CUDA(ctx_, cudaEventCreate(&e1));
-    EQS_CUDA(ctx_, cudaEventCreate(&e2));
+    Event e0, e1, e2;
+    EQS_CUDA(ctx_, e0.create());
+    EQS_CUDA(ctx_, e1.create());
+    EQS_CUDA(ctx_, e2.create());
     const int64_t l0 = launches_;
     EQS_CUDA(ctx_, cudaEventRecord(e0, ctx_->stream));
     int st = init(x0);
@@ -1466,9 +1466,6 @@ int PsoSolver::solve(const double *x0, double *out_x, eqs_report *rep)
         rep->init_ms = ms_init;
         rep->loop_ms = ms_loop;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaEventDestroy(e2);
     return st;
 }
 
