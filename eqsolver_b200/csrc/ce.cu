@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(1024) ce_sigma_apply_kernel(const CeDev P)
 // cost, ties by lower index -- the order of a stable sort, :276), the k elites regenerated into shared memory IN RANK
 // ORDER, and mu / sigma summed by one thread per dimension in exactly the reference's order (:281-297), so with
 // replayed normals and a transcendental-free objective the result is bit-identical to the reference's arithmetic.
-template <class Obj, bool REPLAY> __global__ void __launch_bounds__(1024) ce_small_kernel(const CeDev P, long long iters)
+template <class Obj, bool REPLAY> __global__ void __launch_bounds__(1024, 1) ce_small_kernel(const CeDev P, long long iters)
 {
     extern __shared__ double s_dyn[];
     __shared__ int s_nan;

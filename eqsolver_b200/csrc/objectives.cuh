@@ -145,10 +145,35 @@ template <> struct Objective<EQS_OBJ_THREE_CIRCLES> {
 // O(n^2) by construction in the reference; kept so, for bit parity of each partial sum.
 template <> struct Objective<EQS_OBJ_HEAVY> {
     static constexpr bool streaming = false;
+    // U of the forward sums run side by side: each is still 0 + x_i^2 + x_{i+1}^2 + .. in that order (same bits), but a
+    // thread has U independent DADD chains in flight instead of one (the kernels that call this run one thread per
+    // particle, so a lone chain is pure FP64 latency), and x_j^2 is formed once per U sums.
     template <class X> __device__ __forceinline__ static double eval(const X &x, int n)
     {
+        constexpr int U = 8;
         double acc = 0.0;
-        for (int i = 0; i < n; ++i) {
+        int i = 0;
+        for (; i + U <= n; i += U) {
+            double o[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) o[k] = 0.0;
+#pragma unroll
+            for (int t = 0; t < U; ++t) { // x_{i+t} belongs to the sums that start at or before it
+                const double xj = x[i + t];
+                const double q = xj * xj;
+#pragma unroll
+                for (int k = 0; k <= t; ++k) o[k] += q;
+            }
+            for (int j = i + U; j < n; ++j) {
+                const double xj = x[j];
+                const double q = xj * xj;
+#pragma unroll
+                for (int k = 0; k < U; ++k) o[k] += q;
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) acc += o[k] * o[k];
+        }
+        for (; i < n; ++i) {
             double o = 0.0;
             for (int j = i; j < n; ++j) {
                 const double xj = x[j];
