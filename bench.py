@@ -171,7 +171,7 @@ def also_measured(ctx, E):
     ms, launches = crun.last_step_ms()
     out["c3_cross_entropy"] = {"value": N * 20 / (ms * 1e-3), "unit": "sample-evals/s", "ms_per_pass": ms / 20,
                                "launches_per_pass": launches / 20, "passes": 20,
-                               "bound": "instruction issue, an FP64 instruction taking two slots (DESIGN.md section 4, profiles/r01i_ncu_ce_sample_c3.csv)"}
+                               "bound": "FP64 pipe 62 % busy, issue side (DESIGN.md section 4, profiles/r01i_ncu_ce_sample_c3.csv, profiles/r01i_issue_probe.log)"}
     crun.close()
     # MonteCarlo, the reference's 1-D test integrand at a GPU-sized point count
     count = 1 << 28
