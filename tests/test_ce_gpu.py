@@ -72,6 +72,27 @@ def test_philox_parity_per_iteration(ctx, objective, n):
         assert it == o.iters()
 
 
+@pytest.mark.parametrize("n", [8, 7, 5])
+def test_cosine_arguments_out_of_range_in_some_coordinates(ctx, n):
+    """The sample kernel evaluates four cosines in lock step and repairs the out-of-range ones (|2 pi x| >= 8e5 goes to
+    the full-range cosine) AFTER the arithmetic (devmath.cuh: eqs_cos_vec, LATE).  Ackley's exp(mean cos) shows every
+    cosine: means of 1e16 .. 2e17 in some coordinates, ordinary ones in the others, costs against the oracle's (glibc)."""
+    N, k = 3000, 30
+    x0 = np.array([1e16, 0.3, -2e17, 1.0, 0.5, 3e15, 0.1, -7e16])[:n]
+    s0 = np.full(n, 1.0)
+    ce = (E.CrossEntropy.new(E.Objective.ACKLEY).with_sample_size(N).with_importance_selection_size(k).with_iter_max(3)
+          .with_std_dev(s0).with_mean_divisor(E.MeanDivisor.ELITE_COUNT).with_seed(99).with_tol(0.0).with_context(ctx))
+    run = ce.start(x0)
+    o = O.Ce(int(E.Objective.ACKLEY), x0, sample_size=N, elite_count=k, iter_max=3, std_dev=s0,
+             mean_divisor=O.DIV_ELITE_COUNT, seed=99, tol=0.0)
+    run.step(1)
+    assert o.step() == 0
+    gc, oc = run.costs(), o.costs()
+    assert np.isfinite(gc).all()
+    assert np.ptp(oc) > 0.5  # the cosines of the huge coordinates differ from sample to sample: the check has teeth
+    np.testing.assert_allclose(gc, oc, rtol=1e-12, atol=1e-12)
+
+
 def test_ties_at_kth_cost_lowest_index_first(ctx):
     """Duplicate draws => exactly equal costs; the k-th cost is shared and the tie must split by sample index."""
     n, N, k = 4, 96, 11
