@@ -183,7 +183,7 @@ def also_measured(ctx, E):
     return out
 
 
-def run_reference(args):
+def run_reference(args, out):
     """--impl reference: the reference's CPU algorithm (oracle port; cargo/rustc are absent) on host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -221,8 +221,19 @@ def run_reference(args):
             "e2e": {"value": value, "unit": "particle-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "C restatement of eqsolver's algorithm (oracle/eqs_oracle.c), not the Rust crate: no cargo/rustc here"}
-    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + "\n")
+    out.flush()
     return 0
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries underneath may print there too (NCCL writes its version line to
+    fd 1 when NCCL_DEBUG is set in the environment): from here on fd 1 is stderr, and the returned file is the real
+    stdout, used for the JSON line only."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -236,10 +247,11 @@ def main():
     ap.add_argument("--no-also", action="store_true", help="skip the informational side measurements (N=1 only)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
+    out = claim_stdout()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import torch
     import torch.distributed as dist
@@ -378,7 +390,8 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(args.workload, args.cpu_budget)
-        print(json.dumps(line), flush=True)
+        out.write(json.dumps(line) + "\n")
+        out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
