@@ -183,7 +183,7 @@ def also_measured(ctx, E):
     return out
 
 
-def run_reference(args, out):
+def run_reference(args, json_out):
     """--impl reference: the reference's CPU algorithm (oracle port; cargo/rustc are absent) on host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -221,8 +221,8 @@ def run_reference(args, out):
             "e2e": {"value": value, "unit": "particle-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "C restatement of eqsolver's algorithm (oracle/eqs_oracle.c), not the Rust crate: no cargo/rustc here"}
-    out.write(json.dumps(line) + "\n")
-    out.flush()
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
     return 0
 
 
@@ -247,11 +247,11 @@ def main():
     ap.add_argument("--no-also", action="store_true", help="skip the informational side measurements (N=1 only)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
-    out = claim_stdout()
+    json_out = claim_stdout()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
-        return run_reference(args, out)
+        return run_reference(args, json_out)
 
     import torch
     import torch.distributed as dist
@@ -387,14 +387,16 @@ def main():
     }
     if world == 1 and not args.no_also:
         line["also"] = also_measured(ctx, E)
-    if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_port(args.workload, args.cpu_budget)
-        out.write(json.dumps(line) + "\n")
-        out.flush()
+    # the ranks part before rank 0 formats its line: nothing below is collective, so a failure there cannot leave the
+    # other ranks waiting in a barrier
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_port(args.workload, args.cpu_budget)
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     return 0
 
 
