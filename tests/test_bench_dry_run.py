@@ -19,6 +19,11 @@ import torch
 
 torch.cuda.set_device = lambda d: None
 torch.cuda.synchronize = lambda *a: None
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:       # the multi-rank path: same calls, over gloo and host tensors
+    import torch.distributed as dist
+    _init, _tensor = dist.init_process_group, torch.tensor
+    dist.init_process_group = lambda backend=None, device_id=None, **kw: _init(backend="gloo", **kw)
+    torch.tensor = lambda data, device=None, **kw: _tensor(data, **kw)
 
 
 class Report:
@@ -70,7 +75,8 @@ E = types.ModuleType("eqsolver_b200")
 E.ParticleSwarm, E.CrossEntropy, E.MonteCarlo = Kind("pso"), Kind("ce"), Kind("mc")
 E.Objective = E.PsoMode = E.MeanDivisor = Names()
 ED = types.ModuleType("eqsolver_b200.distributed")
-ED.env_rank_world = lambda: (0, 1, 0)
+ED.env_rank_world = lambda: (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+                             int(os.environ.get("LOCAL_RANK", "0")))
 ED.init_context = lambda local: types.SimpleNamespace(measure_pattern=lambda n, N: 6200.0)
 E.distributed = ED
 sys.modules["eqsolver_b200"], sys.modules["eqsolver_b200.distributed"] = E, ED
@@ -113,3 +119,20 @@ def test_product_arm_flags():
     d = json.loads(line)
     assert d["warmup"] == 3 and d["steps"] == 5        # W >= 3 is enforced
     assert "cpu_baseline" not in d and "also" not in d and d["config"]["n"] == 256
+
+
+def test_product_arm_two_ranks_over_gloo(tmp_path):
+    """The N > 1 control flow (collective decisions, max / sum over ranks, the ranks parting before rank 0 writes its line)
+    as two processes over gloo: rank 0 alone prints, both exit 0, nobody is left in a barrier."""
+    script = tmp_path / "bench_dry_run_driver.py"
+    script.write_text(f"ROOT = {ROOT!r}\n" + DRIVER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29567", str(script), "--gpus", "2", "--steps", "12", "--warmup", "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:2000]
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["steps"] == 12 and d["gpu_launches"] == 24           # summed over the ranks
+    assert d["config"]["particles_total"] == 2 * d["config"]["particles_per_gpu"]
+    assert "cpu_baseline" not in d and "also" not in d                                  # N = 1 only
