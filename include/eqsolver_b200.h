@@ -126,7 +126,10 @@ int eqs_abi_version(void);
 int eqs_ctx_create(int device, eqs_ctx **out);
 int eqs_ctx_destroy(eqs_ctx *ctx);
 /* message behind the last non-zero status on this context (feeds SolverError::ExternalError(String));
- * ctx == NULL reads the message of the last failed eqs_ctx_create on this thread. */
+ * ctx == NULL reads the message of the last failed eqs_ctx_create on this thread.  The pointer is a per-thread
+ * copy, valid until this thread's next call of eqs_last_error: other threads may fail on the same context meanwhile.
+ * A C++ exception stopped at the boundary by the calling thread's last entry (out of host memory ...) is reported here
+ * too. */
 const char *eqs_last_error(const eqs_ctx *ctx);
 int eqs_ctx_sm_count(const eqs_ctx *ctx, int *out);
 
