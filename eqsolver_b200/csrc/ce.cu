@@ -692,6 +692,7 @@ public:
         if (bytes > replay_cap_) {
             if (replay_buf_) EQS_CUDA(ctx_, cudaFree(replay_buf_));
             replay_buf_ = nullptr;
+            replay_cap_ = 0; // a failed cudaMalloc below must not leave the old capacity behind
             EQS_CUDA(ctx_, cudaMalloc(&replay_buf_, bytes));
             replay_cap_ = bytes;
         }
