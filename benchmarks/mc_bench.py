@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     a = ap.parse_args()
     import eqsolver_b200 as E
+    # the CPU restatement is the reported baseline timed BESIDE the GPU arm, like bench.py's cpu_baseline leg: the GPU arm
+    # never calls it, and nothing in the eqsolver_b200 package imports oracle/
     from oracle import oracle as O
     ctx = E.Context(0)
     for name, integrand, n in [("gaussian_1d", E.Objective.GAUSSIAN, 1), ("sincos_2d", E.Objective.SINCOS, 2),
