@@ -166,3 +166,23 @@ def test_null_handles_are_refused_not_dereferenced():
             'eqs_ctx_destroy', 'eqs_pso_destroy', 'eqs_ce_destroy', 'eqs_pso_validate', 'eqs_ce_validate',
             'eqs_mc_validate', 'eqs_miser_validate'}
     assert set(_ffi.SYMBOLS) - pure == set(calls), sorted(set(_ffi.SYMBOLS) - pure - set(calls))
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing in the package (Python host layer, CUDA sources, public headers) may
+    import, include, load or mention a path under it; bench.py uses it for the cpu_baseline / reference arm only."""
+    import re
+    from conftest import ROOT
+    pat = re.compile(r"from\s+oracle|import\s+oracle|oracle[/.](oracle|eqs_oracle)|liboracle|eqs_oracle")
+    offenders = []
+    for top in ("eqsolver_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                    continue
+                path = os.path.join(dirpath, f)
+                with open(path, encoding="utf-8", errors="replace") as fh:
+                    for i, line in enumerate(fh, 1):
+                        if pat.search(line) and "oracle/eqs_oracle.c: orc_objective" not in line:
+                            offenders.append(f"{os.path.relpath(path, ROOT)}:{i}: {line.strip()}")
+    assert not offenders, offenders
