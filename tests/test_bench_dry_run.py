@@ -17,13 +17,24 @@ import os, sys, types, runpy
 import numpy as np
 import torch
 
+os.environ["EQS_BENCH_TENSOR_DEVICE"] = "cpu"
 torch.cuda.set_device = lambda d: None
 torch.cuda.synchronize = lambda *a: None
 if int(os.environ.get("WORLD_SIZE", "1")) > 1:       # the multi-rank path: same calls, over gloo and host tensors
     import torch.distributed as dist
-    _init, _tensor = dist.init_process_group, torch.tensor
+    _init = dist.init_process_group
     dist.init_process_group = lambda backend=None, device_id=None, **kw: _init(backend="gloo", **kw)
-    torch.tensor = lambda data, device=None, **kw: _tensor(data, **kw)
+
+
+def shard_range(count, world, rank):
+    base, rem = divmod(count, world)
+    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
+
+
+class Context:
+    def __init__(self, device=0, rank=0, world=1): self.rank, self.world = rank, world
+    def measure_pattern(self, n, N): return 6200.0
+    def measure_fp64(self): return 34.0
 
 
 class Report:
@@ -32,30 +43,40 @@ class Report:
 
 
 class Run:
-    def __init__(self, n):
-        self.n, self.total, self.last = n, 0, 0
+    def __init__(self, b, n):
+        self.b, self.n, self.total, self.last = b, n, 0, 0
+        ctx = b.ctx or Context()
+        self.first, self.local = shard_range(b.count, ctx.world, ctx.rank)
     def step(self, k=1, *a):
         os.write(1, b"library chatter on fd 1\n")      # what NCCL does with NCCL_DEBUG set
         self.total += k; self.last = k
     def sync(self): pass
     def last_step_ms(self): return 0.25 * self.last, self.last
-    def gbest(self): return np.zeros(self.n), 17.5, self.total, 0, 0
+    def gbest(self): return np.zeros(self.n), 17.5, self.total, 0, 3
+    def ring(self): return np.full(50, np.inf), 0
+    def pbest_costs(self): return 0.5 * np.arange(self.first, self.first + self.local)
     def state(self): return np.zeros(self.n), np.ones(self.n), self.total, 1
+    def elites(self):
+        idx = np.arange(self.first, self.first + self.local, dtype=np.int64)
+        return idx[idx < self.b.k]
     def close(self): pass
 
 
 class Builder:
-    def __init__(self, kind): self.kind, self.iter_max, self.count, self.n = kind, 50, 100, 1
+    def __init__(self, kind): self.kind, self.iter_max, self.count, self.k, self.ctx = kind, 50, 100, 10, None
     def __getattr__(self, name):
         if not name.startswith("with_"): raise AttributeError(name)
         def setter(v=None):
             if name == "with_iter_max": self.iter_max = v
             if name in ("with_particle_count", "with_sample_size", "with_sample_count"): self.count = v
+            if name == "with_importance_selection_size": self.k = v
+            if name == "with_context": self.ctx = v
             return self
         return setter
-    def start(self, x0): return Run(len(x0))
+    def start(self, x0): return Run(self, len(x0))
     def solve(self, x0):
-        self.last_report = Report(self.iter_max, 1 + self.count * (1 + self.iter_max))
+        passes = self.iter_max - 1 if self.kind == "ce" else self.iter_max
+        self.last_report = Report(passes, 1 + self.count * (1 + passes))
         return np.zeros(len(x0))
     def integrate_with_seed(self, lo, hi, seed):
         self.last_report = Report(1, self.count)
@@ -74,10 +95,11 @@ class Names:
 E = types.ModuleType("eqsolver_b200")
 E.ParticleSwarm, E.CrossEntropy, E.MonteCarlo = Kind("pso"), Kind("ce"), Kind("mc")
 E.Objective = E.PsoMode = E.MeanDivisor = Names()
+E.Context, E.shard_range = Context, shard_range
 ED = types.ModuleType("eqsolver_b200.distributed")
 ED.env_rank_world = lambda: (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
                              int(os.environ.get("LOCAL_RANK", "0")))
-ED.init_context = lambda local: types.SimpleNamespace(measure_pattern=lambda n, N: 6200.0)
+ED.init_context = lambda local: Context(local, *ED.env_rank_world()[:2])
 E.distributed = ED
 sys.modules["eqsolver_b200"], sys.modules["eqsolver_b200.distributed"] = E, ED
 
@@ -109,7 +131,15 @@ def test_product_arm_prints_exactly_one_json_line():
     assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-12
     assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "port"
     assert d["gpu_launches"] == 40 and d["value"] > 0 and d["ms_per_step"] > 0
-    assert set(d["also"]) == {"c2_sequential_exact", "c3_cross_entropy", "monte_carlo_1d"}
+    assert set(d["also"]) == {"c4", "c3", "c5", "c1", "c2_sequential_exact", "monte_carlo_1d"}
+    for wl, bound in (("c4", "hbm"), ("c3", "fp64"), ("c5", "fp64")):      # every configuration with its own roofline
+        rf = d["also"][wl]["roofline"]
+        assert rf["bound"] == bound and rf["peak"] > 0 and d["also"][wl]["value"] > 0
+        assert rf["frac"] is None or abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    assert d["fp64_peak"]["value"] == 34.0
+    # e2e counts the K passes only: N x K evaluations, not N x (K + 1) + 1
+    assert abs(d["e2e"]["value"] * d["e2e"]["seconds_per_solve"] - (1 << 20) * 40) < 1.0
+    assert "parity_check" not in d                                          # N > 1 only
 
 
 def test_product_arm_flags():
@@ -119,6 +149,15 @@ def test_product_arm_flags():
     d = json.loads(line)
     assert d["warmup"] == 3 and d["steps"] == 5        # W >= 3 is enforced
     assert "cpu_baseline" not in d and "also" not in d and d["config"]["n"] == 256
+
+
+def test_product_arm_cross_entropy_workload():
+    r = _dry_run("--steps", "6", "--warmup", "3", "--no-cpu-baseline", "--no-also", "--workload", "c3")
+    assert r.returncode == 0, r.stderr[-3000:]
+    (line,) = r.stdout.splitlines()
+    d = json.loads(line)
+    assert d["metric"] == d["unit"] == "sample-evals/s" and d["config"]["n"] == 64 and d["roofline"]["bound"] == "fp64"
+    assert d["e2e"]["passes_per_solve"] == 6 and d["gpu_launches"] == 6
 
 
 def test_product_arm_two_ranks_over_gloo(tmp_path):
@@ -135,4 +174,27 @@ def test_product_arm_two_ranks_over_gloo(tmp_path):
     d = json.loads(lines[0])
     assert d["n_gpus"] == 2 and d["steps"] == 12 and d["gpu_launches"] == 24           # summed over the ranks
     assert d["config"]["particles_total"] == 2 * d["config"]["particles_per_gpu"]
-    assert "cpu_baseline" not in d and "also" not in d                                  # N = 1 only
+    assert "cpu_baseline" not in d                                                      # N = 1 only
+    # the sharded-vs-unsharded check ran for both halves of the metric and is in the line
+    assert d["parity_check"] is True and set(d["parity_detail"]) == {"headline", "c3"}
+    assert d["parity_detail"]["headline"]["pbest_cost_checksums_equal"] and d["parity_detail"]["c3"]["elite_set_equal"]
+    assert set(d["also"]) >= {"c4", "c3", "c5", "c1", "c2_sequential_exact"}           # every N carries the other configs
+
+
+def test_parity_failure_takes_every_rank_out(tmp_path):
+    """A sharded result that differs from the unsharded run: rank 0 still prints its line (parity_check false), and EVERY
+    rank exits non-zero -- nobody hangs in a barrier."""
+    script = tmp_path / "bench_dry_run_driver.py"
+    broken = DRIVER.replace("def pbest_costs(self): return 0.5 * np.arange(self.first, self.first + self.local)",
+                            "def pbest_costs(self): return 0.5 * np.arange(self.first, self.first + self.local) + (self.b.ctx.world > 1)")
+    assert broken != DRIVER
+    script.write_text(f"ROOT = {ROOT!r}\n" + broken)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29568", str(script), "--gpus", "2", "--steps", "5", "--warmup", "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode != 0
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["parity_check"] is False and d["parity_detail"]["headline"]["pbest_cost_checksums_equal"] is False
+    assert "parity_check FAILED" in r.stderr
