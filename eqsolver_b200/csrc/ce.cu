@@ -2,13 +2,19 @@
 //
 // Replaces the body of CrossEntropy::solve, reference src/solvers/global_optimisers/cross_entropy.rs:245-306:
 //   ce_sample_kernel   :256-274  x = mu + sigma z (counter-based Philox + Box-Muller in registers), cost only    (K4)
-//   ce_hist / ce_pick  :276      the full sort is replaced by a 6-pass radix SELECT of the k-th cost key          (K5)
-//   ce_flag/scan/compact         elite set = keys below the k-th key + lowest-index ties, in sample order
+//                                + min / max cost key and NaN count of the pass
+//   ce_level_kernel    :276      the full sort is replaced by a radix SELECT of the k-th cost key over the key RANGE (K5)
+//                                of the pass: 11 bits per level, level A over all keys, level B over all keys while it
+//                                compacts the chosen bucket into a candidate list, further levels over that list
+//   ce_count / compact :284,291  elite set = keys below the k-th key + lowest-index ties, in sample order
 //   ce_elite_gen       :284,291  elites are REGENERATED from their counters into a k x n matrix
-//   ce_rowsum + apply  :281-297  two-pass mean / Bessel-corrected sigma per dimension, fixed summation order       (K6)
-//   ce_sigma_apply     :255,299-302  mu, sigma <- new; iter += 1; loop condition for the next pass
-// Each pass is a sequence of PHASES separated by at most one small exchange (histogram or n doubles), so the
-// same code runs on one GPU, over NCCL, or as virtual ranks driven by a test harness.
+//   ce_rowsum          :281-297  two-pass mean / Bessel-corrected sigma per dimension, fixed summation order        (K6)
+//                      :255,299-302  mu, sigma <- new; iter += 1; loop condition for the next pass
+// A pass is EIGHT launches.  Every step that needs all ranks' data (key range, histogram of a level, moment sums) is done
+// by the LAST CTA of the kernel that produced this rank's share: it all-gathers the shares over the peer-memory
+// mailboxes (common.cuh: mailbox_allgather; nothing to gather on one rank) and applies them, so no collective and no
+// extra kernel sits between the stages.  The same device functions also run as separate PHASES with the exchange done
+// outside (virtual ranks driven by a test harness, NCCL when peer mapping is unavailable).
 #include <algorithm>
 #include <cmath>
 #include <new>
@@ -28,42 +34,54 @@ constexpr int CE_BLOCK = 256;
 #define EQS_CE_DIMS 4
 #endif
 #ifndef EQS_CE_MINBLOCKS
-#define EQS_CE_MINBLOCKS 1
+#define EQS_CE_MINBLOCKS 2
 #endif
-constexpr int CE_BINS = 2048;
-constexpr int CE_PASSES = 6;
-constexpr int CE_TILE = 1024;  // samples per block in flag / compact (256 threads x 4, blocked)
+constexpr int CE_BINS = 2048;  // 11 bits per level
+constexpr int CE_LEVELS = 6;   // ceil(64 / 11): what a 64-bit key range can need
+constexpr int CE_TILE = 1024;  // samples per block in count / compact (256 threads x 4, blocked)
 constexpr int CE_CHUNK = 4096; // elites per block in the row sums
-constexpr int CE_PHASES = 9;
+constexpr int CE_PHASES = 10;
 constexpr int CE_SMALL_MAX = 1024; // samples the single-CTA whole-solve kernel takes (one per thread)
 
-__host__ __device__ inline int pass_shift(int pass) { return pass < 5 ? 53 - 11 * pass : 0; }
-__host__ __device__ inline int pass_width(int pass) { return pass < 5 ? 11 : 9; }
+// how the stages of a pass are joined
+enum { CE_PHASED = 0,      // exchange outside the kernels (virtual ranks, NCCL): one phase per exchange
+       CE_FUSED_LOCAL = 1, // one rank: the last CTA applies its own data
+       CE_FUSED_P2P = 2 }; // the last CTA all-gathers over the peer mailboxes, then applies
 
 struct CeCtrl {
-    unsigned long long prefix; // bits of the k-th key decided so far
-    long long k_rem;           // rank of the k-th key inside the current bucket (1-based)
-    long long tie_take;        // samples with key == k-th key this rank contributes (lowest indices first)
+    unsigned long long base;      // lowest key of the bucket that holds the k-th key (level by level); at the end the k-th key
+    unsigned long long bucket_hi; // highest key of that bucket
+    unsigned long long n_cand;    // keys in the candidate list (level B)
+    long long k_rem;              // rank of the k-th key inside the current bucket (1-based)
+    long long tie_take;           // samples with key == k-th key this rank contributes (lowest indices first)
     long long n_elite_local;
-    long long iter;            // the reference's `iter`, starts at 1 (:253)
-    double sigma_inf;          // max |sigma| (:255)
-    int active;                // loop condition :255 for the NEXT pass
-    int nan_cost;              // a NaN cost was seen: the reference panics in the sort (:276)
-    int bad_sigma;             // a non-finite sigma was produced: the reference panics in Normal::new (:259)
+    long long iter;               // the reference's `iter`, starts at 1 (:253)
+    double sigma_inf;             // max |sigma| (:255)
+    int shift;                    // bin of the current level = (key - base) >> shift
+    int sel_done;                 // the k-th key is known
+    int active;                   // loop condition :255 for the NEXT pass
+    int nan_cost;                 // a NaN cost was seen on SOME rank: the reference panics in the sort (:276)
+    int bad_sigma;                // the loop would go on with a non-finite sigma: the reference panics in Normal::new (:259)
+    int p2p_timeout;              // a peer never showed up in a fused exchange
+    unsigned int ticket;          // last-CTA ticket of the fused kernels (left at 0 by each of them)
 };
 
 struct CeDev {
     double *mu, *sigma, *mu_new; // [n]
     double *cost;                // [ld]
     double *xs;                  // [n][ld] only for strided objectives
-    unsigned long long *hsend, *hrecv; // [BINS], [world][BINS]
+    unsigned long long *hsend, *hrecv; // [BINS], [world][BINS]; words 0..2 double as (min key, max key, NaN count) of the pass
     double *msend, *mrecv;       // [n], [world][n]
+    unsigned long long *cand;    // [ld] keys of the bucket chosen at level A, unordered
     int *blk_less, *blk_tie;     // [ntiles]
     long long *blk_tie_off, *blk_el_off;
     long long *elite_idx;        // [kcap] local sample indices, ascending
     double *Ex;                  // [n][kld] regenerated elites
     double *part;                // [n][nchunks]
     CeCtrl *ctrl;
+    char *mailbox;               // peer-memory exchange (common.cuh), or nullptr
+    char *const *peers;
+    long long p2p_timeout_ns;
     const double *replay;
     long long replay_t0;
     long long ld, nloc, first, ntotal, k, kcap, kld, ntiles;
@@ -73,8 +91,6 @@ struct CeDev {
     double tol;
     PhiloxKey key;
 };
-
-__device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
 // order-preserving f64 -> u64: a < b  <=>  key(a) < key(b); NaN sorts last
 __device__ __forceinline__ unsigned long long cost_key(double c)
@@ -145,16 +161,175 @@ __device__ __forceinline__ void load_mu_sigma(const CeDev &P, double *smu, doubl
     __syncthreads();
 }
 
-// K4: one thread per sample; nothing but the 8-byte cost goes to HBM
-template <class Obj, bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK, EQS_CE_MINBLOCKS) ce_sample_kernel(const CeDev P)
+// ---- joining the stages ------------------------------------------------------------------------------------------
+
+// true in exactly one CTA of the grid, the last one to get here (all of its threads); everything the other CTAs wrote
+// or added before their call is visible to it.  Leaves the ticket at 0 for the next kernel.
+__device__ __forceinline__ bool ce_last_block(CeCtrl *c, unsigned total_blocks)
+{
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&c->ticket, 1u);
+        s_last = (t == total_blocks - 1u);
+        if (s_last) c->ticket = 0u;
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+// every rank's 8-byte words of one exchange, wherever the exchange left them: word i of rank r at p[r * stride + i]
+struct Gathered {
+    const unsigned long long *p;
+    long long stride;
+    int world;
+    __device__ __forceinline__ unsigned long long operator()(int r, long long i) const { return __ldcv(p + r * stride + i); }
+    __device__ __forceinline__ double f64(int r, long long i) const { return __longlong_as_double((long long)(*this)(r, i)); }
+};
+
+// one CTA, fused modes: `words` words at `send` (global memory, complete) from every rank
+__device__ __forceinline__ Gathered ce_gather(const CeDev &P, int fused, const unsigned long long *send, long long words)
+{
+    if (fused == CE_FUSED_P2P) {
+        const unsigned long long *slots =
+            mailbox_allgather(P.mailbox, P.peers, P.rank, P.world, send, words, P.p2p_timeout_ns, &P.ctrl->p2p_timeout);
+        return Gathered{slots, MB_REC_CAP, P.world};
+    }
+    return Gathered{send, 0, 1};
+}
+
+// ---- the select, level by level ----------------------------------------------------------------------------------
+
+// start of the select: key range of the pass over all ranks -> first level; a NaN cost on ANY rank stops the pass on
+// EVERY rank before mu, sigma or iter change (the reference panics in the sort, :276).  One CTA.
+__device__ __forceinline__ void ce_select_begin(const CeDev &P, Gathered g)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        CeCtrl *c = P.ctrl;
+        unsigned long long lo = ~0ULL, hi = 0ULL, nan = 0ULL;
+        for (int r = 0; r < g.world; ++r) {
+            const unsigned long long l = g(r, 0), h = g(r, 1);
+            lo = l < lo ? l : lo;
+            hi = h > hi ? h : hi;
+            nan += g(r, 2);
+        }
+        if (nan) {
+            c->nan_cost = 1;
+            c->active = 0;
+        }
+        if (c->p2p_timeout) c->active = 0;
+        const unsigned long long range = hi >= lo ? hi - lo : 0ULL;
+        const int bits = range ? 64 - __clzll((long long)range) : 0;
+        c->base = lo;
+        c->bucket_hi = hi >= lo ? hi : lo;
+        c->shift = bits > 11 ? bits - 11 : 0;
+        c->k_rem = P.k;
+        c->sel_done = 0;
+        c->n_cand = 0ULL;
+        P.hsend[0] = P.hsend[1] = P.hsend[2] = 0ULL; // the histogram of level A accumulates here
+    }
+    __syncthreads();
+}
+
+// pick the bin that holds the k-th key from all ranks' histograms of the current level and descend into it; after the
+// level with shift 0 the bucket is ONE key: split its ties over the ranks (lowest sample indices first).  One CTA of
+// CE_BLOCK threads, 8 bins per thread.
+__device__ __forceinline__ void ce_pick(const CeDev &P, Gathered g)
+{
+    __shared__ long long s_scan[33];
+    __shared__ int s_bin;
+    __shared__ long long s_excl;
+    CeCtrl *c = P.ctrl;
+    const int tid = threadIdx.x;
+    constexpr int PER = CE_BINS / CE_BLOCK;
+    long long h[PER], tot = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        long long v = 0;
+        for (int r = 0; r < g.world; ++r) v += (long long)g(r, tid * PER + j);
+        h[j] = v;
+        tot += v;
+    }
+    const long long k_rem = ((const volatile CeCtrl *)c)->k_rem;
+    if (tid == 0) {
+        s_bin = 0;
+        s_excl = 0;
+    }
+    long long total;
+    long long excl = block_exclusive_scan(tot, 0LL, OpAddLL(), s_scan, total);
+    if (excl < k_rem && k_rem <= excl + tot) {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (excl < k_rem && k_rem <= excl + h[j]) {
+                s_bin = tid * PER + j;
+                s_excl = excl;
+            }
+            excl += h[j];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int shift = c->shift;
+        const unsigned long long base = c->base + ((unsigned long long)s_bin << shift);
+        const unsigned long long top = base + ((1ULL << shift) - 1ULL);
+        const long long rem = k_rem - s_excl;
+        c->base = base;
+        c->bucket_hi = top < c->bucket_hi ? top : c->bucket_hi;
+        c->k_rem = rem;
+        if (shift == 0) { // rem = how many of the samples with key == k-th key are elite, lowest index first
+            long long before = 0;
+            for (int r = 0; r < P.rank && r < g.world; ++r) before += (long long)g(r, s_bin);
+            const long long mine = (long long)g(g.world == 1 ? 0 : P.rank, s_bin);
+            long long take = rem - before;
+            take = take < 0 ? 0 : (take > mine ? mine : take);
+            c->tie_take = take;
+            c->sel_done = 1;
+        } else {
+            c->shift = shift > 11 ? shift - 11 : 0;
+        }
+        if (c->p2p_timeout) c->active = 0;
+    }
+    __syncthreads();
+    for (int b = tid; b < CE_BINS; b += blockDim.x) P.hsend[b] = 0ULL; // ready for the next level
+    __threadfence_block();
+    __syncthreads();
+}
+
+// histogram of the current level over the candidate list into P.hsend (plain stores: one CTA owns it)
+__device__ __forceinline__ void ce_cand_hist(const CeDev &P, unsigned int *sh)
+{
+    const volatile CeCtrl *c = P.ctrl;
+    const unsigned long long base = c->base, bhi = c->bucket_hi, M = c->n_cand;
+    const int shift = c->shift;
+    for (int b = threadIdx.x; b < CE_BINS; b += blockDim.x) sh[b] = 0u;
+    __syncthreads();
+    for (unsigned long long j = threadIdx.x; j < M; j += blockDim.x) {
+        const unsigned long long key = __ldcg(P.cand + j);
+        if (key >= base && key <= bhi) atomicAdd(&sh[(key - base) >> shift], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < CE_BINS; b += blockDim.x) P.hsend[b] = (unsigned long long)sh[b];
+    __threadfence();
+    __syncthreads();
+}
+
+// K4: one thread per sample; nothing but the 8-byte cost goes to HBM.  Also the pass's key range and NaN count; in the
+// fused modes the last CTA opens the select.
+template <class Obj, bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK, EQS_CE_MINBLOCKS) ce_sample_kernel(const CeDev P, int fused)
 {
     extern __shared__ double s_ms[];
+    __shared__ unsigned long long s_lo[CE_BLOCK / 32], s_hi[CE_BLOCK / 32];
+    __shared__ unsigned int s_nan[CE_BLOCK / 32];
     CeCtrl *c = P.ctrl;
     if (!c->active) return;
     const uint32_t t = (uint32_t)(c->iter - 1);
     double *smu = s_ms, *ssig = s_ms + P.n;
     load_mu_sigma(P, smu, ssig);
-    bool nan = false;
+    unsigned long long klo = ~0ULL, khi = 0ULL;
+    unsigned int nan = 0u;
     for (long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x; li < P.nloc;
          li += (long long)gridDim.x * blockDim.x) {
         const long long gi = P.first + li;
@@ -165,86 +340,121 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK, EQ
             ce_sample_coords<REPLAY>(P, t, gi, smu, ssig, [&](double x, int d) { P.xs[(long long)d * P.ld + li] = x; });
             cost = Obj::eval(StridedView{P.xs + li, P.ld}, P.n);
         }
-        P.cost[li] = cost + 0.0; // -0 -> +0 so that key order and `<` agree
-        if (cost != cost) nan = true;
+        cost = cost + 0.0; // -0 -> +0 so that key order and `<` agree
+        P.cost[li] = cost;
+        if (cost != cost) {
+            nan++;
+        } else {
+            const unsigned long long key = cost_key(cost);
+            klo = key < klo ? key : klo;
+            khi = key > khi ? key : khi;
+        }
     }
-    if (nan) c->nan_cost = 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long l = __shfl_down_sync(0xffffffffu, klo, o), h = __shfl_down_sync(0xffffffffu, khi, o);
+        klo = l < klo ? l : klo;
+        khi = h > khi ? h : khi;
+        nan += __shfl_down_sync(0xffffffffu, nan, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_lo[threadIdx.x >> 5] = klo;
+        s_hi[threadIdx.x >> 5] = khi;
+        s_nan[threadIdx.x >> 5] = nan;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < CE_BLOCK / 32; ++w) {
+            klo = s_lo[w] < klo ? s_lo[w] : klo;
+            khi = s_hi[w] > khi ? s_hi[w] : khi;
+            nan += s_nan[w];
+        }
+        if (klo <= khi) {
+            atomicMin(&P.hsend[0], klo);
+            atomicMax(&P.hsend[1], khi);
+        }
+        if (nan) atomicAdd(&P.hsend[2], (unsigned long long)nan);
+    }
+    if (fused == CE_PHASED) return;
+    if (ce_last_block(c, gridDim.x)) ce_select_begin(P, ce_gather(P, fused, P.hsend, 4));
 }
 
-// K5: one radix pass -- histogram of the current digit over the keys that match the decided prefix
-__global__ void __launch_bounds__(CE_BLOCK) ce_hist_kernel(const CeDev P, int pass)
+// K5, levels A and B: histogram of the current level over ALL keys of this rank; level B (`compact`) also copies the keys
+// of the current bucket -- the one level A chose -- into the candidate list, which every later level works on.  Fused
+// modes: the last CTA picks the bin and, at level B, runs the remaining levels over the candidates by itself.
+__global__ void __launch_bounds__(CE_BLOCK) ce_level_kernel(const CeDev P, int compact, int fused)
 {
     __shared__ unsigned int sh[CE_BINS];
-    if (!P.ctrl->active) return;
+    CeCtrl *c = P.ctrl;
+    if (!c->active || c->sel_done) return;
     for (int b = threadIdx.x; b < CE_BINS; b += blockDim.x) sh[b] = 0u;
     __syncthreads();
-    const int shift = pass_shift(pass), width = pass_width(pass);
-    const unsigned long long mask = (1ULL << width) - 1ULL;
-    const unsigned long long prefix = P.ctrl->prefix;
-    const int hi = shift + width;
-    for (long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x; li < P.nloc;
-         li += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long key = cost_key(P.cost[li]);
-        const bool match = pass == 0 || (key >> hi) == (prefix >> hi);
-        if (match) atomicAdd(&sh[(key >> shift) & mask], 1u);
+    const unsigned long long base = c->base, bhi = c->bucket_hi;
+    const int shift = c->shift;
+    const int lane = threadIdx.x & 31;
+    for (long long b0 = (long long)blockIdx.x * blockDim.x; b0 < P.nloc; b0 += (long long)gridDim.x * blockDim.x) {
+        const long long li = b0 + threadIdx.x;
+        unsigned long long key = 0ULL;
+        bool in = false;
+        if (li < P.nloc) {
+            key = cost_key(P.cost[li]);
+            in = key >= base && key <= bhi;
+        }
+        if (in) atomicAdd(&sh[(key - base) >> shift], 1u);
+        if (compact) { // one atomic per warp; the order of the list does not matter
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (m) {
+                unsigned long long at = 0ULL;
+                if (lane == __ffs(m) - 1) at = atomicAdd(&c->n_cand, (unsigned long long)__popc(m));
+                at = __shfl_sync(0xffffffffu, at, __ffs(m) - 1);
+                if (in) P.cand[at + __popc(m & ((1u << lane) - 1u))] = key;
+            }
+        }
     }
     __syncthreads();
     for (int b = threadIdx.x; b < CE_BINS; b += blockDim.x)
         if (sh[b]) atomicAdd(&P.hsend[b], (unsigned long long)sh[b]);
+    if (fused == CE_PHASED) return;
+    if (!ce_last_block(c, gridDim.x)) return;
+    ce_pick(P, ce_gather(P, fused, P.hsend, CE_BINS));
+    if (!compact) return;
+    for (int level = 2; level < CE_LEVELS; ++level) { // the same number of rounds on every rank: the picks are global
+        if (((const volatile CeCtrl *)c)->sel_done) break;
+        ce_cand_hist(P, sh);
+        ce_pick(P, ce_gather(P, fused, P.hsend, CE_BINS));
+    }
 }
 
-// pick the bucket that holds the k-th key from the (all ranks') histograms; after the last pass split the ties
-__global__ void __launch_bounds__(1024) ce_pick_kernel(const CeDev P, int pass)
+// ---- phased mode: the same steps as kernels of their own, the exchange happens between them --------------------------
+__global__ void ce_begin_kernel(const CeDev P)
 {
-    __shared__ long long s_scan[33];
-    __shared__ int s_bin;
-    __shared__ long long s_excl;
-    CeCtrl *c = P.ctrl;
-    if (!c->active) return;
-    const int tid = threadIdx.x;
-    long long h0 = 0, h1 = 0;
-    for (int r = 0; r < P.world; ++r) {
-        h0 += (long long)P.hrecv[(long long)r * CE_BINS + 2 * tid];
-        h1 += (long long)P.hrecv[(long long)r * CE_BINS + 2 * tid + 1];
-    }
-    const long long k_rem = pass == 0 ? P.k : c->k_rem;
-    const unsigned long long prefix = pass == 0 ? 0ULL : c->prefix;
-    if (tid == 0) {
-        s_bin = 0;
-        s_excl = 0;
-    }
-    long long total;
-    const long long excl = block_exclusive_scan(h0 + h1, 0LL, OpAddLL(), s_scan, total);
-    if (excl < k_rem && k_rem <= excl + h0) {
-        s_bin = 2 * tid;
-        s_excl = excl;
-    } else if (excl + h0 < k_rem && k_rem <= excl + h0 + h1) {
-        s_bin = 2 * tid + 1;
-        s_excl = excl + h0;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        c->prefix = prefix | ((unsigned long long)s_bin << pass_shift(pass));
-        const long long rem = k_rem - s_excl;
-        c->k_rem = rem;
-        if (pass == CE_PASSES - 1) { // rem = how many of the samples with key == k-th key are elite, lowest index first
-            long long before = 0;
-            for (int r = 0; r < P.rank; ++r) before += (long long)P.hrecv[(long long)r * CE_BINS + s_bin];
-            const long long mine = (long long)P.hrecv[(long long)P.rank * CE_BINS + s_bin];
-            long long take = rem - before;
-            take = take < 0 ? 0 : (take > mine ? mine : take);
-            c->tie_take = take;
-        }
-    }
-    __syncthreads();
-    for (int b = tid; b < CE_BINS; b += blockDim.x) P.hsend[b] = 0ULL; // ready for the next pass
+    if (!P.ctrl->active) return;
+    ce_select_begin(P, Gathered{P.hrecv, CE_BINS, P.world});
 }
 
-__global__ void __launch_bounds__(CE_BLOCK) ce_flag_kernel(const CeDev P)
+__global__ void __launch_bounds__(CE_BLOCK) ce_pick_kernel(const CeDev P)
+{
+    if (!P.ctrl->active || P.ctrl->sel_done) return;
+    ce_pick(P, Gathered{P.hrecv, CE_BINS, P.world});
+}
+
+__global__ void __launch_bounds__(CE_BLOCK) ce_cand_level_kernel(const CeDev P)
+{
+    __shared__ unsigned int sh[CE_BINS];
+    if (!P.ctrl->active || P.ctrl->sel_done) return;
+    ce_cand_hist(P, sh);
+}
+
+// ---- the elite set in sample order --------------------------------------------------------------------------------
+
+// per tile: samples below the k-th key and samples equal to it; the last CTA turns the counts into offsets
+__global__ void __launch_bounds__(CE_BLOCK) ce_count_kernel(const CeDev P)
 {
     __shared__ int s_a[33], s_b[33];
-    if (!P.ctrl->active) return;
-    const unsigned long long T = P.ctrl->prefix;
+    __shared__ long long s_scan[33];
+    CeCtrl *c = P.ctrl;
+    if (!c->active) return;
+    const unsigned long long T = c->base;
     const long long base = (long long)blockIdx.x * CE_TILE + threadIdx.x * 4;
     int less = 0, ties = 0;
 #pragma unroll
@@ -263,22 +473,16 @@ __global__ void __launch_bounds__(CE_BLOCK) ce_flag_kernel(const CeDev P)
         P.blk_less[blockIdx.x] = tl;
         P.blk_tie[blockIdx.x] = tt;
     }
-}
-
-__global__ void __launch_bounds__(1024) ce_scan_kernel(const CeDev P)
-{
-    __shared__ long long s_scan[33];
-    CeCtrl *c = P.ctrl;
-    if (!c->active) return;
+    if (!ce_last_block(c, gridDim.x)) return;
     const long long tie_take = c->tie_take;
     long long run_tie = 0, run_el = 0;
     for (long long t0 = 0; t0 < P.ntiles; t0 += blockDim.x) {
         const long long t = t0 + threadIdx.x;
-        const long long lt = t < P.ntiles ? P.blk_less[t] : 0, tt = t < P.ntiles ? P.blk_tie[t] : 0;
+        const long long lt = t < P.ntiles ? __ldcg(P.blk_less + t) : 0, tc = t < P.ntiles ? __ldcg(P.blk_tie + t) : 0;
         long long tot_tie, tot_el;
-        const long long ex_tie = run_tie + block_exclusive_scan(tt, 0LL, OpAddLL(), s_scan, tot_tie);
+        const long long ex_tie = run_tie + block_exclusive_scan(tc, 0LL, OpAddLL(), s_scan, tot_tie);
         long long tie_el = tie_take - ex_tie;
-        tie_el = tie_el < 0 ? 0 : (tie_el > tt ? tt : tie_el);
+        tie_el = tie_el < 0 ? 0 : (tie_el > tc ? tc : tie_el);
         const long long ex_el = run_el + block_exclusive_scan(lt + tie_el, 0LL, OpAddLL(), s_scan, tot_el);
         if (t < P.ntiles) {
             P.blk_tie_off[t] = ex_tie;
@@ -295,7 +499,7 @@ __global__ void __launch_bounds__(CE_BLOCK) ce_compact_kernel(const CeDev P)
 {
     __shared__ int s_a[33];
     if (!P.ctrl->active) return;
-    const unsigned long long T = P.ctrl->prefix;
+    const unsigned long long T = P.ctrl->base;
     const long long tie_take = P.ctrl->tie_take;
     const long long base = (long long)blockIdx.x * CE_TILE + threadIdx.x * 4;
     bool less[4], tie[4];
@@ -343,12 +547,73 @@ template <bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK) ce_elite_gen_
     }
 }
 
-// K6: per-dimension partial sums over a chunk of elites; mode 0: sum x, mode 1: sum (x - mu_new)^2 (:283-293)
-__global__ void __launch_bounds__(CE_BLOCK) ce_rowsum_kernel(const CeDev P, int mode)
+// ---- K6: moments ---------------------------------------------------------------------------------------------------
+
+// mu_new = (sum over ranks, in rank order) / 10 or k  (:287).  Any number of threads of one CTA.
+__device__ __forceinline__ void ce_mean_apply(const CeDev &P, Gathered g)
+{
+    for (int d = threadIdx.x; d < P.n; d += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < g.world; ++r) s += g.f64(r, d);
+        P.mu_new[d] = s / (P.divisor_mode == EQS_CE_DIV_REFERENCE_TEN ? 10.0 : (double)P.k);
+    }
+}
+
+// sigma_new = sqrt(sum / (k-1)) (:295-296); mus, sigmas <- new; iter += 1 (:299-302); loop condition (:255).  One CTA.
+// A non-finite sigma is an error only if the loop goes on with it: Normal::new (:259) is what panics, and only on sigma.
+__device__ __forceinline__ void ce_sigma_apply(const CeDev &P, Gathered g)
+{
+    __shared__ double s_max[32];
+    __shared__ int s_bad[32];
+    CeCtrl *c = P.ctrl;
+    double mx = 0.0;
+    int bad = 0;
+    for (int d = threadIdx.x; d < P.n; d += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < g.world; ++r) s += g.f64(r, d);
+        const double sg = sqrt(s / (double)(P.k - 1));
+        P.sigma[d] = sg;
+        P.mu[d] = P.mu_new[d];
+        const double a = fabs(sg);
+        if (a > mx) mx = a;
+        if (!isfinite(sg)) bad = 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_down_sync(0xffffffffu, mx, o);
+        mx = w > mx ? w : mx;
+        bad |= __shfl_down_sync(0xffffffffu, bad, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        s_max[threadIdx.x >> 5] = mx;
+        s_bad[threadIdx.x >> 5] = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)((blockDim.x + 31) >> 5); ++w) {
+            mx = s_max[w] > mx ? s_max[w] : mx;
+            bad |= s_bad[w];
+        }
+        c->sigma_inf = mx;
+        c->iter += 1;
+        const bool go_on = (mx > P.tol) && (c->iter < P.iter_max);
+        if (bad && go_on) c->bad_sigma = 1;
+        c->active = go_on && !c->bad_sigma && !c->p2p_timeout;
+        P.hsend[0] = ~0ULL; // identities of the next pass's (min key, max key, NaN count)
+        P.hsend[1] = 0ULL;
+        P.hsend[2] = 0ULL;
+    }
+}
+
+// per-dimension partial sums over a chunk of elites; mode 0: sum x, mode 1: sum (x - mu_new)^2 (:283-293).  Fused modes:
+// the last CTA adds the chunks in chunk order, gathers the ranks' sums and applies them (mean, or sigma + loop control).
+__global__ void __launch_bounds__(CE_BLOCK) ce_rowsum_kernel(const CeDev P, int mode, int fused)
 {
     __shared__ double s_w[32];
-    if (!P.ctrl->active) return;
-    const long long ne = P.ctrl->n_elite_local;
+    CeCtrl *c = P.ctrl;
+    if (!c->active) return;
+    const long long ne = c->n_elite_local;
     const int d = blockIdx.y;
     const long long j0 = (long long)blockIdx.x * CE_CHUNK, j1 = j0 + CE_CHUNK < ne ? j0 + CE_CHUNK : ne;
     const double m = mode ? P.mu_new[d] : 0.0;
@@ -371,9 +636,21 @@ __global__ void __launch_bounds__(CE_BLOCK) ce_rowsum_kernel(const CeDev P, int 
         for (int w = 0; w < CE_BLOCK / 32; ++w) s += s_w[w];
         P.part[(long long)d * P.nchunks + blockIdx.x] = s;
     }
+    if (fused == CE_PHASED) return;
+    if (!ce_last_block(c, gridDim.x * gridDim.y)) return;
+    for (int dd = threadIdx.x; dd < P.n; dd += blockDim.x) {
+        double s = 0.0;
+        for (int ch = 0; ch < P.nchunks; ++ch) s += __ldcg(P.part + (long long)dd * P.nchunks + ch);
+        P.msend[dd] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    const Gathered g = ce_gather(P, fused, reinterpret_cast<const unsigned long long *>(P.msend), P.n);
+    if (mode == 0) ce_mean_apply(P, g);
+    else ce_sigma_apply(P, g);
 }
 
-// this rank's per-dimension sum, chunks added in chunk order
+// phased mode: this rank's per-dimension sum, chunks added in chunk order
 __global__ void ce_moment_local_kernel(const CeDev P)
 {
     if (!P.ctrl->active) return;
@@ -384,58 +661,16 @@ __global__ void ce_moment_local_kernel(const CeDev P)
     P.msend[d] = s;
 }
 
-// mu_new = (sum over ranks, in rank order) / 10 or k  (:287)
-__global__ void ce_mean_apply_kernel(const CeDev P)
+__global__ void __launch_bounds__(CE_BLOCK) ce_mean_apply_kernel(const CeDev P)
 {
     if (!P.ctrl->active) return;
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= P.n) return;
-    double s = 0.0;
-    for (int r = 0; r < P.world; ++r) s += P.mrecv[(long long)r * P.n + d];
-    P.mu_new[d] = s / (P.divisor_mode == EQS_CE_DIV_REFERENCE_TEN ? 10.0 : (double)P.k);
+    ce_mean_apply(P, Gathered{reinterpret_cast<const unsigned long long *>(P.mrecv), P.n, P.world});
 }
 
-// sigma_new = sqrt(sum / (k-1)) (:295-296); mus, sigmas <- new; iter += 1 (:299-302); loop condition (:255)
-__global__ void __launch_bounds__(1024) ce_sigma_apply_kernel(const CeDev P)
+__global__ void __launch_bounds__(CE_BLOCK) ce_sigma_apply_kernel(const CeDev P)
 {
-    __shared__ double s_max[32];
-    __shared__ int s_bad[32];
-    CeCtrl *c = P.ctrl;
-    if (!c->active) return;
-    double mx = 0.0;
-    int bad = 0;
-    for (int d = threadIdx.x; d < P.n; d += blockDim.x) {
-        double s = 0.0;
-        for (int r = 0; r < P.world; ++r) s += P.mrecv[(long long)r * P.n + d];
-        const double sg = sqrt(s / (double)(P.k - 1));
-        const double m = P.mu_new[d];
-        P.sigma[d] = sg;
-        P.mu[d] = m;
-        const double a = fabs(sg);
-        if (a > mx) mx = a;
-        if (!isfinite(sg) || !isfinite(m)) bad = 1;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double w = __shfl_down_sync(0xffffffffu, mx, o);
-        mx = w > mx ? w : mx;
-        bad |= __shfl_down_sync(0xffffffffu, bad, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        s_max[threadIdx.x >> 5] = mx;
-        s_bad[threadIdx.x >> 5] = bad;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-            mx = s_max[w] > mx ? s_max[w] : mx;
-            bad |= s_bad[w];
-        }
-        c->sigma_inf = mx;
-        c->iter += 1;
-        if (bad) c->bad_sigma = 1;
-        c->active = (mx > P.tol) && (c->iter < P.iter_max) && !c->nan_cost && !c->bad_sigma;
-    }
+    if (!P.ctrl->active) return;
+    ce_sigma_apply(P, Gathered{reinterpret_cast<const unsigned long long *>(P.mrecv), P.n, P.world});
 }
 
 // Small sample sizes (N <= CE_SMALL_MAX on one rank): the reference's default shape is 100 samples x 49 passes
@@ -513,7 +748,7 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(1024, 1) ce_
             P.sigma[d] = sg;
             const double a = fabs(sg);
             if (a > mx) mx = a;
-            if (!isfinite(sg) || !isfinite(mu)) bad = 1;
+            if (!isfinite(sg)) bad = 1;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -534,8 +769,9 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(1024, 1) ce_
             c->sigma_inf = mx;
             c->n_elite_local = k;
             c->iter += 1; // :302
-            if (bad) c->bad_sigma = 1;
-            c->active = (mx > P.tol) && (c->iter < P.iter_max) && !c->bad_sigma;
+            const bool go_on = (mx > P.tol) && (c->iter < P.iter_max);
+            if (bad && go_on) c->bad_sigma = 1; // Normal::new (:259) panics only if another pass samples with it
+            c->active = go_on && !c->bad_sigma;
         }
         __threadfence_block();
         __syncthreads();
@@ -596,6 +832,23 @@ public:
             if (world < 1 || rank < 0 || rank >= world) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "bad virtual rank/world");
         }
         manual_ = p->exchange == EQS_EXCHANGE_MANUAL && world > 1;
+        // how the stages are joined: on one rank, and over the peer mailboxes, the last CTA of each stage applies it;
+        // virtual ranks, and real ranks without peer mapping (NCCL), run the pass phase by phase
+        d_.mailbox = nullptr;
+        d_.peers = nullptr;
+        d_.p2p_timeout_ns = comm_p2p_timeout_ns();
+        fused_ = CE_PHASED;
+        if (!manual_ && !getenv("EQS_CE_PHASED")) {
+            char *mb = nullptr;
+            char *const *peers = nullptr;
+            if (world == 1) {
+                fused_ = CE_FUSED_LOCAL;
+            } else if ((size_t)std::max(n, CE_BINS) <= (size_t)MB_REC_CAP && comm_p2p(ctx_, &mb, &peers)) {
+                d_.mailbox = mb;
+                d_.peers = peers;
+                fused_ = CE_FUSED_P2P;
+            }
+        }
         EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
         int64_t first = 0, nloc = 0;
         eqs_shard_range(p->sample_size, world, rank, &first, &nloc);
@@ -638,7 +891,7 @@ public:
             return o;
         };
         const size_t o_mu = plan(n * 8), o_sig = plan(n * 8), o_mun = plan(n * 8);
-        const size_t o_cost = plan(D.ld * 8);
+        const size_t o_cost = plan(D.ld * 8), o_cand = plan(D.ld * 8);
         const size_t o_xs = strided ? plan((size_t)n * D.ld * 8) : 0;
         const bool own_recv = !(world == 1 && !manual_);
         const size_t o_hs = plan(CE_BINS * 8), o_hr = own_recv ? plan((size_t)world * CE_BINS * 8) : o_hs;
@@ -655,6 +908,7 @@ public:
         D.sigma = (double *)(base + o_sig);
         D.mu_new = (double *)(base + o_mun);
         D.cost = (double *)(base + o_cost);
+        D.cand = (unsigned long long *)(base + o_cand);
         D.xs = strided ? (double *)(base + o_xs) : nullptr;
         D.hsend = (unsigned long long *)(base + o_hs);
         D.hrecv = (unsigned long long *)(base + o_hr);
@@ -673,12 +927,14 @@ public:
         memset(h_ctrl_, 0, sizeof(CeCtrl));
         h_ctrl_->iter = 1; // :253
         h_ctrl_->sigma_inf = smax;
+        bad_sigma0_ = bad_sigma0_ && (smax > p->tol) && (1 < p->iter_max); // an error only if the loop samples with it
         h_ctrl_->active = (smax > p->tol) && (1 < p->iter_max) && !bad_sigma0_;
         cudaStream_t s = ctx_->stream;
         EQS_CUDA(ctx_, cudaMemcpyAsync(D.mu, x0, n * 8, cudaMemcpyHostToDevice, s)); // mus = x0, :246
         EQS_CUDA(ctx_, cudaMemcpyAsync(D.sigma, sig.data(), n * 8, cudaMemcpyHostToDevice, s));
         EQS_CUDA(ctx_, cudaMemcpyAsync(D.ctrl, h_ctrl_, sizeof(CeCtrl), cudaMemcpyHostToDevice, s));
         EQS_CUDA(ctx_, cudaMemsetAsync(D.hsend, 0, CE_BINS * 8, s));
+        EQS_CUDA(ctx_, cudaMemsetAsync(D.hsend, 0xff, 8, s)); // identity of the pass's min key (words 1, 2: max key, NaN count)
         EQS_CUDA(ctx_, cudaStreamSynchronize(s));
         EQS_CUDA(ctx_, cudaEventCreate(&ev0_));
         EQS_CUDA(ctx_, cudaEventCreate(&ev1_));
@@ -713,82 +969,124 @@ public:
         return (int)std::min<long long>(need, (long long)ctx_->sm_count * 8);
     }
 
-    // phase kinds of exchange: 0 none, 1 histogram (u64[BINS]), 2 moments (f64[n])
-    static int phase_exchange(int phase) { return phase <= 5 ? 1 : (phase <= 7 ? 2 : 0); }
+    // phase kinds of exchange: 0 none, 1 histogram-sized (u64[BINS]: key range of the pass, or a level), 2 moments (f64[n])
+    static int phase_exchange(int phase) { return phase <= 6 ? 1 : (phase <= 8 ? 2 : 0); }
 
-    int launch_phase(int phase)
+    int launch_sample(int fused)
     {
         cudaStream_t s = ctx_->stream;
         const CeDev &D = d_;
         const bool replay = D.replay != nullptr;
         const size_t smem = (size_t)2 * D.n * sizeof(double);
-        auto hist = [&](int pass) {
-            ce_hist_kernel<<<grid_for(D.nloc), CE_BLOCK, 0, s>>>(D, pass);
-            launches_++;
-        };
-        auto pick = [&](int pass) {
-            ce_pick_kernel<<<1, 1024, 0, s>>>(D, pass);
-            launches_++;
-        };
-        const int dim_grid = (D.n + 127) / 128;
         int rc = EQS_OK;
-        if (phase == 0) {
-            dispatch_objective(p_.objective_id, [&]<class Obj>() {
-                auto run = [&](auto kernel) {
-                    if (smem > kSmemOptIn) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    if (sample_grid_ == 0) {
-                        int nb = 0;
-                        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, CE_BLOCK, smem);
-                        if (nb < 1) {
-                            rc = ctx_->fail(EQS_ERR_EXTERNAL, "sample kernel does not fit on an SM");
-                            return;
-                        }
-                        const long long need = std::max<long long>(1, (D.nloc + CE_BLOCK - 1) / CE_BLOCK);
-                        sample_grid_ = (int)std::min<long long>(need, (long long)nb * ctx_->sm_count);
-                    }
-                    kernel<<<sample_grid_, CE_BLOCK, smem, s>>>(D);
-                    launches_++;
-                };
-                if (replay) run(ce_sample_kernel<Obj, true>);
-                else run(ce_sample_kernel<Obj, false>);
-            });
-            EQS_TRY(rc);
-            hist(0);
-        } else if (phase <= 5) {
-            pick(phase - 1);
-            hist(phase);
-        } else if (phase == 6) {
-            pick(CE_PASSES - 1);
-            if (D.ntiles > 0) {
-                ce_flag_kernel<<<(unsigned)D.ntiles, CE_BLOCK, 0, s>>>(D);
-                launches_++;
-            }
-            ce_scan_kernel<<<1, 1024, 0, s>>>(D);
-            launches_++;
-            if (D.ntiles > 0) {
-                ce_compact_kernel<<<(unsigned)D.ntiles, CE_BLOCK, 0, s>>>(D);
-                launches_++;
-            }
-            auto gen = [&](auto kernel) {
+        dispatch_objective(p_.objective_id, [&]<class Obj>() {
+            auto run = [&](auto kernel) {
                 if (smem > kSmemOptIn) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                kernel<<<grid_for(D.kcap), CE_BLOCK, smem, s>>>(D);
+                if (sample_grid_ == 0) {
+                    int nb = 0;
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, CE_BLOCK, smem);
+                    if (nb < 1) {
+                        rc = ctx_->fail(EQS_ERR_EXTERNAL, "sample kernel does not fit on an SM");
+                        return;
+                    }
+                    const long long need = std::max<long long>(1, (D.nloc + CE_BLOCK - 1) / CE_BLOCK);
+                    sample_grid_ = (int)std::min<long long>(need, (long long)nb * ctx_->sm_count);
+                }
+                kernel<<<sample_grid_, CE_BLOCK, smem, s>>>(D, fused);
                 launches_++;
             };
-            if (replay) gen(ce_elite_gen_kernel<true>);
-            else gen(ce_elite_gen_kernel<false>);
-            ce_rowsum_kernel<<<dim3(D.nchunks, D.n), CE_BLOCK, 0, s>>>(D, 0);
-            ce_moment_local_kernel<<<dim_grid, 128, 0, s>>>(D);
-            launches_ += 2;
+            if (replay) run(ce_sample_kernel<Obj, true>);
+            else run(ce_sample_kernel<Obj, false>);
+        });
+        return rc;
+    }
+
+    void launch_level(int compact, int fused)
+    {
+        ce_level_kernel<<<grid_for(d_.nloc), CE_BLOCK, 0, ctx_->stream>>>(d_, compact, fused);
+        launches_++;
+    }
+
+    // the elite list in sample order and the regenerated elites
+    void launch_elites()
+    {
+        cudaStream_t s = ctx_->stream;
+        const CeDev &D = d_;
+        const size_t smem = (size_t)2 * D.n * sizeof(double);
+        ce_count_kernel<<<(unsigned)std::max<long long>(D.ntiles, 1), CE_BLOCK, 0, s>>>(D);
+        launches_++;
+        if (D.ntiles > 0) {
+            ce_compact_kernel<<<(unsigned)D.ntiles, CE_BLOCK, 0, s>>>(D);
+            launches_++;
+        }
+        auto gen = [&](auto kernel) {
+            if (smem > kSmemOptIn) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kernel<<<grid_for(D.kcap), CE_BLOCK, smem, s>>>(D);
+            launches_++;
+        };
+        if (D.replay != nullptr) gen(ce_elite_gen_kernel<true>);
+        else gen(ce_elite_gen_kernel<false>);
+    }
+
+    void launch_rowsum(int mode, int fused)
+    {
+        ce_rowsum_kernel<<<dim3(d_.nchunks, d_.n), CE_BLOCK, 0, ctx_->stream>>>(d_, mode, fused);
+        launches_++;
+    }
+
+    // one pass, fused: 8 launches, every exchange inside the kernels
+    int launch_pass_fused()
+    {
+        EQS_TRY(launch_sample(fused_));
+        launch_level(0, fused_);
+        launch_level(1, fused_);
+        launch_elites();
+        launch_rowsum(0, fused_);
+        launch_rowsum(1, fused_);
+        EQS_CUDA(ctx_, cudaGetLastError());
+        return EQS_OK;
+    }
+
+    // one phase of the phased pass (the exchange named by phase_exchange follows it)
+    int launch_phase(int phase)
+    {
+        cudaStream_t s = ctx_->stream;
+        const CeDev &D = d_;
+        const int dim_grid = (D.n + 127) / 128;
+        auto pick = [&] {
+            ce_pick_kernel<<<1, CE_BLOCK, 0, s>>>(D);
+            launches_++;
+        };
+        if (phase == 0) {
+            EQS_TRY(launch_sample(CE_PHASED));
+        } else if (phase == 1) {
+            ce_begin_kernel<<<1, 32, 0, s>>>(D);
+            launches_++;
+            launch_level(0, CE_PHASED);
+        } else if (phase == 2) {
+            pick();
+            launch_level(1, CE_PHASED);
+        } else if (phase <= 6) {
+            pick();
+            ce_cand_level_kernel<<<1, CE_BLOCK, 0, s>>>(D);
+            launches_++;
         } else if (phase == 7) {
-            ce_mean_apply_kernel<<<dim_grid, 128, 0, s>>>(D);
-            ce_rowsum_kernel<<<dim3(D.nchunks, D.n), CE_BLOCK, 0, s>>>(D, 1);
+            pick();
+            launch_elites();
+            launch_rowsum(0, CE_PHASED);
             ce_moment_local_kernel<<<dim_grid, 128, 0, s>>>(D);
-            launches_ += 3;
+            launches_++;
         } else if (phase == 8) {
-            ce_sigma_apply_kernel<<<1, 1024, 0, s>>>(D);
+            ce_mean_apply_kernel<<<1, CE_BLOCK, 0, s>>>(D);
+            launches_++;
+            launch_rowsum(1, CE_PHASED);
+            ce_moment_local_kernel<<<dim_grid, 128, 0, s>>>(D);
+            launches_++;
+        } else if (phase == 9) {
+            ce_sigma_apply_kernel<<<1, CE_BLOCK, 0, s>>>(D);
             launches_++;
         } else {
-            return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "phase must be 0..8");
+            return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "phase must be 0..%d", CE_PHASES - 1);
         }
         EQS_CUDA(ctx_, cudaGetLastError());
         return EQS_OK;
@@ -820,7 +1118,7 @@ public:
     {
         EQS_CUDA(ctx_, cudaSetDevice(ctx_->device));
         if (manual_) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "exchange = MANUAL: drive the phases with eqs_ce_phase");
-        if (bad_sigma0_ && p_.iter_max > 1) return ctx_->fail(EQS_ERR_NAN, "non-finite standard deviation (the reference panics in Normal::new, cross_entropy.rs:259)");
+        if (bad_sigma0_) return ctx_->fail(EQS_ERR_NAN, "non-finite standard deviation (the reference panics in Normal::new, cross_entropy.rs:259)");
         EQS_TRY(prepare_replay(replay, iters));
         const int64_t l0 = launches_;
         EQS_CUDA(ctx_, cudaEventRecord(ev0_, ctx_->stream));
@@ -850,11 +1148,16 @@ public:
         } else {
             small_path_ = false;
         }
-        for (int64_t it = 0; it < (small ? 0 : iters); ++it)
+        for (int64_t it = 0; it < (small ? 0 : iters); ++it) {
+            if (fused_ != CE_PHASED) {
+                EQS_TRY(launch_pass_fused());
+                continue;
+            }
             for (int ph = 0; ph < CE_PHASES; ++ph) {
                 EQS_TRY(launch_phase(ph));
                 EQS_TRY(exchange(phase_exchange(ph)));
             }
+        }
         EQS_CUDA(ctx_, cudaEventRecord(ev1_, ctx_->stream));
         last_launches_ = launches_ - l0;
         return EQS_OK;
@@ -862,8 +1165,9 @@ public:
 
     int check_flags()
     {
+        if (h_ctrl_->p2p_timeout) return ctx_->fail(EQS_ERR_EXTERNAL, "a peer rank did not reach an exchange of the CrossEntropy pass (peer-memory mailbox timed out)");
         if (h_ctrl_->nan_cost) return ctx_->fail(EQS_ERR_NAN, "a sample cost is NaN (the reference panics in sort_unstable_by, cross_entropy.rs:276)");
-        if (h_ctrl_->bad_sigma) return ctx_->fail(EQS_ERR_NAN, "a non-finite mean or standard deviation was produced (the reference panics in Normal::new, cross_entropy.rs:259)");
+        if (h_ctrl_->bad_sigma) return ctx_->fail(EQS_ERR_NAN, "a non-finite standard deviation was produced and the loop goes on (the reference panics in Normal::new, cross_entropy.rs:259)");
         return EQS_OK;
     }
 
@@ -929,6 +1233,7 @@ public:
     int sample_grid_ = 0;
     int64_t launches_ = 0, last_launches_ = 0;
     bool manual_ = false, bad_sigma0_ = false;
+    int fused_ = CE_PHASED;
     bool small_path_ = false; // the last step() ran ce_small_kernel (elite list is in cost order)
 };
 

@@ -151,6 +151,16 @@ bool comm_p2p(Ctx *ctx, char **mailbox, char *const **d_peers)
     return true;
 }
 
+long long comm_p2p_timeout_ns()
+{
+    double seconds = 20.0;
+    if (const char *e = getenv("EQS_P2P_TIMEOUT_S")) {
+        const double v = atof(e);
+        if (v > 0.0) seconds = v;
+    }
+    return (long long)(seconds * 1e9);
+}
+
 int comm_unique_id(void *out128, std::string &err)
 {
     NcclApi &a = nccl();

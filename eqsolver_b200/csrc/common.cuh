@@ -192,6 +192,10 @@ constexpr long long MB_REC_CAP = REC_X + 12800 + 2; // doubles per record slot (
 constexpr size_t MB_BYTES = MB_REC + 2ull * MB_MAX_WORLD * MB_REC_CAP * sizeof(double);
 // returns false when the context has no peer mailboxes (single rank, IPC unavailable, or EQS_P2P=0)
 bool comm_p2p(Ctx *ctx, char **mailbox, char *const **d_peers);
+// How long a kernel waits in a mailbox for a peer before it gives up (the solve then fails with ExternalError instead of
+// hanging the GPU): EQS_P2P_TIMEOUT_S seconds, default 20.  All ranks must therefore enqueue the same pass within that
+// time of each other ("co-scheduling").
+long long comm_p2p_timeout_ns();
 
 // Dynamic shared memory beyond this many bytes is requested with cudaFuncAttributeMaxDynamicSharedMemorySize.  The
 // limit without the opt-in is 48 KB for STATIC + dynamic together, so the threshold leaves room for the kernels' static
@@ -199,6 +203,71 @@ bool comm_p2p(Ctx *ctx, char **mailbox, char *const **d_peers);
 constexpr size_t kSmemOptIn = 32 * 1024;
 
 // ---- device helpers ------------------------------------------------------------------------------------
+// system-scope flag accesses of the mailbox protocol
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *flag == expect; false when timeout_ns of wall-clock time passed first (the clock is read every 32 polls)
+__device__ __forceinline__ bool mailbox_wait(const unsigned long long *flag, unsigned long long expect, long long timeout_ns)
+{
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0;; ++spins) {
+        if (ld_acquire_sys(flag) == expect) return true;
+        if ((spins & 31u) == 31u) {
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if ((long long)(now - t0) > timeout_ns) return false;
+        }
+    }
+}
+
+// ALLGATHER OVER THE MAILBOXES, executed by ONE CTA (all of its threads call): `words` 8-byte words at `send` (memory
+// this CTA may read: its own shared memory, or global memory that is complete for it) go into slot (exchange number & 1,
+// my rank) of EVERY rank's mailbox over NVLink; the exchange number is release-stored into the matching flags; then the
+// CTA acquire-waits until its own mailbox holds that number from every peer.  Returns the slot array of this exchange in
+// the rank's own mailbox: rank r's words start at result + r * MB_REC_CAP (read them with __ldcv: written by peers).
+// Every rank runs the same sequence of exchanges on a context, two slots deep: a rank can be at most one exchange ahead
+// of its slowest peer (it needs that peer's flag for exchange s+1, which the peer only sets after it has consumed s).
+// No deadlock: a CTA only ever waits for kernels running on OTHER GPUs.  *timed_out is set when a peer never arrived.
+__device__ __forceinline__ const unsigned long long *mailbox_allgather(char *mailbox, char *const *peers, int rank, int world,
+                                                                       const unsigned long long *send, long long words,
+                                                                       long long timeout_ns, int *timed_out)
+{
+    const int tid = threadIdx.x;
+    unsigned long long *seq_p = reinterpret_cast<unsigned long long *>(mailbox + MB_SEQ);
+    const unsigned long long s = *seq_p + 1;
+    const int slot = (int)(s & 1ull);
+    __syncthreads(); // `send` complete, everyone has read seq
+    for (int r = 0; r < world; ++r) {
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(peers[r] + MB_REC) + ((size_t)slot * world + rank) * MB_REC_CAP;
+        for (long long i = tid; i < words; i += blockDim.x) dst[i] = send[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) {
+        unsigned long long *theirs = reinterpret_cast<unsigned long long *>(peers[tid] + MB_FLAG) + slot * world + rank;
+        st_release_sys(theirs, s);
+        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(mailbox + MB_FLAG) + slot * world + tid;
+        if (!mailbox_wait(mine, s, timeout_ns)) *timed_out = 1;
+    }
+    __syncthreads();
+    if (tid == 0) *seq_p = s;
+    return reinterpret_cast<const unsigned long long *>(mailbox + MB_REC) + (size_t)slot * world * MB_REC_CAP;
+}
+
 __device__ __forceinline__ double sanitize_cost(double c) { return (c != c) ? __longlong_as_double(0x7ff0000000000000LL) : c; }
 
 __device__ __forceinline__ double shfl_down_f64(double v, int delta)

@@ -59,16 +59,24 @@ struct D4 {
     double e[4];
 };
 
+// Both are volatile with a "memory" clobber: to the compiler an asm statement without them is a pure function of its
+// register operands, which it may hoist over the stores that produced the data or merge with an earlier identical load
+// (the commit-then-speculate sequence of pso_seqw_kernel, the random-access objectives that read x back with plain
+// loads).  Program order already is "all loads of a batch, math, stores", so nothing is lost by pinning it.
 __device__ __forceinline__ D4 ld256(const double *p)
 {
     D4 r;
-    asm("ld.global" EQS_PSO_LDHINT ".v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.e[0]), "=d"(r.e[1]), "=d"(r.e[2]), "=d"(r.e[3]) : "l"(p));
+    asm volatile("ld.global" EQS_PSO_LDHINT ".v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.e[0]), "=d"(r.e[1]), "=d"(r.e[2]), "=d"(r.e[3])
+                 : "l"(p)
+                 : "memory");
     return r;
 }
 
 __device__ __forceinline__ void st256(double *p, const D4 &v)
 {
-    asm volatile("st.global" EQS_PSO_STHINT ".v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.e[0]), "d"(v.e[1]), "d"(v.e[2]), "d"(v.e[3]));
+    asm volatile("st.global" EQS_PSO_STHINT ".v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.e[0]), "d"(v.e[1]), "d"(v.e[2]), "d"(v.e[3])
+                 : "memory");
 }
 
 __device__ __forceinline__ long long goff(const PsoDev &P, int q, long long li) { return ((long long)q * P.ld + li) * 4; }
@@ -287,51 +295,17 @@ __device__ __forceinline__ void pso_apply_step(const PsoDev &P, const double *re
 }
 
 // ---- the exchange fused into the step kernel (one kernel per pass at any world size) ---------------------------
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// Called by the LAST CTA of the step kernel once P.send holds this rank's record.  Stores the record into every
-// rank's mailbox over NVLink, publishes the exchange number, waits for every peer's number, then applies the same
-// gbest selection as pso_step_apply_kernel.  No deadlock: a CTA only waits for kernels running on OTHER GPUs.
+// Called by the LAST CTA of the step kernel once P.send holds this rank's record: all-gather of the records over the
+// peer mailboxes (common.cuh: mailbox_allgather), then the same gbest selection as pso_step_apply_kernel.
 __device__ __forceinline__ void pso_p2p_exchange_apply(const PsoDev &P)
 {
-    const int tid = threadIdx.x;
     const long long R = record_doubles(P.n);
-    unsigned long long *seq_p = reinterpret_cast<unsigned long long *>(P.mailbox + MB_SEQ);
-    const unsigned long long s = *seq_p + 1; // every rank runs the same sequence of exchanges
-    const int slot = (int)(s & 1ull);
-    __syncthreads(); // P.send complete, everyone has read seq
-    for (int r = 0; r < P.world; ++r) {
-        double *dst = reinterpret_cast<double *>(P.peers[r] + MB_REC) + ((size_t)slot * P.world + P.rank) * MB_REC_CAP;
-        for (long long i = tid; i < R; i += blockDim.x) dst[i] = P.send[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < P.world) {
-        unsigned long long *theirs = reinterpret_cast<unsigned long long *>(P.peers[tid] + MB_FLAG) + slot * P.world + P.rank;
-        st_release_sys(theirs, s);
-        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(P.mailbox + MB_FLAG) + slot * P.world + tid;
-        const long long t0 = clock64();
-        while (ld_acquire_sys(mine) != s) {
-            if (clock64() - t0 > 6000000000LL) { // ~3 s: a peer died; fail instead of hanging the GPU
-                P.ctrl->p2p_timeout = 1;
-                break;
-            }
-        }
-    }
-    __syncthreads();
-    const double *src = reinterpret_cast<const double *>(P.mailbox + MB_REC) + (size_t)slot * P.world * MB_REC_CAP;
+    const unsigned long long *slots = mailbox_allgather(P.mailbox, P.peers, P.rank, P.world,
+                                                        reinterpret_cast<const unsigned long long *>(P.send), R,
+                                                        P.p2p_timeout_ns, &P.ctrl->p2p_timeout);
+    const double *src = reinterpret_cast<const double *>(slots);
     for (int r = 0; r < P.world; ++r)
-        for (long long i = tid; i < R; i += blockDim.x) P.recv[r * R + i] = __ldcv(src + r * MB_REC_CAP + i);
-    if (tid == 0) *seq_p = s;
+        for (long long i = threadIdx.x; i < R; i += blockDim.x) P.recv[r * R + i] = __ldcv(src + r * MB_REC_CAP + i);
     __threadfence_block();
     __syncthreads();
     pso_apply_step(P, P.recv, P.world);
@@ -585,7 +559,9 @@ __global__ void __launch_bounds__(PSO_BLOCK) pso_spec_kernel(const PsoDev P, lon
         if (gi < start_g) continue;
         const double cost = pso_move<Obj, REPLAY>(P, t, li, sG, P.x, P.v, P.pb, P.x2, P.v2, true);
         P.cost[li] = cost;
-        if (cost < Gc && gi < first.i) first.i = gi; // :417,:420 (cost < Gc implies cost < pbest cost)
+        // :417,:420 -- the gbest test is nested in the pbest test; the two differ when the pbest cost is NaN (then the
+        // particle can never update either), so both are spelled out
+        if (cost < P.pbc[li] && cost < Gc && gi < first.i) first.i = gi;
     }
     MinLoc win;
     if (grid_minloc_last_block(P, first, s_red, win)) {
@@ -720,7 +696,7 @@ __global__ void __launch_bounds__(PSO_BLOCK) pso_seqw_kernel(const PsoDev P)
         for (long long li = first_at(start); li < wend; li += stride) {
             const double cost = pso_move<Obj, REPLAY>(P, t, li, sG, xa, va, P.pb, xb, vb, true);
             P.cost[li] = cost;
-            if (cost < Gc && li < first.i) first.i = li; // :417,:420 (cost < Gc implies cost < pbest cost)
+            if (cost < P.pbc[li] && cost < Gc && li < first.i) first.i = li; // :417,:420 (nested; see pso_spec_kernel)
         }
     }
     MinLoc win;
@@ -816,7 +792,7 @@ __global__ void __launch_bounds__(PSO_SMALL_BLOCK) pso_small_kernel(const PsoDev
                     if (gi < start) continue;
                     const double cost = pso_move<Obj, false>(P, t, li, sG, P.x, P.v, P.pb, P.x2, P.v2, true);
                     P.cost[li] = cost;
-                    if (cost < Gc && gi < first.i) first.i = gi; // :417,:420
+                    if (cost < P.pbc[li] && cost < Gc && gi < first.i) first.i = gi; // :417,:420 (nested)
                 }
                 const MinLoc b = block_minloc(first, s_red);
                 if (tid == 0) s_win = b;
@@ -1014,6 +990,7 @@ int PsoSolver::create(const eqs_pso_params *p)
         if (comm_p2p(ctx_, &mb, &peers)) {
             D.mailbox = mb;
             D.peers = peers;
+            D.p2p_timeout_ns = comm_p2p_timeout_ns();
             fused_exchange_ = true;
         }
     }

@@ -50,6 +50,7 @@ struct PsoDev {
     double *send, *recv;            // exchange records: [R], [world][R]
     char *mailbox;                  // peer-memory exchange (common.cuh): this rank's mailbox, or nullptr
     char *const *peers;             // device table of every rank's mailbox as mapped on this GPU
+    long long p2p_timeout_ns;       // how long the fused exchange waits for a peer (comm_p2p_timeout_ns)
     const double *lower, *upper;    // [n]
     const double *replay;           // device copy of the caller's draw stream, or nullptr
     long long ld, nloc, first, ntotal;

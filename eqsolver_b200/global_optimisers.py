@@ -559,8 +559,8 @@ class CeRun:
         self.ctx.check(_ffi.lib().eqs_ce_read_costs(self._h, _p(c)))
         return c
 
-    # split-phase protocol (virtual ranks): phases 0..8 of one pass
-    N_PHASES = 9
+    # split-phase protocol (virtual ranks): phases 0..9 of one pass
+    N_PHASES = 10
 
     def phase(self, phase: int, replay_normals=None):
         r = None if replay_normals is None else _arr(replay_normals, self.cfg.sample_size * self.n)

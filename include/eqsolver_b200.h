@@ -33,7 +33,7 @@ extern "C" {
 typedef enum {
     EQS_OK = 0,
     EQS_ERR_MAX_ITER = 1,        /* MaxIterReached(usize)   -- never produced by this path */
-    EQS_ERR_NAN = 2,             /* NotANumber: where the reference panics on NaN cost / non-finite sigma */
+    EQS_ERR_NAN = 2,             /* NotANumber: where the reference panics on a NaN cost / on sampling with a non-finite sigma */
     EQS_ERR_INCORRECT_INPUT = 3, /* IncorrectInput{details} */
     EQS_ERR_BAD_JACOBIAN = 4,    /* BadJacobian             -- never produced by this path */
     EQS_ERR_TYPE_CONVERSION = 5, /* TypeConversionError     -- MISER only (miser.rs:413-419) */
@@ -213,11 +213,12 @@ int eqs_ce_read_state(eqs_ce *h, double *mu, double *sigma, int64_t *iters_run, 
 int eqs_ce_read_elites(eqs_ce *h, int64_t *idx, int64_t *count);
 int eqs_ce_read_costs(eqs_ce *h, double *costs);
 int eqs_ce_local_range(eqs_ce *h, int64_t *first, int64_t *local);
-/* split-phase protocol (EQS_EXCHANGE_MANUAL; also how the NCCL path is sequenced).  One pass of the while
- * body is phases 0..8; after phase p the caller gathers eqs_ce_exchange_words(h, p) 8-byte words from every
- * rank (get) and hands all ranks' words back in rank order (set): phases 0-5 a radix-select histogram
- * (u64[2048]), phases 6-7 the elite moment sums (f64[n]), phase 8 nothing.  replay_normals (phase 0 only):
- * NULL or z [N][n] for this pass. */
+/* split-phase protocol (EQS_EXCHANGE_MANUAL; also how the pass is sequenced over NCCL when the ranks cannot map each
+ * other's memory -- with peer mapping, and on one rank, the exchanges happen inside the kernels).  One pass of the while
+ * body is phases 0..9; after phase p the caller gathers eqs_ce_exchange_words(h, p) 8-byte words from every rank (get)
+ * and hands all ranks' words back in rank order (set): phase 0 the key range and NaN count of the pass (u64[2048], words
+ * 0..2 used), phases 1-6 the histogram of one level of the radix select (u64[2048]), phases 7-8 the elite moment sums
+ * (f64[n]), phase 9 nothing.  replay_normals (phase 0 only): NULL or z [N][n] for this pass. */
 int eqs_ce_phase(eqs_ce *h, int32_t phase, const double *replay_normals);
 int64_t eqs_ce_exchange_words(eqs_ce *h, int32_t phase);
 int eqs_ce_get_exchange(eqs_ce *h, int32_t phase, void *words);

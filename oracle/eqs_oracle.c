@@ -655,8 +655,8 @@ int orc_ce_step(orc_ce *s)
     const orc_ce_params *p = &s->p;
     int n = p->n;
     int64_t N = p->local_count, k = p->elite_count;
-    if (!sigma_finite(s)) return -ORC_ERR_NAN; /* Normal::new(..).unwrap() panics, :259 */
-    if (!orc_ce_active(s)) return 1;
+    if (!orc_ce_active(s)) return 1;            /* the loop condition comes first (:255): a non-finite sigma only ... */
+    if (!sigma_finite(s)) return -ORC_ERR_NAN;  /* ... panics when another pass samples with it: Normal::new(..).unwrap(), :259 */
     orc_ce_sample_local(s);
     for (int64_t i = 0; i < N; ++i) {
         if (s->costs[i] != s->costs[i]) return -ORC_ERR_NAN; /* partial_cmp().unwrap() panics, :276 */

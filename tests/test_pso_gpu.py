@@ -730,3 +730,37 @@ def test_dynamic_shared_memory_just_below_48k(ctx):
     np.testing.assert_allclose(ce.solve(np.zeros(19)), oc.solve(), rtol=1e-10, atol=1e-12)
     r = E.MonteCarlo.new(E.Objective.SPHERE).with_sample_count(5000).with_context(ctx).integrate_with_seed([0.0] * 3050, [1.0] * 3050, 1)
     assert abs(r.mean - 3050 / 3.0) < 5.0       # 2 * 3050 * 8 = 48 800 B of box data in shared memory
+
+
+@pytest.mark.parametrize("N,host_driven", [(500, False), (3000, False), (3000, True)])
+def test_sequential_mode_nan_pbest_cost_never_updates(ctx, N, host_driven):
+    """particle_swarm.rs:417-425 nests the gbest test inside `cost < best_cost`: a particle whose FIRST cost is NaN keeps a
+    NaN pbest cost, so it can never improve its pbest or move gbest, however good its later positions are.  SERIES(x) =
+    sum (-1)^i x^i is NaN for x > 2.03 (inf - inf), so on [-1, 3]^2 four particles in ten start like that.  All three
+    sequential paths (single-CTA, windowed device-driven, host-driven rounds), bit for bit against the oracle."""
+    n, iters = 2, 6
+    lower, upper, x0 = [-1.0] * n, [3.0] * n, np.full(n, 0.25)
+    if host_driven:
+        os.environ["EQS_PSO_SEQ_HOST"] = "1"
+    try:
+        run = (E.ParticleSwarm.new(E.Objective.SERIES, lower, upper).with_particle_count(N).with_tol(0.0).with_seed(77)
+               .with_mode(E.PsoMode.SEQUENTIAL_EXACT).with_context(ctx)).start(x0)
+    finally:
+        os.environ.pop("EQS_PSO_SEQ_HOST", None)
+    o = O.Pso(O.SERIES, lower, upper, particle_count=N, tol=0.0, mode=O.SEQUENTIAL, seed=77)
+    o.init(x0)
+    pbc0 = run.pbest_costs()
+    assert 0.2 * N < np.isnan(pbc0).sum() < 0.7 * N          # the case under test is there
+    for t in range(iters):
+        run.step(1)
+        o.step()
+        g, c, it, _, imp = run.gbest()
+        assert_bit_equal(g, o.gbest(), f"gbest pass {t}")
+        assert c == o.gbest_cost()
+        for a, b, nm in zip(run.state(), o.state(), ("x", "v", "pbest", "pbest cost")):
+            if nm == "pbest cost":   # a NaN's sign and payload are not part of the contract (x86: inf - inf = -NaN)
+                assert np.array_equal(np.isnan(a), np.isnan(b)), f"{nm} pass {t}"
+                a, b = np.where(np.isnan(a), 0.0, a), np.where(np.isnan(b), 0.0, b)
+            assert_bit_equal(a, b, f"{nm} pass {t}")
+    assert np.array_equal(np.isnan(run.pbest_costs()), np.isnan(pbc0))   # NaN pbest costs stayed NaN, nobody else got one
+    run.close()
