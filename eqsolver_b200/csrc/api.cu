@@ -6,6 +6,7 @@
 #include <exception>
 #include <new>
 
+#define EQS_DEVMATH_TABLES // draws_kernel samples normals: log_unit_tab's shared-memory tables (devmath.cuh)
 #include "common.cuh"
 #include "objectives.cuh"
 #include "philox.cuh"
@@ -71,6 +72,7 @@ __global__ void cos_kernel(const double *x, long long count, double *out)
 __global__ void draws_kernel(int kind, PhiloxKey key, uint32_t t, long long first, long long count, int n, double *a, double *b)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (kind == 2) devmath_tables_load(); // every thread of the block: it ends with a barrier
     if (i >= count) return;
     const long long gi = first + i;
     if (kind == 2) {

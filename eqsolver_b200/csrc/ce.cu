@@ -20,6 +20,7 @@
 #include <new>
 
 #define EQS_COS_TABLE 1 // issue-bound sample kernels: constant-operand cos (devmath.cuh)
+#define EQS_DEVMATH_TABLES // Box-Muller's logarithm reads its tables from shared memory (devmath.cuh: log_unit_tab)
 #include "common.cuh"
 #include "objectives.cuh"
 #include "philox.cuh"
@@ -38,7 +39,9 @@ constexpr int CE_BLOCK = 256;
 #endif
 constexpr int CE_BINS = 2048;  // 11 bits per level
 constexpr int CE_LEVELS = 6;   // ceil(64 / 11): what a 64-bit key range can need
-constexpr int CE_TILE = 1024;  // samples per block in count / compact (256 threads x 4, blocked)
+constexpr int CE_SEL_BLOCK = 512; // threads of the select kernels: few, fat CTAs keep the histogram flush (global atomics) short
+constexpr int CE_TILE = 2048;  // samples per block in count / compact (256 threads x 8, blocked)
+constexpr int CE_GEN_BLOCK = 64; // elite regeneration: k threads in all, small CTAs spread them over the SMs
 constexpr int CE_CHUNK = 4096; // elites per block in the row sums
 constexpr int CE_PHASES = 10;
 constexpr int CE_SMALL_MAX = 1024; // samples the single-CTA whole-solve kernel takes (one per thread)
@@ -234,17 +237,19 @@ __device__ __forceinline__ void ce_select_begin(const CeDev &P, Gathered g)
     __syncthreads();
 }
 
-// pick the bin that holds the k-th key from all ranks' histograms of the current level and descend into it; after the
-// level with shift 0 the bucket is ONE key: split its ties over the ranks (lowest sample indices first).  One CTA of
-// CE_BLOCK threads, 8 bins per thread.
+// pick the bin that holds the k-th key from all ranks' histograms of the current level and descend into it.  The select
+// ends (a) after the level with shift 0 -- the bucket is ONE key: split its ties over the ranks, lowest sample indices
+// first -- or (b) as soon as the k-th key is the LAST key of the chosen bin: then every key up to the bin's upper end is
+// elite and nothing has to be resolved inside it (the usual way out: two levels leave a handful of keys per bin).
+// One CTA of CE_SEL_BLOCK threads, CE_BINS / CE_SEL_BLOCK bins per thread.
 __device__ __forceinline__ void ce_pick(const CeDev &P, Gathered g)
 {
     __shared__ long long s_scan[33];
     __shared__ int s_bin;
-    __shared__ long long s_excl;
+    __shared__ long long s_excl, s_cnt;
     CeCtrl *c = P.ctrl;
     const int tid = threadIdx.x;
-    constexpr int PER = CE_BINS / CE_BLOCK;
+    constexpr int PER = CE_BINS / CE_SEL_BLOCK;
     long long h[PER], tot = 0;
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
@@ -257,6 +262,7 @@ __device__ __forceinline__ void ce_pick(const CeDev &P, Gathered g)
     if (tid == 0) {
         s_bin = 0;
         s_excl = 0;
+        s_cnt = 0;
     }
     long long total;
     long long excl = block_exclusive_scan(tot, 0LL, OpAddLL(), s_scan, total);
@@ -266,6 +272,7 @@ __device__ __forceinline__ void ce_pick(const CeDev &P, Gathered g)
             if (excl < k_rem && k_rem <= excl + h[j]) {
                 s_bin = tid * PER + j;
                 s_excl = excl;
+                s_cnt = h[j];
             }
             excl += h[j];
         }
@@ -274,10 +281,9 @@ __device__ __forceinline__ void ce_pick(const CeDev &P, Gathered g)
     if (tid == 0) {
         const int shift = c->shift;
         const unsigned long long base = c->base + ((unsigned long long)s_bin << shift);
-        const unsigned long long top = base + ((1ULL << shift) - 1ULL);
+        unsigned long long top = base + ((1ULL << shift) - 1ULL);
+        top = top < c->bucket_hi ? top : c->bucket_hi;
         const long long rem = k_rem - s_excl;
-        c->base = base;
-        c->bucket_hi = top < c->bucket_hi ? top : c->bucket_hi;
         c->k_rem = rem;
         if (shift == 0) { // rem = how many of the samples with key == k-th key are elite, lowest index first
             long long before = 0;
@@ -285,9 +291,18 @@ __device__ __forceinline__ void ce_pick(const CeDev &P, Gathered g)
             const long long mine = (long long)g(g.world == 1 ? 0 : P.rank, s_bin);
             long long take = rem - before;
             take = take < 0 ? 0 : (take > mine ? mine : take);
+            c->base = base;
+            c->bucket_hi = base;
             c->tie_take = take;
             c->sel_done = 1;
+        } else if (rem == s_cnt) { // the whole bin is elite: threshold = its upper end, every key equal to that is taken
+            c->base = top;
+            c->bucket_hi = top;
+            c->tie_take = 0x7fffffffffffffffLL;
+            c->sel_done = 1;
         } else {
+            c->base = base;
+            c->bucket_hi = top;
             c->shift = shift > 11 ? shift - 11 : 0;
         }
         if (c->p2p_timeout) c->active = 0;
@@ -327,6 +342,7 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK, EQ
     if (!c->active) return;
     const uint32_t t = (uint32_t)(c->iter - 1);
     double *smu = s_ms, *ssig = s_ms + P.n;
+    if constexpr (!REPLAY) devmath_tables_load();
     load_mu_sigma(P, smu, ssig);
     unsigned long long klo = ~0ULL, khi = 0ULL;
     unsigned int nan = 0u;
@@ -382,7 +398,8 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK, EQ
 // K5, levels A and B: histogram of the current level over ALL keys of this rank; level B (`compact`) also copies the keys
 // of the current bucket -- the one level A chose -- into the candidate list, which every later level works on.  Fused
 // modes: the last CTA picks the bin and, at level B, runs the remaining levels over the candidates by itself.
-__global__ void __launch_bounds__(CE_BLOCK) ce_level_kernel(const CeDev P, int compact, int fused)
+// Grid: two CTAs of 512 threads per SM at most -- every CTA ends with up to 2048 global atomics, so few fat CTAs.
+__global__ void __launch_bounds__(CE_SEL_BLOCK) ce_level_kernel(const CeDev P, int compact, int fused)
 {
     __shared__ unsigned int sh[CE_BINS];
     CeCtrl *c = P.ctrl;
@@ -392,22 +409,30 @@ __global__ void __launch_bounds__(CE_BLOCK) ce_level_kernel(const CeDev P, int c
     const unsigned long long base = c->base, bhi = c->bucket_hi;
     const int shift = c->shift;
     const int lane = threadIdx.x & 31;
-    for (long long b0 = (long long)blockIdx.x * blockDim.x; b0 < P.nloc; b0 += (long long)gridDim.x * blockDim.x) {
-        const long long li = b0 + threadIdx.x;
-        unsigned long long key = 0ULL;
-        bool in = false;
-        if (li < P.nloc) {
-            key = cost_key(P.cost[li]);
-            in = key >= base && key <= bhi;
+    const long long npair = (P.nloc + 1) >> 1; // P.cost is 256-byte aligned and padded to ld >= nloc rounded up to 16
+    for (long long b0 = (long long)blockIdx.x * blockDim.x; b0 < npair; b0 += (long long)gridDim.x * blockDim.x) {
+        const long long pi = b0 + threadIdx.x;
+        unsigned long long key[2] = {0ULL, 0ULL};
+        bool in[2] = {false, false};
+        if (pi < npair) {
+            const double2 cv = reinterpret_cast<const double2 *>(P.cost)[pi];
+            key[0] = cost_key(cv.x);
+            key[1] = cost_key(cv.y);
+            in[0] = key[0] >= base && key[0] <= bhi;
+            in[1] = 2 * pi + 1 < P.nloc && key[1] >= base && key[1] <= bhi;
         }
-        if (in) atomicAdd(&sh[(key - base) >> shift], 1u);
-        if (compact) { // one atomic per warp; the order of the list does not matter
-            const unsigned m = __ballot_sync(0xffffffffu, in);
-            if (m) {
-                unsigned long long at = 0ULL;
-                if (lane == __ffs(m) - 1) at = atomicAdd(&c->n_cand, (unsigned long long)__popc(m));
-                at = __shfl_sync(0xffffffffu, at, __ffs(m) - 1);
-                if (in) P.cand[at + __popc(m & ((1u << lane) - 1u))] = key;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (in[q]) atomicAdd(&sh[(key[q] - base) >> shift], 1u);
+            if (compact) { // one atomic per warp; the order of the list does not matter
+                const unsigned m = __ballot_sync(0xffffffffu, in[q]);
+                if (m) {
+                    const int leader = __ffs(m) - 1;
+                    unsigned long long at = 0ULL;
+                    if (lane == leader) at = atomicAdd(&c->n_cand, (unsigned long long)__popc(m));
+                    at = __shfl_sync(0xffffffffu, at, leader);
+                    if (in[q]) P.cand[at + __popc(m & ((1u << lane) - 1u))] = key[q];
+                }
             }
         }
     }
@@ -432,13 +457,13 @@ __global__ void ce_begin_kernel(const CeDev P)
     ce_select_begin(P, Gathered{P.hrecv, CE_BINS, P.world});
 }
 
-__global__ void __launch_bounds__(CE_BLOCK) ce_pick_kernel(const CeDev P)
+__global__ void __launch_bounds__(CE_SEL_BLOCK) ce_pick_kernel(const CeDev P)
 {
     if (!P.ctrl->active || P.ctrl->sel_done) return;
     ce_pick(P, Gathered{P.hrecv, CE_BINS, P.world});
 }
 
-__global__ void __launch_bounds__(CE_BLOCK) ce_cand_level_kernel(const CeDev P)
+__global__ void __launch_bounds__(CE_SEL_BLOCK) ce_cand_level_kernel(const CeDev P)
 {
     __shared__ unsigned int sh[CE_BINS];
     if (!P.ctrl->active || P.ctrl->sel_done) return;
@@ -446,6 +471,25 @@ __global__ void __launch_bounds__(CE_BLOCK) ce_cand_level_kernel(const CeDev P)
 }
 
 // ---- the elite set in sample order --------------------------------------------------------------------------------
+
+constexpr int CE_PER_THREAD = CE_TILE / CE_BLOCK;
+
+// the keys of this thread's CE_PER_THREAD consecutive samples of tile `tile`; `valid` bit q = sample exists
+__device__ __forceinline__ unsigned tile_keys(const CeDev &P, long long tile, unsigned long long (&key)[CE_PER_THREAD])
+{
+    const long long base = tile * CE_TILE + (long long)threadIdx.x * CE_PER_THREAD;
+    unsigned valid = 0u;
+#pragma unroll
+    for (int q = 0; q < CE_PER_THREAD; q += 2) {
+        double2 cv = make_double2(0.0, 0.0);
+        if (base + q < P.nloc) cv = *reinterpret_cast<const double2 *>(P.cost + base + q); // ld is a multiple of 16
+        key[q] = cost_key(cv.x);
+        key[q + 1] = cost_key(cv.y);
+        if (base + q < P.nloc) valid |= 1u << q;
+        if (base + q + 1 < P.nloc) valid |= 1u << (q + 1);
+    }
+    return valid;
+}
 
 // per tile: samples below the k-th key and samples equal to it; the last CTA turns the counts into offsets
 __global__ void __launch_bounds__(CE_BLOCK) ce_count_kernel(const CeDev P)
@@ -455,16 +499,14 @@ __global__ void __launch_bounds__(CE_BLOCK) ce_count_kernel(const CeDev P)
     CeCtrl *c = P.ctrl;
     if (!c->active) return;
     const unsigned long long T = c->base;
-    const long long base = (long long)blockIdx.x * CE_TILE + threadIdx.x * 4;
+    unsigned long long key[CE_PER_THREAD];
+    const unsigned valid = tile_keys(P, blockIdx.x, key);
     int less = 0, ties = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const long long li = base + q;
-        if (li < P.nloc) {
-            const unsigned long long key = cost_key(P.cost[li]);
-            less += key < T;
-            ties += key == T;
-        }
+    for (int q = 0; q < CE_PER_THREAD; ++q) {
+        const bool v = (valid >> q) & 1u;
+        less += v && key[q] < T;
+        ties += v && key[q] == T;
     }
     int tl, tt;
     block_exclusive_scan(less, 0, OpAddI(), s_a, tl);
@@ -474,24 +516,35 @@ __global__ void __launch_bounds__(CE_BLOCK) ce_count_kernel(const CeDev P)
         P.blk_tie[blockIdx.x] = tt;
     }
     if (!ce_last_block(c, gridDim.x)) return;
+    // offsets: every thread owns a run of consecutive tiles; two block scans in all (ties first: how many of a tile's
+    // ties are elite depends on the ties before it)
     const long long tie_take = c->tie_take;
-    long long run_tie = 0, run_el = 0;
-    for (long long t0 = 0; t0 < P.ntiles; t0 += blockDim.x) {
-        const long long t = t0 + threadIdx.x;
-        const long long lt = t < P.ntiles ? __ldcg(P.blk_less + t) : 0, tc = t < P.ntiles ? __ldcg(P.blk_tie + t) : 0;
-        long long tot_tie, tot_el;
-        const long long ex_tie = run_tie + block_exclusive_scan(tc, 0LL, OpAddLL(), s_scan, tot_tie);
-        long long tie_el = tie_take - ex_tie;
+    const long long per = (P.ntiles + blockDim.x - 1) / blockDim.x;
+    const long long t0 = (long long)threadIdx.x * per, t1 = t0 + per < P.ntiles ? t0 + per : P.ntiles;
+    long long my_tie = 0;
+    for (long long t = t0; t < t1; ++t) my_tie += __ldcg(P.blk_tie + t);
+    long long total;
+    const long long ex_tie0 = block_exclusive_scan(my_tie, 0LL, OpAddLL(), s_scan, total);
+    long long my_el = 0, run_tie = ex_tie0;
+    for (long long t = t0; t < t1; ++t) {
+        const long long tc = __ldcg(P.blk_tie + t);
+        long long tie_el = tie_take - run_tie;
         tie_el = tie_el < 0 ? 0 : (tie_el > tc ? tc : tie_el);
-        const long long ex_el = run_el + block_exclusive_scan(lt + tie_el, 0LL, OpAddLL(), s_scan, tot_el);
-        if (t < P.ntiles) {
-            P.blk_tie_off[t] = ex_tie;
-            P.blk_el_off[t] = ex_el;
-        }
-        run_tie += tot_tie;
-        run_el += tot_el;
+        my_el += __ldcg(P.blk_less + t) + tie_el;
+        run_tie += tc;
     }
-    if (threadIdx.x == 0) c->n_elite_local = run_el;
+    long long run_el = block_exclusive_scan(my_el, 0LL, OpAddLL(), s_scan, total);
+    run_tie = ex_tie0;
+    for (long long t = t0; t < t1; ++t) {
+        const long long tc = __ldcg(P.blk_tie + t);
+        long long tie_el = tie_take - run_tie;
+        tie_el = tie_el < 0 ? 0 : (tie_el > tc ? tc : tie_el);
+        P.blk_tie_off[t] = run_tie;
+        P.blk_el_off[t] = run_el;
+        run_el += __ldcg(P.blk_less + t) + tie_el;
+        run_tie += tc;
+    }
+    if (threadIdx.x == 0) c->n_elite_local = total;
 }
 
 // elite local indices in ascending sample order (deterministic summation order downstream)
@@ -501,44 +554,41 @@ __global__ void __launch_bounds__(CE_BLOCK) ce_compact_kernel(const CeDev P)
     if (!P.ctrl->active) return;
     const unsigned long long T = P.ctrl->base;
     const long long tie_take = P.ctrl->tie_take;
-    const long long base = (long long)blockIdx.x * CE_TILE + threadIdx.x * 4;
-    bool less[4], tie[4];
-    int tc = 0;
+    const long long base = (long long)blockIdx.x * CE_TILE + (long long)threadIdx.x * CE_PER_THREAD;
+    unsigned long long key[CE_PER_THREAD];
+    const unsigned valid = tile_keys(P, blockIdx.x, key);
+    unsigned less = 0u, tie = 0u;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const long long li = base + q;
-        less[q] = tie[q] = false;
-        if (li < P.nloc) {
-            const unsigned long long key = cost_key(P.cost[li]);
-            less[q] = key < T;
-            tie[q] = key == T;
-        }
-        tc += tie[q];
+    for (int q = 0; q < CE_PER_THREAD; ++q) {
+        const bool v = (valid >> q) & 1u;
+        if (v && key[q] < T) less |= 1u << q;
+        if (v && key[q] == T) tie |= 1u << q;
     }
     int dummy;
-    long long tie_rank = P.blk_tie_off[blockIdx.x] + block_exclusive_scan(tc, 0, OpAddI(), s_a, dummy);
-    bool el[4];
-    int ec = 0;
+    long long tie_rank = P.blk_tie_off[blockIdx.x] + block_exclusive_scan(__popc(tie), 0, OpAddI(), s_a, dummy);
+    unsigned el = less;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        el[q] = less[q] || (tie[q] && tie_rank < tie_take);
-        tie_rank += tie[q];
-        ec += el[q];
+    for (int q = 0; q < CE_PER_THREAD; ++q) {
+        if ((tie >> q) & 1u) {
+            if (tie_rank < tie_take) el |= 1u << q;
+            tie_rank++;
+        }
     }
-    long long pos = P.blk_el_off[blockIdx.x] + block_exclusive_scan(ec, 0, OpAddI(), s_a, dummy);
+    long long pos = P.blk_el_off[blockIdx.x] + block_exclusive_scan(__popc(el), 0, OpAddI(), s_a, dummy);
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-        if (el[q]) P.elite_idx[pos++] = base + q;
+    for (int q = 0; q < CE_PER_THREAD; ++q)
+        if ((el >> q) & 1u) P.elite_idx[pos++] = base + q;
 }
 
 // regenerate the elites from their counters into Ex[d][j] (the N x n sample matrix never existed)
-template <bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK) ce_elite_gen_kernel(const CeDev P)
+template <bool REPLAY> __global__ void __launch_bounds__(CE_GEN_BLOCK) ce_elite_gen_kernel(const CeDev P)
 {
     extern __shared__ double s_ms[];
     CeCtrl *c = P.ctrl;
     if (!c->active) return;
     const uint32_t t = (uint32_t)(c->iter - 1);
     double *smu = s_ms, *ssig = s_ms + P.n;
+    if constexpr (!REPLAY) devmath_tables_load();
     load_mu_sigma(P, smu, ssig);
     const long long ne = c->n_elite_local;
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < ne; j += (long long)gridDim.x * blockDim.x) {
@@ -688,6 +738,7 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(1024, 1) ce_
     CeCtrl *c = P.ctrl;
     const int tid = threadIdx.x, n = P.n, N = (int)P.nloc, k = (int)P.k;
     double *smu = s_dyn, *ssig = s_dyn + n, *scost = s_dyn + 2 * n, *sEx = s_dyn + 2 * n + N; // [n] [n] [N] [k][n]
+    if constexpr (!REPLAY) devmath_tables_load();
     for (long long pass = 0; pass < iters; ++pass) {
         if (!c->active) break; // :255 (uniform: written before the last barrier of the previous pass)
         const uint32_t t = (uint32_t)(c->iter - 1);
@@ -1003,7 +1054,9 @@ public:
 
     void launch_level(int compact, int fused)
     {
-        ce_level_kernel<<<grid_for(d_.nloc), CE_BLOCK, 0, ctx_->stream>>>(d_, compact, fused);
+        const long long need = std::max<long long>(1, ((d_.nloc + 1) / 2 + CE_SEL_BLOCK - 1) / CE_SEL_BLOCK);
+        const int grid = (int)std::min<long long>(need, 2LL * ctx_->sm_count);
+        ce_level_kernel<<<grid, CE_SEL_BLOCK, 0, ctx_->stream>>>(d_, compact, fused);
         launches_++;
     }
 
@@ -1021,7 +1074,8 @@ public:
         }
         auto gen = [&](auto kernel) {
             if (smem > kSmemOptIn) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kernel<<<grid_for(D.kcap), CE_BLOCK, smem, s>>>(D);
+            const long long need = std::max<long long>(1, (D.kcap + CE_GEN_BLOCK - 1) / CE_GEN_BLOCK);
+            kernel<<<(int)std::min<long long>(need, 32LL * ctx_->sm_count), CE_GEN_BLOCK, smem, s>>>(D);
             launches_++;
         };
         if (D.replay != nullptr) gen(ce_elite_gen_kernel<true>);
@@ -1054,7 +1108,7 @@ public:
         const CeDev &D = d_;
         const int dim_grid = (D.n + 127) / 128;
         auto pick = [&] {
-            ce_pick_kernel<<<1, CE_BLOCK, 0, s>>>(D);
+            ce_pick_kernel<<<1, CE_SEL_BLOCK, 0, s>>>(D);
             launches_++;
         };
         if (phase == 0) {
@@ -1068,7 +1122,7 @@ public:
             launch_level(1, CE_PHASED);
         } else if (phase <= 6) {
             pick();
-            ce_cand_level_kernel<<<1, CE_BLOCK, 0, s>>>(D);
+            ce_cand_level_kernel<<<1, CE_SEL_BLOCK, 0, s>>>(D);
             launches_++;
         } else if (phase == 7) {
             pick();

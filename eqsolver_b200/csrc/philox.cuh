@@ -67,17 +67,20 @@ __device__ __forceinline__ double u01(uint32_t w_lo, uint32_t w_hi)
     return __dadd_rn(__hiloint2double((int)((w_hi & 0xFFFFFu) | 0x3FF00000u), (int)w_lo), -1.0);
 }
 
+#ifdef EQS_DEVMATH_TABLES
 // Box-Muller on one block per dimension PAIR: z0 = r cos(2 pi u2), z1 = r sin(2 pi u2), r = sqrt(-2 ln(1-u1)).
-// Stands in for rand_distr's StandardNormal (cross_entropy.rs:270).
+// Stands in for rand_distr's StandardNormal (cross_entropy.rs:270).  The logarithm reads devmath.cuh's shared-memory
+// tables: the calling kernel runs devmath_tables_load() first.
 __device__ __forceinline__ void normal_pair(uint4 w, double &z0, double &z1)
 {
     // 1 - u1 = 2 - (1.mantissa): the same value as 1.0 - u01(w.x, w.y) (both differences are exact) in one DADD
     const double u1c = __dsub_rn(2.0, __hiloint2double((int)((w.y & 0xFFFFFu) | 0x3FF00000u), (int)w.x));
-    const double r = sqrt_boxmuller(-2.0 * log_unit(u1c));
+    const double r = sqrt_boxmuller(-2.0 * log_unit_tab(u1c));
     double s, c;
     sincos2pi_mantissa(__hiloint2double((int)((w.w & 0xFFFFFu) | 0x3FF00000u), (int)w.z), s, c); // u2 = this - 1
     z0 = r * c;
     z1 = r * s;
 }
+#endif // EQS_DEVMATH_TABLES
 
 } // namespace eqs
