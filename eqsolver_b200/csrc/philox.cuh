@@ -37,10 +37,15 @@ __host__ __device__ inline PhiloxKey philox_key(uint32_t lo, uint32_t hi)
 
 __host__ __device__ inline PhiloxKey philox_key(uint64_t seed) { return philox_key((uint32_t)seed, (uint32_t)(seed >> 32)); }
 
+// EQS_PHILOX_ROUNDS exists for ONE purpose: measuring what the ten rounds cost (profiles/r02_sweep.md builds a 7-round
+// variant, Random123's smallest Crush-resistant one).  The draw contract, the oracle and every parity test are 10 rounds.
+#ifndef EQS_PHILOX_ROUNDS
+#define EQS_PHILOX_ROUNDS 10
+#endif
 __host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKey &key)
 {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < EQS_PHILOX_ROUNDS; ++r) {
         const uint32_t k0 = key.k0[r], k1 = key.k1[r];
         const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
         const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
