@@ -533,130 +533,10 @@ __global__ void __launch_bounds__(PSO_BLOCK, EQS_PSO_MINB) pso_step_kernel(const
     }
 }
 
-// K2p: the same pass with the population STREAMED THROUGH SHARED MEMORY by per-thread cp.async (LDGSTS), two stages deep.
-// Why: the register kernel above keeps a warp's loads in flight only while the warp waits for them -- during its 8
-// dimensions of Philox + update + objective nothing of that warp is on the way, so on average well under half of the
-// 96 KB per SM it could have outstanding are outstanding, and the kernel sits at 0.82-0.88 of the bandwidth its own access
-// pattern reaches without arithmetic (eqs_measure_pattern).  Here the copy of batch i+1 (or of the next particle's first
-// batch) is issued BEFORE the math of batch i, into the other stage of a ring in shared memory, with no registers held
-// for it.  Unlike a TMA tile (tried in round 1: a bulk tile cannot skip the stale pbest sectors or follow the per-particle
-// buffer roles) every thread still chooses its own addresses: role-swapped buffers and the stale-pbest skip are kept, so
-// the traffic stays <= 40n + 16 bytes per particle-evaluation.  A thread only ever reads what it copied itself, so
-// cp.async.wait_group is all the synchronisation there is.  Same device functions per group as the register kernel:
-// the results are bit-identical.  Used for streaming objectives, device draws and n a multiple of 8.
-constexpr int PIPE_PIECES = 12; // 16-byte pieces per thread and stage: {x, v, pbest} x 2 groups x 2 halves of a sector
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// piece p of this thread in `stage`: consecutive lanes are consecutive 16-byte words (no bank conflicts either way)
-__device__ __forceinline__ double2 *pipe_slot(double2 *ring, int stage, int p)
-{
-    return ring + ((stage * PIPE_PIECES + p) * PSO_BLOCK + threadIdx.x);
-}
-
-// Issue the copies of batch b (groups 2b, 2b+1) for the 32 particles of this warp.  A lane does NOT copy its own
-// particle: a 16-byte cp.async per lane on its own 32-byte sector would touch every sector twice (two half-sector
-// requests per warp instruction: measured 25 % slower than the register kernel).  Instead lane l copies half (l & 1) of
-// the sector of the particle owned by lane 16 j + (l >> 1), j = 0, 1: every warp instruction moves 16 whole, consecutive
-// sectors.  li0 = particle of lane 0, f = this lane's flag byte (shuffled to the copying lane).
-__device__ __forceinline__ void pipe_issue(const PsoDev &P, double2 *ring, int stage, long long li0, int b, unsigned f)
-{
-    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31, h = lane & 1;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int sl = 16 * j + (lane >> 1);             // whose sector this lane copies
-        const unsigned fs = __shfl_sync(0xffffffffu, f, sl);
-        const long long ls = li0 + sl;
-        if (ls >= P.nloc) continue;
-        const bool stale = fs & 1u, role = fs & 2u;
-        const double *xin = role ? P.pb : P.x, *pbin = role ? P.x : P.pb;
-        double2 *dst = ring + (size_t)stage * PIPE_PIECES * PSO_BLOCK + wbase + sl;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            const long long off = goff(P, 2 * b + g, ls) + 2 * h;
-            cp_async16(dst + ((0 * 2 + g) * 2 + h) * PSO_BLOCK, xin + off);
-            cp_async16(dst + ((1 * 2 + g) * 2 + h) * PSO_BLOCK, P.v + off);
-            if (!stale) cp_async16(dst + ((2 * 2 + g) * 2 + h) * PSO_BLOCK, pbin + off);
-        }
-    }
-}
-
-__device__ __forceinline__ D4 pipe_read(double2 *ring, int stage, int arr, int g)
-{
-    const double2 lo = *pipe_slot(ring, stage, (arr * 2 + g) * 2), hi = *pipe_slot(ring, stage, (arr * 2 + g) * 2 + 1);
-    D4 r;
-    r.e[0] = lo.x; r.e[1] = lo.y; r.e[2] = hi.x; r.e[3] = hi.y;
-    return r;
-}
-
-template <class Obj>
-__global__ void __launch_bounds__(PSO_BLOCK, EQS_PSO_MINB) pso_step_pipe_kernel(const PsoDev P, int inline_apply)
-{
-    extern __shared__ double sG[];
-    __shared__ MinLoc s_red[32];
-    PsoCtrl *ctrl = P.ctrl;
-    if (ctrl->stalled) return; // :395-397
-    const uint32_t t = (uint32_t)ctrl->iter;
-    load_gbest(P, sG);
-    const int n = P.n, nb = n >> 3, lane = threadIdx.x & 31;
-    double2 *ring = reinterpret_cast<double2 *>(sG + ((n + 3) & ~3)); // n is a multiple of 8: 16-byte aligned
-    MinLoc best{dinf(), kNoIndex};
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x; // this lane's particle; the loop is uniform per WARP
-    unsigned f = li < P.nloc ? P.pbflag[li] : 0u;
-    int stage = 0;
-    if (li - lane < P.nloc) pipe_issue(P, ring, 0, li - lane, 0, f);
-    cp_async_commit();
-    while (li - lane < P.nloc) {
-        const bool valid = li < P.nloc;
-        const long long li_next = li + stride;
-        const unsigned f_next = li_next < P.nloc ? P.pbflag[li_next] : 0u;
-        const double pbc_old = valid ? P.pbc[li] : 0.0; // issued now, consumed after the last dimension
-        const bool stale = f & 1u, role = f & 2u;
-        double *xout = (role != stale) ? P.pb : P.x; // a stale particle moves to the other buffer
-        ObjAcc acc;
-        Obj::begin(acc, n);
-        for (int b = 0; b < nb; ++b) {
-            __syncwarp(); // every lane is done reading the stage that is about to be refilled
-            if (b + 1 < nb) pipe_issue(P, ring, stage ^ 1, li - lane, b + 1, f);
-            else if (li_next - lane < P.nloc) pipe_issue(P, ring, stage ^ 1, li_next - lane, 0, f_next);
-            cp_async_commit();  // possibly an empty group: the count below stays uniform
-            cp_async_wait<1>(); // everything but the group just committed has landed: this batch is in `stage`
-            __syncwarp();       // ... including what the other lanes copied for this one
-            if (valid) {
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    D4 x = pipe_read(ring, stage, 0, g), v = pipe_read(ring, stage, 1, g);
-                    const D4 pb = stale ? x : pipe_read(ring, stage, 2, g);
-                    pso_group_math<Obj, false, true>(P, t, P.first + li, 2 * b + g, sG, acc, x, v, pb, 4);
-                    const long long off = goff(P, 2 * b + g, li);
-                    st256(xout + off, x);
-                    st256(P.v + off, v);
-                }
-            }
-            stage ^= 1;
-        }
-        if (valid) pso_finish_particle(P, li, Obj::end(acc, n), pbc_old, f, best);
-        li = li_next;
-        f = f_next;
-    }
-    cp_async_wait<0>();
-    MinLoc win;
-    if (grid_minloc_last_block(P, best, s_red, win)) {
-        write_record(P, win.c, win.i, nullptr);
-        if (inline_apply == 1) {
-            __syncthreads();
-            pso_apply_step(P, P.send, 1);
-        } else if (inline_apply == 2) {
-            pso_p2p_exchange_apply(P);
-        }
-    }
-}
+// (A variant of this kernel that streams the population through a two-stage shared-memory ring with per-thread cp.async
+// was built and measured in round 2 -- bit-identical, but slower: 0.64-0.87 of measured HBM on C2 and 0.59-0.67 on C4
+// against 0.88 / 0.82 here, because a 16-byte LDGSTS per lane doubles the L2 sector requests and the ring's LDS / LDGSTS
+// traffic stalls the MIO queue.  profiles/r02_sweep.md has the ncu rows; the code is in the history, not in the product.)
 
 __global__ void pso_step_apply_kernel(const PsoDev P)
 {
@@ -1130,7 +1010,6 @@ int PsoSolver::create(const eqs_pso_params *p)
     EQS_CUDA(ctx_, cudaEventCreate(&ev1_));
     // sequential mode on one rank beyond the single-CTA kernel's reach: device-driven windowed rounds
     // (EQS_PSO_SEQ_HOST=1 keeps the host-driven whole-suffix rounds, which ranks > 1 always use)
-    if (const char *e = getenv("EQS_PSO_PIPE")) pipe_enabled_ = atoi(e) != 0;
     seq_windowed_ = p->mode == EQS_PSO_SEQUENTIAL_EXACT && d_.world == 1 && !manual_ && d_.nloc > PSO_SMALL_MAX &&
                     !getenv("EQS_PSO_SEQ_HOST");
     return EQS_OK;
@@ -1243,7 +1122,7 @@ int PsoSolver::launch_step()
     const bool replay = d_.replay != nullptr;
     const int inline_apply = (d_.world == 1 && !manual_) ? 1 : (fused_exchange_ ? 2 : 0);
     int rc = EQS_OK;
-    size_t smem = (size_t)((d_.n + 3) / 4) * 4 * sizeof(double);
+    const size_t smem = (size_t)((d_.n + 3) / 4) * 4 * sizeof(double);
     dispatch_objective(p_.objective_id, [&]<class Obj>() {
         auto run = [&](auto kernel) {
             if (grid_step_ == 0) {
@@ -1253,16 +1132,6 @@ int PsoSolver::launch_step()
             kernel<<<grid_step_, PSO_BLOCK, smem, ctx_->stream>>>(d_, inline_apply);
             launches_++;
         };
-        // streaming objective, device draws, whole batches of 8 dimensions: the cp.async-pipelined kernel (K2p)
-        bool pipe = false;
-        if constexpr (Obj::streaming) pipe = !replay && d_.n % 8 == 0 && pipe_enabled_;
-        if constexpr (Obj::streaming) {
-            if (pipe) {
-                smem += (size_t)2 * PIPE_PIECES * PSO_BLOCK * sizeof(double2);
-                run(pso_step_pipe_kernel<Obj>);
-                return;
-            }
-        }
         if (replay) run(pso_step_kernel<Obj, true>);
         else run(pso_step_kernel<Obj, false>);
     });

@@ -105,7 +105,6 @@ public:
     bool fused_exchange_ = false; // synchronous step exchanges over peer memory inside the step kernel
     bool in_sync_step_ = false;
     bool initialised_ = false;    // init() / init_apply() has run: stepping or reading before that is refused
-    bool pipe_enabled_ = true;    // synchronous step through the cp.async-pipelined kernel where it applies (EQS_PSO_PIPE=0: never)
     bool seq_windowed_ = false;   // sequential mode: device-driven windowed rounds (one rank, more than PSO_SMALL_MAX particles)
     int grid_seqw_ = 0;
     double seq_rounds_per_pass_ = 16.0;
