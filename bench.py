@@ -632,6 +632,16 @@ def main():
         # the same access pattern with the arithmetic removed, measured now on this GPU (informational second ceiling)
         pattern = b.ctx.measure_pattern(n, per_gpu) if n % 8 == 0 else None
         roofline = pso_roofline(wl, n, per_gpu, ms / args.steps, pattern)
+        if pattern is not None:
+            # the same pattern SUSTAINED for a second (csrc/api.cu: EQS_PATTERN_SECONDS): what the power-capped board
+            # delivers for this traffic without any arithmetic -- the ceiling a long run of the step kernel is under
+            os.environ["EQS_PATTERN_SECONDS"] = "1.0"
+            try:
+                sustained = b.ctx.measure_pattern(n, per_gpu)
+            finally:
+                os.environ.pop("EQS_PATTERN_SECONDS", None)
+            roofline["pattern_ceiling"]["sustained"] = {"value": sustained, "unit": "GB/s", "seconds": 1.0,
+                                                        "frac": roofline["achieved"] / sustained}
 
     line = {
         "metric": unit, "value": value, "unit": unit, "n_gpus": world,

@@ -443,6 +443,21 @@ int eqs_measure_pattern(eqs_ctx *ctx, int32_t n, int64_t particles, double *gbps
         cudaEventElapsedTime(&ms, e0, e1);
         if (rep > 0) best = std::max(best, 5.0 * (double)bytes / (ms * 1e-3) / 1e9);
     }
+    // EQS_PATTERN_SECONDS=t: the SUSTAINED figure instead of the burst -- launches back to back for about t seconds
+    // between two events (what the board delivers for this traffic once the power cap has settled the clocks)
+    if (const char *e = getenv("EQS_PATTERN_SECONDS")) {
+        const double seconds = atof(e);
+        if (seconds > 0.0) {
+            const long long launches = std::max<long long>(8, (long long)(seconds * best * 1e9 / (5.0 * (double)bytes)));
+            cudaEventRecord(e0, c->stream);
+            for (long long k = 0; k < launches; ++k) pattern_kernel<<<grid, 256, 0, c->stream>>>(buf[0], buf[1], buf[2], ld, groups);
+            cudaEventRecord(e1, c->stream);
+            EQS_CUDA(c, cudaEventSynchronize(e1));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            best = 5.0 * (double)bytes * (double)launches / (ms * 1e-3) / 1e9;
+        }
+    }
     *gbps = best;
     return EQS_OK;
     EQS_BOUNDARY_CATCH

@@ -342,6 +342,9 @@ template <class Obj> __global__ void pso_x0_kernel(const PsoDev P)
     c->seq_target = 0;
     c->seq_parity = 0;
     c->seq_commit_buf = 0;
+    c->seq_round = 0ULL;
+    c->seq_barrier = 0u;
+    c->seq_slot[0] = c->seq_slot[1] = c->seq_slot[2] = ~0ULL;
 }
 
 // :361-389 without the (order-dependent) gbest bookkeeping, which pso_ring_scan_kernel reconstructs
@@ -644,6 +647,7 @@ __global__ void __launch_bounds__(PSO_BLOCK) pso_commit_kernel(const PsoDev P, l
 __global__ void pso_seq_arm_kernel(const PsoDev P, long long iters, long long wmin, long long wmax, long long w0, double wscale)
 {
     PsoCtrl *c = P.ctrl;
+    c->seq_barrier = 0u;
     c->seq_target = c->iter + iters;
     c->seq_wmin = wmin;
     c->seq_wmax = wmax;
@@ -657,93 +661,179 @@ __global__ void pso_seq_arm_kernel(const PsoDev P, long long iters, long long wm
     if (c->seq_window > wmax) c->seq_window = wmax;
 }
 
+// Round 2: the rounds no longer are launches.  ONE persistent kernel (cooperative launch: every CTA resident) runs all
+// rounds of all `iters` passes; the rounds are separated by a grid-wide barrier (one atomic per CTA on a monotonic
+// counter) instead of a kernel boundary.  Every CTA keeps its OWN copy of the loop state (gbest cost, stall ring, window,
+// parity, pass counter) in shared memory and advances it with the same deterministic rule from the same inputs, so the
+// only thing that crosses CTAs per round is the first improving index: an atomicMin on one of three rotating slots before
+// the barrier, one load after it (the slot of round r is reset in round r+1's shadow for round r+3... see below).  The
+// improving particle's position is read straight from the speculated buffer by every CTA into its shared-memory gbest.
+// Fixed cost of a round: ~11 us as a launch (launch gap + tail + last-CTA reduction) -> the barrier's ~2 us, which also
+// moves the best window size down by 2x (W ~ sqrt(c_r)).
+struct SeqLocal {
+    double Gc;
+    double ring[EQS_STALL_WINDOW];
+    double kest;
+    long long ring_i, iter, improvements, imp0;
+    long long start, window, commit_lo, commit_hi;
+    unsigned long long round;
+    int parity, commit_buf, stalled;
+};
+
+// all threads of every CTA call; returns when every CTA of the grid has arrived.  `counter` only grows: arrival number
+// k of this launch waits for k * gridDim.x (reset to 0 by pso_seq_arm_kernel before the launch).
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int &target)
+{
+    __threadfence(); // this thread's writes, before the block's arrival is published
+    __syncthreads();
+    target += gridDim.x;
+    if (threadIdx.x == 0) {
+        atomicAdd(counter, 1u);
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+    }
+    __syncthreads();
+}
+
 template <class Obj, bool REPLAY>
-__global__ void __launch_bounds__(PSO_BLOCK) pso_seqw_kernel(const PsoDev P)
+__global__ void __launch_bounds__(PSO_BLOCK) pso_seqp_kernel(const PsoDev P)
 {
     extern __shared__ double sG[];
     __shared__ MinLoc s_red[32];
-    __shared__ int s_found;
+    __shared__ SeqLocal S;
+    __shared__ unsigned long long s_first;
     PsoCtrl *ctrl = P.ctrl;
-    const long long clo = ctrl->seq_commit_lo, chi = ctrl->seq_commit_hi;
-    const int cbuf = ctrl->seq_commit_buf, parity = ctrl->seq_parity;
-    const bool active = !ctrl->stalled && ctrl->iter < ctrl->seq_target;
-    const long long start = ctrl->seq_start, W = ctrl->seq_window, N = P.nloc;
-    const uint32_t t = (uint32_t)ctrl->iter;
-    const double Gc = ctrl->Gc;
-    if (!active && clo > chi) return; // uniform over the grid: nothing pending, nothing to do
-    const long long stride = (long long)gridDim.x * blockDim.x, gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int tid = threadIdx.x;
+    const long long N = P.nloc;
+    if (tid == 0) { // every CTA reads the same control block: nothing writes it until the kernel's last lines
+        S.Gc = ctrl->Gc;
+        for (int j = 0; j < EQS_STALL_WINDOW; ++j) S.ring[j] = ctrl->ring[j];
+        S.ring_i = ctrl->ring_i;
+        S.iter = ctrl->iter;
+        S.improvements = ctrl->improvements;
+        S.imp0 = ctrl->seq_imp0;
+        S.kest = ctrl->seq_kest;
+        S.start = ctrl->seq_start;
+        S.window = ctrl->seq_window;
+        S.commit_lo = ctrl->seq_commit_lo;
+        S.commit_hi = ctrl->seq_commit_hi;
+        S.commit_buf = ctrl->seq_commit_buf;
+        S.parity = ctrl->seq_parity;
+        S.stalled = ctrl->stalled;
+        S.round = ctrl->seq_round;
+    }
+    const long long target_iter = ctrl->seq_target, wmin = ctrl->seq_wmin, wmax = ctrl->seq_wmax;
+    const double wscale = ctrl->seq_wscale;
+    load_gbest(P, sG); // ends with a barrier: S is visible
+    unsigned int arrivals = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x, gtid = (long long)blockIdx.x * blockDim.x + tid;
     // particle li is always handled by thread li mod stride, so a particle's pending commit precedes its speculation
     auto first_at = [&](long long lo) {
         long long r = (gtid - lo) % stride;
         if (r < 0) r += stride;
         return lo + r;
     };
-    if (clo <= chi) { // :417-419 for the particles the previous round made final
-        const double *src = cbuf ? P.x2 : P.x;
-        const int nq = (P.n + 3) >> 2;
-        for (long long li = first_at(clo); li <= chi; li += stride) {
-            const double c = P.cost[li];
-            if (c < P.pbc[li]) {
-                P.pbc[li] = c;
-                for (int q = 0; q < nq; ++q) {
-                    const long long off = goff(P, q, li);
-                    st256(P.pb + off, ld256(src + off));
+    for (;;) {
+        const bool active = !S.stalled && S.iter < target_iter;
+        const long long clo = S.commit_lo, chi = S.commit_hi, start = S.start, W = S.window;
+        const int cbuf = S.commit_buf, parity = S.parity;
+        const double Gc = S.Gc;
+        const unsigned long long round = S.round;
+        if (clo <= chi) { // :417-419 for the particles the previous round made final
+            const double *src = cbuf ? P.x2 : P.x;
+            const int nq = (P.n + 3) >> 2;
+            for (long long li = first_at(clo); li <= chi; li += stride) {
+                const double c = P.cost[li];
+                if (c < P.pbc[li]) {
+                    P.pbc[li] = c;
+                    for (int q = 0; q < nq; ++q) {
+                        const long long off = goff(P, q, li);
+                        st256(P.pb + off, ld256(src + off));
+                    }
                 }
             }
         }
-    }
-    MinLoc first{0.0, kNoIndex}; // min over the index only
-    const long long wend = start + W < N ? start + W : N;
-    if (active) {
-        load_gbest(P, sG);
+        if (!active) break; // the same decision in every CTA; the pending commit above was the last thing to do
+        const uint32_t t = (uint32_t)S.iter;
+        const long long wend = start + W < N ? start + W : N;
         const double *xa = parity ? P.x2 : P.x, *va = parity ? P.v2 : P.v;
         double *xb = parity ? P.x : P.x2, *vb = parity ? P.v : P.v2;
+        MinLoc first{0.0, kNoIndex}; // min over the index only
         for (long long li = first_at(start); li < wend; li += stride) {
             const double cost = pso_move<Obj, REPLAY>(P, t, li, sG, xa, va, P.pb, xb, vb, true);
             P.cost[li] = cost;
             if (cost < P.pbc[li] && cost < Gc && li < first.i) first.i = li; // :417,:420 (nested; see pso_spec_kernel)
         }
-    }
-    MinLoc win;
-    if (!grid_minloc_last_block(P, first, s_red, win)) return;
-    if (threadIdx.x == 0) {
-        PsoCtrl *c = ctrl;
-        int found = 0;
-        if (active) {
-            found = win.i != kNoIndex;
-            const long long hi = found ? win.i : wend - 1;
-            c->seq_commit_lo = start;
-            c->seq_commit_hi = hi;
-            c->seq_commit_buf = parity ^ 1;
+        const MinLoc b = block_minloc(first, s_red);
+        if (tid == 0 && b.i != kNoIndex) atomicMin(&ctrl->seq_slot[round % 3], (unsigned long long)b.i);
+        grid_barrier(&ctrl->seq_barrier, arrivals);
+        if (tid == 0) {
+            unsigned long long w;
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(&ctrl->seq_slot[round % 3]) : "memory");
+            s_first = w;
+            // the slot of round r+2: its last readers (round r-1) are behind this barrier, its next writers (round r+2)
+            // are behind the NEXT barrier, which this thread reaches only after the store
+            if (blockIdx.x == 0) ctrl->seq_slot[(round + 2) % 3] = ~0ULL;
+        }
+        __syncthreads();
+        const unsigned long long istar = s_first;
+        const bool found = istar != ~0ULL;
+        if (found) // gbest <- the improving particle's speculated position (buffer B), into this CTA's copy
+            for (int d = tid; d < P.n; d += blockDim.x) sG[d] = __ldcg(xb + goff(P, d >> 2, (long long)istar) + (d & 3));
+        if (tid == 0) {
+            const long long hi = found ? (long long)istar : wend - 1;
+            S.commit_lo = start;
+            S.commit_hi = hi;
+            S.commit_buf = parity ^ 1;
             if (found) { // :420-425
-                ring_push(c, c->Gc);
-                c->Gc = __ldcg(P.cost + win.i);
-                c->improvements += 1;
+                S.ring[S.ring_i] = S.Gc;
+                S.ring_i = (S.ring_i + 1) % EQS_STALL_WINDOW;
+                S.Gc = __ldcg(P.cost + istar);
+                S.improvements += 1;
             }
             if (hi + 1 >= N) { // the pass is complete
-                c->iter += 1;
-                c->stalled = stall_test(c, P.tol);
-                c->seq_start = 0;
-                c->seq_parity = parity ^ 1;
-                c->seq_kest = 0.5 * c->seq_kest + 0.5 * (double)(c->improvements - c->seq_imp0);
-                c->seq_imp0 = c->improvements;
-                const double w = sqrt(c->seq_wscale * (double)N / fmax(c->seq_kest, 0.02));
-                long long wn = w < 9.0e18 ? (long long)w : c->seq_wmax;
-                wn = wn < c->seq_wmin ? c->seq_wmin : wn;
-                c->seq_window = wn > c->seq_wmax ? c->seq_wmax : wn;
+                S.iter += 1;
+                int stalled = 1; // stalled_too_long, :433-441
+                for (int j = 0; j < EQS_STALL_WINDOW; ++j)
+                    if (!(fabs(S.ring[j] - S.Gc) < P.tol)) stalled = 0;
+                S.stalled = stalled;
+                S.start = 0;
+                S.parity = parity ^ 1;
+                S.kest = 0.5 * S.kest + 0.5 * (double)(S.improvements - S.imp0);
+                S.imp0 = S.improvements;
+                const double w = sqrt(wscale * (double)N / fmax(S.kest, 0.02));
+                long long wn = w < 9.0e18 ? (long long)w : wmax;
+                wn = wn < wmin ? wmin : wn;
+                S.window = wn > wmax ? wmax : wn;
             } else {
-                c->seq_start = hi + 1;
+                S.start = hi + 1;
             }
-        } else {
-            c->seq_commit_lo = 1;
-            c->seq_commit_hi = 0;
+            S.round = round + 1;
         }
-        s_found = found;
+        __syncthreads();
     }
-    __syncthreads();
-    if (s_found) { // gbest <- the improving particle's speculated position (buffer B)
-        const double *xb = parity ? P.x : P.x2;
-        for (int d = threadIdx.x; d < P.n; d += blockDim.x) P.G[d] = __ldcg(xb + goff(P, d >> 2, win.i) + (d & 3));
+    // every CTA holds the same final state; one of them stores it
+    if (blockIdx.x == 0) {
+        for (int d = tid; d < P.n; d += blockDim.x) P.G[d] = sG[d];
+        if (tid == 0) {
+            ctrl->Gc = S.Gc;
+            for (int j = 0; j < EQS_STALL_WINDOW; ++j) ctrl->ring[j] = S.ring[j];
+            ctrl->ring_i = S.ring_i;
+            ctrl->iter = S.iter;
+            ctrl->improvements = S.improvements;
+            ctrl->seq_imp0 = S.imp0;
+            ctrl->seq_kest = S.kest;
+            ctrl->seq_start = S.start;
+            ctrl->seq_window = S.window;
+            ctrl->seq_commit_lo = 1; // nothing pending: the loop only ends after the last round's commit
+            ctrl->seq_commit_hi = 0;
+            ctrl->seq_commit_buf = S.commit_buf;
+            ctrl->seq_parity = S.parity;
+            ctrl->stalled = S.stalled;
+            ctrl->seq_round = S.round;
+        }
     }
 }
 
@@ -1188,57 +1278,37 @@ int PsoSolver::sequential_pass()
     return EQS_OK;
 }
 
-// `iters` passes of the sequential mode as device-driven windowed rounds (pso_seqw_kernel).  The host enqueues launches
-// in batches and looks at the control block between batches; launches past the target are no-ops.
+// `iters` passes of the sequential mode as device-driven windowed rounds: one cooperative launch of the persistent
+// kernel (pso_seqp_kernel) behind a one-thread kernel that arms the target pass count and the window policy.
 int PsoSolver::sequential_windowed(int64_t iters)
 {
     const bool replay = d_.replay != nullptr;
     const size_t smem = (size_t)((d_.n + 3) / 4) * 4 * sizeof(double);
     int rc = EQS_OK;
-    auto launch = [&](int count) {
-        dispatch_objective(p_.objective_id, [&]<class Obj>() {
-            auto run = [&](auto kernel) {
-                if (grid_seqw_ == 0) {
-                    rc = persistent_grid(ctx_, kernel, PSO_BLOCK, smem, PSO_BLOCK, d_.nloc, grid_seqw_);
-                    if (rc != EQS_OK) return;
-                }
-                for (int k = 0; k < count; ++k) kernel<<<grid_seqw_, PSO_BLOCK, smem, ctx_->stream>>>(d_);
-                launches_ += count;
-            };
-            if (replay) run(pso_seqw_kernel<Obj, true>);
-            else run(pso_seqw_kernel<Obj, false>);
-        });
-    };
-    launch(0); // sizes the grid
+    const void *kernel_fn = nullptr;
+    dispatch_objective(p_.objective_id, [&]<class Obj>() {
+        auto pick = [&](auto kernel) {
+            kernel_fn = (const void *)kernel;
+            if (grid_seqw_ == 0) rc = persistent_grid(ctx_, kernel, PSO_BLOCK, smem, PSO_BLOCK, d_.nloc, grid_seqw_);
+        };
+        if (replay) pick(pso_seqp_kernel<Obj, true>);
+        else pick(pso_seqp_kernel<Obj, false>);
+    });
     EQS_TRY(rc);
-    // a round costs about 11 us beyond its particles (launch, tail, last-CTA reduction; measured on B200) and a
+    // a round costs about 4 us beyond its particles (grid barrier, ramp-up and tail of the wave; a launch per round cost
+    // 11 -- swept on C2: 1 / 2.5 / 4 / 8 us give 0.447 / 0.402 / 0.386 / 0.416 ms per pass, profiles/r02_sweep.md) and a
     // particle (40n + 16) B of HBM traffic at ~5.7 TB/s
     const long long wave = (long long)grid_seqw_ * PSO_BLOCK;
-    long long wmin = std::min<long long>(8192, wave), wmax = std::max<long long>(d_.nloc, wmin), w0 = std::min(wave, wmax);
-    const double wscale = 2.0 * 11.0 * 5.7e6 / (40.0 * d_.n + 16.0);
+    long long wmin = std::min<long long>(4096, wave), wmax = std::max<long long>(d_.nloc, wmin), w0 = std::min(wave, wmax);
+    double round_us = 4.0;
+    if (const char *e = getenv("EQS_PSO_SEQ_ROUND_US")) round_us = std::max(0.1, atof(e));
+    const double wscale = 2.0 * round_us * 5.7e6 / (40.0 * d_.n + 16.0);
     if (const char *e = getenv("EQS_PSO_SEQ_WINDOW")) wmin = wmax = w0 = std::max<long long>(1, atoll(e));
-    EQS_TRY(fetch_ctrl());
-    if (h_ctrl_->stalled) return EQS_OK;
-    const long long target = h_ctrl_->iter + iters;
     pso_seq_arm_kernel<<<1, 1, 0, ctx_->stream>>>(d_, (long long)iters, wmin, wmax, w0, wscale);
     launches_++;
-    for (;;) {
-        const long long left = target - h_ctrl_->iter;
-        const bool pending = h_ctrl_->seq_commit_lo <= h_ctrl_->seq_commit_hi;
-        if (left <= 0 || h_ctrl_->stalled) {
-            if (pending) launch(1); // the last round's pbest update
-            EQS_TRY(rc);
-            break;
-        }
-        const int batch = (int)std::min<double>(96.0, std::max<double>(4.0, seq_rounds_per_pass_ * (double)left + 1.0));
-        const long long it0 = h_ctrl_->iter;
-        launch(batch);
-        EQS_TRY(rc);
-        EQS_CUDA(ctx_, cudaGetLastError());
-        EQS_TRY(fetch_ctrl());
-        const long long done = h_ctrl_->iter - it0;
-        if (done > 0) seq_rounds_per_pass_ = 0.5 * seq_rounds_per_pass_ + 0.5 * std::min(64.0, (double)batch / (double)done);
-    }
+    void *args[] = {(void *)&d_};
+    EQS_CUDA(ctx_, cudaLaunchCooperativeKernel(kernel_fn, dim3(grid_seqw_), dim3(PSO_BLOCK), args, smem, ctx_->stream));
+    launches_++;
     return EQS_OK;
 }
 

@@ -35,6 +35,9 @@ struct PsoCtrl {
     long long seq_target;           // launches are no-ops once iter reaches it
     int seq_parity;                 // 0: the committed (x, v) live in x / v, 1: in x2 / v2
     int seq_commit_buf;             // which of x (0) / x2 (1) holds the positions of the pending commit
+    unsigned long long seq_round;   // rounds so far (picks the slot below)
+    unsigned long long seq_slot[3]; // first improving particle of round r in slot r % 3 (atomicMin; ~0 = none)
+    unsigned int seq_barrier;       // arrivals at the grid barrier of the current launch of pso_seqp_kernel
 };
 
 struct PsoDev {
@@ -107,7 +110,6 @@ public:
     bool initialised_ = false;    // init() / init_apply() has run: stepping or reading before that is refused
     bool seq_windowed_ = false;   // sequential mode: device-driven windowed rounds (one rank, more than PSO_SMALL_MAX particles)
     int grid_seqw_ = 0;
-    double seq_rounds_per_pass_ = 16.0;
     int max_grid_ = 0;
 
 private:

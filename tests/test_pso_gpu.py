@@ -352,6 +352,23 @@ def test_small_kernel_equals_multi_launch_path(ctx, mode, monkeypatch):
     assert small.last_step_ms()[1] == 1 and big.last_step_ms()[1] >= iters   # launches
 
 
+def test_sequential_passes_are_one_persistent_kernel(ctx):
+    """Above the single-CTA limit, on one rank, ALL rounds of ALL passes of a step() call run inside one cooperative
+    launch (pso_seqp_kernel: grid barriers instead of kernel boundaries) behind a one-thread arming kernel."""
+    n, N = 8, 50000
+    g, o = make(E.Objective.ROSENBROCK, n, N, E.PsoMode.SEQUENTIAL_EXACT, seed=5)
+    x0 = np.full(n, 2.0)
+    run = g.with_context(ctx).start(x0)
+    o.init(x0)
+    for k in (7, 1, 12):
+        run.step(k)
+        for _ in range(k):
+            assert o.step() == 0
+        assert run.last_step_ms()[1] == 2
+        compare_state(run, o, True, f"after {k} passes")
+    assert run.gbest()[4] > 20        # many repair rounds happened
+
+
 def test_sequential_host_driven_path_large_population(ctx):
     """Populations above the single-CTA limit run speculate-and-repair with host-driven rounds."""
     n, N, iters = 5, 2600, 4
