@@ -390,23 +390,27 @@ def pso_roofline(workload: str, n: int, per_gpu: int, ms_per_pass: float, patter
 
 
 def ce_roofline(workload: str, per_gpu: int, ms_per_pass: float, fp64_peak_tflops: float):
-    """The sample kernel against the FP64 pipe: FP64 instructions per sample (static, from the committed ncu capture of
-    this kernel) x samples per second, as DFMA-equivalent TFLOP/s (2 flop per lane), over the DFMA rate eqs_measure_fp64
-    reached in THIS run.  The whole pass is charged to the sample kernel (it is 90+ % of it), so `frac` is a lower bound
-    for the kernel alone."""
+    """The sample kernel against the FP64 pipe: FP64 instructions per sample (static SASS count of this build, cross-checked
+    by the committed ncu capture) x samples per second, as DFMA-equivalent TFLOP/s (2 flop per lane), over the DFMA rate
+    eqs_measure_fp64 reached in THIS run.  The whole pass is charged to the sample kernel (it is 95 % of it), so `frac`
+    is a lower bound for the kernel alone.  `issue_frac` is the same rate against the ISSUE side of the same machine: a
+    scheduler issues one warp instruction per cycle and the FP64 pipe takes one from it every second cycle, so a trip of F
+    FP64 and O other instructions needs at least 2F + O scheduler cycles -- that, not the FP64 pipe alone, is what this
+    kernel runs into, and why the work of both rounds went into the instruction count."""
     obj, n, *_ = CE_WORKLOADS[workload]
     prof = profile_json("ce_sample_fp64.json").get(workload, {})
-    per_sample = prof.get("fp64_instr_per_sample")
+    per_sample, other = prof.get("fp64_instr_per_sample"), prof.get("other_instr_per_sample")
     rate = per_gpu / (ms_per_pass * 1e-3)
     achieved = None if per_sample is None else rate * per_sample * 2.0 / 1e12
-    return {"bound": "fp64", "achieved": achieved, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
-            "frac": None if achieved is None or not fp64_peak_tflops else achieved / fp64_peak_tflops,
+    frac = None if achieved is None or not fp64_peak_tflops else achieved / fp64_peak_tflops
+    return {"bound": "fp64", "achieved": achieved, "peak": fp64_peak_tflops, "unit": "TFLOP/s", "frac": frac,
+            "issue_frac": None if frac is None or other is None else frac * (2.0 * per_sample + other) / (2.0 * per_sample),
             "traffic": prof.get("dram_bytes_per_launch"),
             "traffic_source": ("static: " + prof["source"]) if prof.get("source") else None,
             "peak_source": "measured in this run (eqs_measure_fp64: independent DFMA chains on every SM)",
-            "kernel": "ce_sample_kernel", "fp64_instr_per_sample": per_sample, "samples_per_launch": per_gpu,
-            "algorithmic_hbm_bytes_per_sample": 8,
-            "note": "FP64-pipe (issue) bound, not HBM: the sample matrix never leaves the registers"}
+            "kernel": "ce_sample_kernel", "fp64_instr_per_sample": per_sample, "other_instr_per_sample": other,
+            "samples_per_launch": per_gpu, "algorithmic_hbm_bytes_per_sample": 8,
+            "note": "FP64-pipe / issue bound, not HBM: the sample matrix never leaves the registers"}
 
 
 def bits_checksum(a: np.ndarray) -> np.ndarray:

@@ -1,18 +1,20 @@
 set -x
-D=gpurun_out/r02k; mkdir -p $D
-timeout 900 python -m pytest tests/test_pso_gpu.py tests/test_random_shapes_gpu.py -m gpu -q -x > $D/pytest.log 2>&1; echo "pytest rc=$?" >> $D/pytest.log
-tail -12 $D/pytest.log
-for us in 2.5 1.0 4.0 8.0; do
-  EQS_PSO_SEQ_ROUND_US=$us timeout 120 python benchmarks/seq_bench.py >> $D/seq.log 2>> $D/err.log
+D=gpurun_out/r02m; mkdir -p $D
+# own bounds checks: the variant library under the smoke script and the select / pso tests
+EQS_B200_LIBRARY=$PWD/eqsolver_b200/lib/variants/libeqsolver_b200_bounds.so timeout 600 python tests/sanitizer_smoke.py > $D/bounds_smoke.log 2>&1; echo "bounds smoke rc=$?"
+EQS_B200_LIBRARY=$PWD/eqsolver_b200/lib/variants/libeqsolver_b200_bounds.so timeout 900 python -m pytest tests/test_ce_select_gpu.py tests/test_ce_gpu.py tests/test_pso_gpu.py tests/test_random_shapes_gpu.py -m gpu -q -x -k "not user_objective_hook and not out_of_device_memory" > $D/bounds_pytest.log 2>&1; echo "bounds pytest rc=$?"
+tail -3 $D/bounds_smoke.log; tail -4 $D/bounds_pytest.log
+timeout 600 python -m pytest tests/test_cpp_and_rust_bindings.py -m gpu -q > $D/cpp.log 2>&1; tail -3 $D/cpp.log
+# CrossEntropy: one GPU vs two (p2p mailboxes vs NCCL between the phases)
+timeout 300 python benchmarks/ce_bench.py --no-peaks > $D/ce_c3_n1.json 2>> $D/err.log
+timeout 300 python benchmarks/ce_bench.py --dim 1024 --samples 8388608 --objective ROSENBROCK --iters 5 --warmup 2 --no-peaks > $D/ce_c5_n1.json 2>> $D/err.log
+for p2p in 1 0; do
+EQS_P2P=$p2p timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2961$p2p benchmarks/ce_bench.py --no-peaks > $D/ce_c3_n2_p2p$p2p.json 2>> $D/err.log
+EQS_P2P=$p2p timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2962$p2p benchmarks/ce_bench.py --dim 1024 --samples 8388608 --objective ROSENBROCK --iters 5 --warmup 2 --no-peaks > $D/ce_c5_n2_p2p$p2p.json 2>> $D/err.log
 done
-for w in 20000 40000 80000 160000; do
-  EQS_PSO_SEQ_WINDOW=$w timeout 120 python benchmarks/seq_bench.py >> $D/seqw.log 2>> $D/err.log
-done
-timeout 120 python benchmarks/seq_bench.py --objective RASTRIGIN --lower -5.12 --upper 5.12 >> $D/seq_other.log 2>> $D/err.log
-timeout 120 python benchmarks/seq_bench.py --objective ACKLEY --dim 256 --particles 2097152 --lower -32.768 --upper 32.768 --iters 10 >> $D/seq_other.log 2>> $D/err.log
-cat $D/seq.log $D/seqw.log $D/seq_other.log | python -c "
+grep -h sample_evals $D/ce_*.json | python -c "
 import sys,json
 for ln in sys.stdin:
-    d=json.loads(ln); print(d['workload'][:50], 'sync %.4f ms  seq %.4f ms  x%.2f  seq evals/s %.3e launches/pass %.2f' % (d['synchronous']['ms_per_pass'], d['sequential_exact']['ms_per_pass'], d['sequential_over_synchronous_time'], d['sequential_exact']['evals_per_s'], d['sequential_exact']['launches_per_pass']))
+    d=json.loads(ln); print(d['n_gpus'], d['workload'][:40], '%.4f ms/pass %.4e/s launches %.1f' % (d['ms_per_pass'], d['sample_evals_per_s'], d['kernel_launches_per_pass']))
 "
-tail -3 $D/err.log
+ls $D

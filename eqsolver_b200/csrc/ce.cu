@@ -323,7 +323,10 @@ __device__ __forceinline__ void ce_cand_hist(const CeDev &P, unsigned int *sh)
     __syncthreads();
     for (unsigned long long j = threadIdx.x; j < M; j += blockDim.x) {
         const unsigned long long key = __ldcg(P.cand + j);
-        if (key >= base && key <= bhi) atomicAdd(&sh[(key - base) >> shift], 1u);
+        if (key >= base && key <= bhi) {
+            EQS_CHECK(((key - base) >> shift) < CE_BINS);
+            atomicAdd(&sh[(key - base) >> shift], 1u);
+        }
     }
     __syncthreads();
     for (int b = threadIdx.x; b < CE_BINS; b += blockDim.x) P.hsend[b] = (unsigned long long)sh[b];
@@ -423,6 +426,7 @@ __global__ void __launch_bounds__(CE_SEL_BLOCK) ce_level_kernel(const CeDev P, i
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
+            EQS_CHECK(!in[q] || ((key[q] - base) >> shift) < CE_BINS);
             if (in[q]) atomicAdd(&sh[(key[q] - base) >> shift], 1u);
             if (compact) { // one atomic per warp; the order of the list does not matter
                 const unsigned m = __ballot_sync(0xffffffffu, in[q]);
@@ -431,6 +435,7 @@ __global__ void __launch_bounds__(CE_SEL_BLOCK) ce_level_kernel(const CeDev P, i
                     unsigned long long at = 0ULL;
                     if (lane == leader) at = atomicAdd(&c->n_cand, (unsigned long long)__popc(m));
                     at = __shfl_sync(0xffffffffu, at, leader);
+                    EQS_CHECK(at + __popc(m) <= (unsigned long long)P.ld);
                     if (in[q]) P.cand[at + __popc(m & ((1u << lane) - 1u))] = key[q];
                 }
             }
@@ -577,7 +582,10 @@ __global__ void __launch_bounds__(CE_BLOCK) ce_compact_kernel(const CeDev P)
     long long pos = P.blk_el_off[blockIdx.x] + block_exclusive_scan(__popc(el), 0, OpAddI(), s_a, dummy);
 #pragma unroll
     for (int q = 0; q < CE_PER_THREAD; ++q)
-        if ((el >> q) & 1u) P.elite_idx[pos++] = base + q;
+        if ((el >> q) & 1u) {
+            EQS_CHECK(pos >= 0 && pos < P.kcap && base + q < P.nloc);
+            P.elite_idx[pos++] = base + q;
+        }
 }
 
 // regenerate the elites from their counters into Ex[d][j] (the N x n sample matrix never existed)
@@ -593,6 +601,7 @@ template <bool REPLAY> __global__ void __launch_bounds__(CE_GEN_BLOCK) ce_elite_
     const long long ne = c->n_elite_local;
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < ne; j += (long long)gridDim.x * blockDim.x) {
         const long long li = P.elite_idx[j];
+        EQS_CHECK(li >= 0 && li < P.nloc && j < P.kld);
         ce_sample_coords<REPLAY>(P, t, P.first + li, smu, ssig, [&](double x, int d) { P.Ex[(long long)d * P.kld + j] = x; });
     }
 }

@@ -203,6 +203,17 @@ long long comm_p2p_timeout_ns();
 constexpr size_t kSmemOptIn = 32 * 1024;
 
 // ---- device helpers ------------------------------------------------------------------------------------
+// Index checks of our own (compute-sanitizer is closed on the B200 pool, profiles/r02_sanitizer.md): a build with
+// -DEQS_BOUNDS_CHECK (benchmarks/build_variant.py bounds -DEQS_BOUNDS_CHECK) asserts every computed offset of the
+// population, cost, candidate, elite and histogram accesses against the extent of its buffer; a violation traps the
+// kernel, which the next API call reports as ExternalError.  The default build compiles the checks away.
+#ifdef EQS_BOUNDS_CHECK
+#include <cassert>
+#define EQS_CHECK(cond) assert(cond)
+#else
+#define EQS_CHECK(cond) ((void)0)
+#endif
+
 // system-scope flag accesses of the mailbox protocol
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
 {

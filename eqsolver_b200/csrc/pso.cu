@@ -79,7 +79,11 @@ __device__ __forceinline__ void st256(double *p, const D4 &v)
                  : "memory");
 }
 
-__device__ __forceinline__ long long goff(const PsoDev &P, int q, long long li) { return ((long long)q * P.ld + li) * 4; }
+__device__ __forceinline__ long long goff(const PsoDev &P, int q, long long li)
+{
+    EQS_CHECK(q >= 0 && q < ((P.n + 3) >> 2) && li >= 0 && li < P.ld);
+    return ((long long)q * P.ld + li) * 4;
+}
 
 // ---- draws: (rp, rg) of particle_swarm.rs:407-408 ------------------------------------------------------------
 template <bool REPLAY>

@@ -8,6 +8,7 @@
 //   CrossEntropy(objective).with_*(..).solve(x0)     ~ cross_entropy.rs:75-85, 108-223, 245-306
 // The closure `f` is an Objective ID (device functors are compiled ahead of time).  Link with -leqsolver_b200.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <memory>
@@ -103,6 +104,39 @@ public:
         seed_ = seed;
         return solve(x0, report);
     }
+    // solve on caller-supplied draws instead of a generator (the replay mode of the parity tests as a feature; the
+    // closest thing the reference has is integrate_with_rng, integrators/mod.rs:56-61).  init_draws [N][2][n]: u in
+    // [0, 1) for the start positions, then the velocities (the samplers of particle_swarm.rs:367,373 scale them);
+    // step_draws [passes][N][n][2]: (r_p, r_g) of :407-408.  Runs min(passes, iter_max) passes, fewer when the stall
+    // test (:433-441) fires.
+    SolverResult<Vector> solve_with_draws(const Vector &x0, const Vector &init_draws, const Vector &step_draws) const
+    {
+        const size_t n = lower_.size(), N = static_cast<size_t>(particle_count_);
+        if (x0.size() != n) return SolverError{SolverError::IncorrectInput, "x0 and bounds differ in length"};
+        if (init_draws.size() != N * 2 * n) return SolverError{SolverError::IncorrectInput, "init_draws must hold particle_count * 2n draws"};
+        const size_t per_pass = N * n * 2;
+        if (per_pass == 0 || step_draws.size() % per_pass) return SolverError{SolverError::IncorrectInput, "step_draws must hold whole passes of particle_count * n * 2 draws"};
+        std::shared_ptr<Context> ctx = ctx_;
+        if (!ctx) {
+            auto made = Context::create(0);
+            if (!made.is_ok()) return made.unwrap_err();
+            ctx = made.unwrap();
+        }
+        eqs_pso_params p = params();
+        p.replay_init = init_draws.data();
+        eqs_pso *h = nullptr;
+        int st = eqs_pso_create(ctx->raw(), &p, &h);
+        if (st != EQS_OK) return ctx->error(st);
+        Vector out(n);
+        st = eqs_pso_init(h, x0.data());
+        const int64_t passes = std::min<int64_t>(static_cast<int64_t>(step_draws.size() / per_pass), iter_max_);
+        for (int64_t t = 0; st == EQS_OK && t < passes; ++t) st = eqs_pso_step(h, 1, step_draws.data() + t * per_pass);
+        if (st == EQS_OK) st = eqs_pso_read_gbest(h, out.data(), nullptr, nullptr, nullptr, nullptr);
+        const SolverError err = st == EQS_OK ? SolverError{} : ctx->error(st);
+        eqs_pso_destroy(h);
+        if (st != EQS_OK) return err;
+        return out;
+    }
     // solve(x0), particle_swarm.rs:356-431: the global best position
     SolverResult<Vector> solve(const Vector &x0, eqs_report *report = nullptr) const
     {
@@ -168,6 +202,33 @@ public:
         seed_ = seed;
         return solve(x0, report);
     }
+    // solve on caller-supplied standard normals `normals` [passes][N][n] (the z of Normal::sample, cross_entropy.rs:270):
+    // runs min(passes, iter_max - 1) passes (`iter` starts at 1, :253) or stops when max |sigma| <= tol
+    SolverResult<Vector> solve_with_draws(const Vector &x0, const Vector &normals) const
+    {
+        if (!std_dev_.empty() && std_dev_.size() != x0.size())
+            return SolverError{SolverError::IncorrectInput, "std_dev and x0 differ in length"};
+        const size_t per_pass = static_cast<size_t>(sample_size_) * x0.size();
+        if (per_pass == 0 || normals.size() % per_pass) return SolverError{SolverError::IncorrectInput, "normals must hold whole passes of sample_size * n draws"};
+        std::shared_ptr<Context> ctx = ctx_;
+        if (!ctx) {
+            auto made = Context::create(0);
+            if (!made.is_ok()) return made.unwrap_err();
+            ctx = made.unwrap();
+        }
+        const eqs_ce_params p = params(x0.size());
+        eqs_ce *h = nullptr;
+        int st = eqs_ce_create(ctx->raw(), &p, x0.data(), &h);
+        if (st != EQS_OK) return ctx->error(st);
+        Vector out(x0.size());
+        const int64_t passes = std::min<int64_t>(static_cast<int64_t>(normals.size() / per_pass), std::max<int64_t>(iter_max_ - 1, 0));
+        for (int64_t t = 0; st == EQS_OK && t < passes; ++t) st = eqs_ce_step(h, 1, normals.data() + t * per_pass);
+        if (st == EQS_OK) st = eqs_ce_read_state(h, out.data(), nullptr, nullptr, nullptr);
+        const SolverError err = st == EQS_OK ? SolverError{} : ctx->error(st);
+        eqs_ce_destroy(h);
+        if (st != EQS_OK) return err;
+        return out;
+    }
     // solve(x0), cross_entropy.rs:245-306: the final mean; the reference's panics become NotANumber
     SolverResult<Vector> solve(const Vector &x0, eqs_report *report = nullptr) const
     {
@@ -179,8 +240,18 @@ public:
             if (!made.is_ok()) return made.unwrap_err();
             ctx = made.unwrap();
         }
+        const eqs_ce_params p = params(x0.size());
+        Vector out(x0.size());
+        const int st = eqs_ce_solve(ctx->raw(), &p, x0.data(), out.data(), report);
+        if (st != EQS_OK) return ctx->error(st);
+        return out;
+    }
+
+private:
+    eqs_ce_params params(size_t n) const
+    {
         eqs_ce_params p{};
-        p.n = static_cast<int32_t>(x0.size());
+        p.n = static_cast<int32_t>(n);
         p.objective_id = static_cast<int32_t>(objective_);
         p.mean_divisor = static_cast<int32_t>(divisor_);
         p.exchange = EQS_EXCHANGE_AUTO;
@@ -191,13 +262,8 @@ public:
         p.std_dev = std_dev_.empty() ? nullptr : std_dev_.data();
         p.seed = seed_;
         p.virtual_world = 1;
-        Vector out(x0.size());
-        const int st = eqs_ce_solve(ctx->raw(), &p, x0.data(), out.data(), report);
-        if (st != EQS_OK) return ctx->error(st);
-        return out;
+        return p;
     }
-
-private:
     Objective objective_;
     Vector std_dev_;
     double tol_ = DEFAULT_TOL;

@@ -144,6 +144,44 @@ where
         self.solve(x0)
     }
 
+    /// `solve` on caller-supplied draws instead of a generator (the replay mode of the parity tests as a feature).
+    /// `init_draws` `[N][2][n]`: u in [0, 1) for the start positions, then the velocities, which the samplers of
+    /// `particle_swarm.rs:367,373` scale into their ranges; `step_draws` `[passes][N][n][2]`: (r_p, r_g) of `:407-408`.
+    /// Runs `min(passes, iter_max)` passes, fewer when the stall test (`:433-441`) fires.
+    pub fn solve_with_draws(&self, x0: VectorType<D>, init_draws: &[f64], step_draws: &[f64]) -> SolverResult<VectorType<D>> {
+        let n = self.lower_bounds.len();
+        let per_pass = self.particle_count * n * 2;
+        if x0.len() != n || init_draws.len() != per_pass || per_pass == 0 || step_draws.len() % per_pass != 0 {
+            return Err(SolverError::IncorrectInput { details: "init_draws: particle_count * 2n draws; step_draws: whole passes of particle_count * n * 2 draws" });
+        }
+        let ctx = match &self.context {
+            Some(c) => c.clone(),
+            None => Context::new(0)?,
+        };
+        let mut p = self.params();
+        p.replay_init = init_draws.as_ptr();
+        let mut h: *mut sys::eqs_pso = ptr::null_mut();
+        ctx.check(unsafe { sys::eqs_pso_create(ctx.0 .0, &p, &mut h) })?;
+        let mut out = x0.clone();
+        let mut st = unsafe { sys::eqs_pso_init(h, x0.as_ptr()) };
+        let passes = (step_draws.len() / per_pass).min(self.iter_max);
+        for t in 0..passes {
+            if st != sys::EQS_OK {
+                break;
+            }
+            st = unsafe { sys::eqs_pso_step(h, 1, step_draws[t * per_pass..].as_ptr()) };
+        }
+        if st == sys::EQS_OK {
+            st = unsafe {
+                sys::eqs_pso_read_gbest(h, out.as_mut_ptr(), ptr::null_mut(), ptr::null_mut(), ptr::null_mut(), ptr::null_mut())
+            };
+        }
+        let res = ctx.check(st); // reads the message before the handle goes away
+        unsafe { sys::eqs_pso_destroy(h) };
+        res?;
+        Ok(out)
+    }
+
     /// `solve(x0)`, `particle_swarm.rs:356-431`: the global best position.
     pub fn solve(&self, x0: VectorType<D>) -> SolverResult<VectorType<D>> {
         let ctx = match &self.context {
@@ -231,20 +269,46 @@ where
         self.solve(x0)
     }
 
-    /// `solve(x0)`, `cross_entropy.rs:245-306`: the final mean.  Where the reference panics (NaN cost, non-finite
-    /// standard deviation) this returns `Err(SolverError::NotANumber)`.
-    pub fn solve(&self, x0: VectorType<D>) -> SolverResult<VectorType<D>> {
+    /// `solve` on caller-supplied standard normals `normals` `[passes][N][n]` (the z of `Normal::sample`,
+    /// `cross_entropy.rs:270`): runs `min(passes, iter_max - 1)` passes (`iter` starts at 1, `:253`) or stops on `tol`.
+    pub fn solve_with_draws(&self, x0: VectorType<D>, normals: &[f64]) -> SolverResult<VectorType<D>> {
+        let per_pass = self.sample_size * x0.len();
+        if per_pass == 0 || normals.len() % per_pass != 0 {
+            return Err(SolverError::IncorrectInput { details: "normals must hold whole passes of sample_size * n draws" });
+        }
         let ctx = match &self.context {
             Some(c) => c.clone(),
             None => Context::new(0)?,
         };
+        let p = self.params(x0.len())?;
+        let mut h: *mut sys::eqs_ce = ptr::null_mut();
+        ctx.check(unsafe { sys::eqs_ce_create(ctx.0 .0, &p, x0.as_ptr(), &mut h) })?;
+        let mut out = x0.clone();
+        let mut st = sys::EQS_OK;
+        let passes = (normals.len() / per_pass).min(self.iter_max.saturating_sub(1));
+        for t in 0..passes {
+            if st != sys::EQS_OK {
+                break;
+            }
+            st = unsafe { sys::eqs_ce_step(h, 1, normals[t * per_pass..].as_ptr()) };
+        }
+        if st == sys::EQS_OK {
+            st = unsafe { sys::eqs_ce_read_state(h, out.as_mut_ptr(), ptr::null_mut(), ptr::null_mut(), ptr::null_mut()) };
+        }
+        let res = ctx.check(st);
+        unsafe { sys::eqs_ce_destroy(h) };
+        res?;
+        Ok(out)
+    }
+
+    fn params(&self, n: usize) -> SolverResult<sys::eqs_ce_params> {
         if let Some(s) = &self.std_dev {
-            if s.len() != x0.len() {
+            if s.len() != n {
                 return Err(SolverError::IncorrectInput { details: "std_dev and x0 differ in length" });
             }
         }
-        let p = sys::eqs_ce_params {
-            n: x0.len() as i32,
+        Ok(sys::eqs_ce_params {
+            n: n as i32,
             objective_id: self.objective as i32,
             mean_divisor: self.mean_divisor as i32,
             exchange: sys::EQS_EXCHANGE_AUTO,
@@ -256,7 +320,17 @@ where
             seed: self.seed,
             virtual_rank: 0,
             virtual_world: 1,
+        })
+    }
+
+    /// `solve(x0)`, `cross_entropy.rs:245-306`: the final mean.  Where the reference panics (NaN cost, sampling with
+    /// a non-finite standard deviation) this returns `Err(SolverError::NotANumber)`.
+    pub fn solve(&self, x0: VectorType<D>) -> SolverResult<VectorType<D>> {
+        let ctx = match &self.context {
+            Some(c) => c.clone(),
+            None => Context::new(0)?,
         };
+        let p = self.params(x0.len())?;
         let mut out = x0.clone();
         let mut report = sys::eqs_report::default();
         let st = unsafe { sys::eqs_ce_solve(ctx.0 .0, &p, x0.as_ptr(), out.as_mut_ptr(), &mut report) };

@@ -79,6 +79,39 @@ static int gpu_tests()
         auto bad = MonteCarlo(Objective::Gaussian).with_context(ctx).integrate({1.0}, {0.0});
         CHECK(!bad.is_ok() && bad.unwrap_err().kind == SolverError::ExternalError);
     }
+    // solve_with_draws: the same draws give the same answer, other draws another; a transparent case checked by hand:
+    // every step draw 0 leaves v = w v, so with w = 0 the particles stand still and gbest is the best start position
+    {
+        const int n = 3;
+        const int64_t N = 64, passes = 4;
+        Vector init(N * 2 * n), steps(passes * N * n * 2, 0.0);
+        for (size_t i = 0; i < init.size(); ++i) init[i] = std::fmod(0.6180339887 * (double)(i + 1), 1.0);
+        auto ps = ParticleSwarm::create(Objective::Sphere, Vector(n, -1.0), Vector(n, 1.0)).unwrap();
+        ps.with_context(ctx).with_particle_count(N).with_iter_max(passes).with_tol(0.0).with_inertia_weight(0.0);
+        auto a = ps.solve_with_draws(Vector(n, 0.9), init, steps), b = ps.solve_with_draws(Vector(n, 0.9), init, steps);
+        CHECK(a.is_ok() && b.is_ok() && a.unwrap() == b.unwrap());
+        double best = 1e300;
+        Vector arg(n);
+        for (int64_t i = 0; i < N; ++i) { // the particles after the first pass: x0 + v0 (w = 0 keeps them there)
+            double c = 0.0;
+            Vector x(n);
+            for (int d = 0; d < n; ++d) {
+                const double pos = init[i * 2 * n + d] * 2.0 + -1.0, vel = init[i * 2 * n + n + d] * 4.0 + -2.0;
+                (void)vel;
+                x[d] = pos;
+                c += pos * pos;
+            }
+            if (c < best) { best = c; arg = x; }
+        }
+        CHECK(a.unwrap() == arg);
+        auto bad = ps.solve_with_draws(Vector(n, 0.9), Vector(5, 0.0), steps);
+        CHECK(!bad.is_ok() && bad.unwrap_err().kind == SolverError::IncorrectInput);
+        // CrossEntropy: normals all zero -> every sample is the mean, sigma collapses to 0 and the loop ends
+        Vector z(2 * 50 * n, 0.0);
+        auto ce = CrossEntropy(Objective::Sphere).with_context(ctx).with_sample_size(50).with_importance_selection_size(5)
+                      .with_std_dev(Vector(n, 1.0)).with_mean_divisor(MeanDivisor::EliteCount).solve_with_draws(Vector(n, 0.25), z);
+        CHECK(ce.is_ok() && ce.unwrap() == Vector(n, 0.25));
+    }
     std::printf("gpu tests ok\n");
     return 0;
 }
