@@ -30,8 +30,10 @@ void boundary_exception_clear() noexcept;
 // ---- exchange record (doubles) --------------------------------------------------------------------------
 // One record per rank and exchange: the only data that ever crosses NVLink for ParticleSwarm.
 //   [0] cost   [1] global particle index (as f64, exact below 2^53; -1 = none)   [2] ring pushes of the
-//   init scan   [3] pad   [4..54) last <=50 pushed values in order   [54..54+n) the particle's position
-constexpr int REC_COST = 0, REC_IDX = 1, REC_PUSHES = 2, REC_RING = 4, REC_X = REC_RING + EQS_STALL_WINDOW;
+//   init scan   [3] pad   [4..54) last <=50 pushed values in order   [54..104) the global indices of the particles
+//   that pushed them (the ranks' pushes are merged by position)   [104..104+n) the particle's position
+constexpr int REC_COST = 0, REC_IDX = 1, REC_PUSHES = 2, REC_RING = 4, REC_RPOS = REC_RING + EQS_STALL_WINDOW,
+              REC_X = REC_RPOS + EQS_STALL_WINDOW;
 __host__ __device__ inline int64_t record_doubles(int n) { return (int64_t)REC_X + n; }
 
 // ---- context -------------------------------------------------------------------------------------------

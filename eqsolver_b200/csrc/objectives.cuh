@@ -33,6 +33,11 @@ template <int M> __device__ __forceinline__ void obj_cos_vec(const double (&y)[M
 {
     eqs_cos_vec<(EQS_COS_TABLE != 0), M>(y, out);
 }
+// the range test deferred to the end of the particle (devmath.cuh: DEFER)
+template <int M> __device__ __forceinline__ void obj_cos_vec_defer(const double (&y)[M], double (&out)[M], unsigned &hi_max)
+{
+    eqs_cos_vec<(EQS_COS_TABLE != 0), M, true>(y, out, &hi_max);
+}
 
 struct ObjAcc {
     double a, b, p;
@@ -92,6 +97,16 @@ template <> struct Objective<EQS_OBJ_RASTRIGIN> {
 #pragma unroll
         for (int j = 0; j < M; ++j) s.a += x[j] * x[j] - 10.0 * c[j];
     }
+    // same, the cosine's range test deferred (hi_max: devmath.cuh, eqs_cos_vec DEFER)
+    template <int M> __device__ __forceinline__ static void feed_vec_defer(ObjAcc &s, const double (&x)[M], int, unsigned &hi_max)
+    {
+        double y[M], c[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) y[j] = kTwoPi * x[j];
+        obj_cos_vec_defer<M>(y, c, hi_max);
+#pragma unroll
+        for (int j = 0; j < M; ++j) s.a += x[j] * x[j] - 10.0 * c[j];
+    }
     __device__ __forceinline__ static double end(const ObjAcc &s, int) { return s.a; }
 };
 
@@ -109,6 +124,18 @@ template <> struct Objective<EQS_OBJ_ACKLEY> {
 #pragma unroll
         for (int j = 0; j < M; ++j) y[j] = kTwoPi * x[j];
         obj_cos_vec<M>(y, c);
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            s.a += x[j] * x[j];
+            s.b += c[j];
+        }
+    }
+    template <int M> __device__ __forceinline__ static void feed_vec_defer(ObjAcc &s, const double (&x)[M], int, unsigned &hi_max)
+    {
+        double y[M], c[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) y[j] = kTwoPi * x[j];
+        obj_cos_vec_defer<M>(y, c, hi_max);
 #pragma unroll
         for (int j = 0; j < M; ++j) {
             s.a += x[j] * x[j];
@@ -256,6 +283,19 @@ template <class Obj, int M> __device__ __forceinline__ void objective_feed_vec(O
     } else {
 #pragma unroll
         for (int j = 0; j < M; ++j) Obj::feed(acc, x[j], d0 + j);
+    }
+}
+
+// The same for callers that can evaluate a particle a second time: functors with a feed_vec_defer skip their per-call
+// range tests and report through hi_max instead (test it against kCosHiLimit after the last coordinate; if it fired, the
+// accumulated value is meaningless and objective_on() below gives the right one).
+template <class Obj, int M>
+__device__ __forceinline__ void objective_feed_vec_defer(ObjAcc &acc, const double (&x)[M], int d0, unsigned &hi_max)
+{
+    if constexpr (requires(ObjAcc &a, unsigned &h) { Obj::template feed_vec_defer<M>(a, x, d0, h); }) {
+        Obj::template feed_vec_defer<M>(acc, x, d0, hi_max);
+    } else {
+        objective_feed_vec<Obj, M>(acc, x, d0);
     }
 }
 

@@ -29,6 +29,9 @@
 #include <cstdlib>
 #include <cstring>
 
+#ifdef EQS_PSO_COS_TABLE // tuning sweeps: where the step kernels' cosine takes its coefficients from (devmath.cuh)
+#define EQS_COS_TABLE EQS_PSO_COS_TABLE
+#endif
 #include "objectives.cuh"
 #include "pso.cuh"
 
@@ -49,6 +52,15 @@ namespace {
 #endif
 #ifndef EQS_PSO_MINB
 #define EQS_PSO_MINB 2
+#endif
+// 1: the objective takes the 4 * UQ coordinates of a load batch at once, after the batch's stores, instead of 4 at a time
+// between them (measured on one box, profiles/r02_sweep.md section 3: C2 0.866 -> 0.892, C4 0.875 -> 0.881 of measured HBM)
+#ifndef EQS_PSO_FEED_BATCH
+#define EQS_PSO_FEED_BATCH 1
+#endif
+// 1: the cosine objectives test their argument range once per particle instead of once per 4 coordinates (devmath.cuh)
+#ifndef EQS_PSO_COS_DEFER
+#define EQS_PSO_COS_DEFER 1
 #endif
 
 constexpr long long kNoIndex = 0x7fffffffffffffffLL;
@@ -123,9 +135,9 @@ __device__ __forceinline__ void ring_push(PsoCtrl *c, double v)
 }
 
 // one 4-dimension group already in registers: draws, update, objective; `dims` = live dimensions in the group
-template <class Obj, bool REPLAY, bool FULL>
+template <class Obj, bool REPLAY, bool FULL, bool FEED = true>
 __device__ __forceinline__ void pso_group_math(const PsoDev &P, uint32_t t, long long gi, int q, const double *sG, ObjAcc &acc,
-                                               D4 &x, D4 &v, const D4 &pb, int dims)
+                                               D4 &x, D4 &v, const D4 &pb, int dims, unsigned &hi_max)
 {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -137,14 +149,17 @@ __device__ __forceinline__ void pso_group_math(const PsoDev &P, uint32_t t, long
             if constexpr (Obj::streaming && !FULL) Obj::feed(acc, x.e[j], d);
         }
     }
-    if constexpr (Obj::streaming && FULL) objective_feed_vec<Obj, 4>(acc, x.e, 4 * q); // the group's 4 coordinates at once
+    if constexpr (Obj::streaming && FULL && FEED) { // the group's 4 coordinates at once
+        if constexpr (EQS_PSO_COS_DEFER) objective_feed_vec_defer<Obj, 4>(acc, x.e, 4 * q, hi_max);
+        else objective_feed_vec<Obj, 4>(acc, x.e, 4 * q);
+    }
 }
 
 // K consecutive groups of one particle: all loads first (3K independent 32-byte requests), then math, then stores
 template <class Obj, bool REPLAY, int K>
 __device__ __forceinline__ void pso_groups(const PsoDev &P, uint32_t t, long long li, int q, const double *sG, ObjAcc &acc,
                                            const double *xin, const double *vin, const double *pbin, double *xout,
-                                           double *vout, bool load_pb)
+                                           double *vout, bool load_pb, unsigned &hi_max)
 {
     D4 xs[K], vs[K], ps[K];
 #pragma unroll
@@ -158,12 +173,22 @@ __device__ __forceinline__ void pso_groups(const PsoDev &P, uint32_t t, long lon
 #pragma unroll
         for (int k = 0; k < K; ++k) ps[k] = xs[k];
     }
+    constexpr bool batch_feed = EQS_PSO_FEED_BATCH && Obj::streaming && K > 1;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        pso_group_math<Obj, REPLAY, true>(P, t, P.first + li, q + k, sG, acc, xs[k], vs[k], ps[k], 4);
+        pso_group_math<Obj, REPLAY, true, !batch_feed>(P, t, pso_gidx(P, li), q + k, sG, acc, xs[k], vs[k], ps[k], 4, hi_max);
         const long long off = goff(P, q + k, li);
         st256(xout + off, xs[k]);
         st256(vout + off, vs[k]);
+    }
+    if constexpr (batch_feed) { // all 4 K coordinates of the batch in lock step: a coefficient is materialised once per 4 K uses
+        double xx[4 * K];
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xx[4 * k + j] = xs[k].e[j];
+        if constexpr (EQS_PSO_COS_DEFER) objective_feed_vec_defer<Obj, 4 * K>(acc, xx, 4 * q, hi_max);
+        else objective_feed_vec<Obj, 4 * K>(acc, xx, 4 * q);
     }
 }
 
@@ -174,21 +199,30 @@ __device__ __forceinline__ double pso_move(const PsoDev &P, uint32_t t, long lon
 {
     const int n = P.n, nfull = n >> 2, rem = n & 3;
     ObjAcc acc;
+    unsigned hi_max = 0;
     if constexpr (Obj::streaming) Obj::begin(acc, n);
     constexpr int UQ = EQS_PSO_UQ;
     int q = 0;
-    for (; q + UQ <= nfull; q += UQ) pso_groups<Obj, REPLAY, UQ>(P, t, li, q, sG, acc, xin, vin, pbin, xout, vout, load_pb);
-    for (; q < nfull; ++q) pso_groups<Obj, REPLAY, 1>(P, t, li, q, sG, acc, xin, vin, pbin, xout, vout, load_pb);
+    for (; q + UQ <= nfull; q += UQ) {
+        pso_groups<Obj, REPLAY, UQ>(P, t, li, q, sG, acc, xin, vin, pbin, xout, vout, load_pb, hi_max);
+    }
+    for (; q < nfull; ++q) pso_groups<Obj, REPLAY, 1>(P, t, li, q, sG, acc, xin, vin, pbin, xout, vout, load_pb, hi_max);
     if (rem) { // ragged last group: the padding dimensions are carried through unchanged
         const long long off = goff(P, q, li);
         D4 x = ld256(xin + off), v = ld256(vin + off), pb = x;
         if (load_pb) pb = ld256(pbin + off);
-        pso_group_math<Obj, REPLAY, false>(P, t, P.first + li, q, sG, acc, x, v, pb, rem);
+        pso_group_math<Obj, REPLAY, false>(P, t, pso_gidx(P, li), q, sG, acc, x, v, pb, rem, hi_max);
         st256(xout + off, x);
         st256(vout + off, v);
     }
-    if constexpr (Obj::streaming) return Obj::end(acc, n);
-    else return Obj::eval(GroupedView{xout + li * 4, P.ld * 4}, n);
+    if constexpr (Obj::streaming) {
+        // a deferred range test fired (never on sane inputs): the sums hold garbage, evaluate the stored position again
+        // through the scalar path, whose cosine handles every argument
+        if (EQS_PSO_COS_DEFER && hi_max >= kCosHiLimit) return objective_on<Obj>(GroupedView{xout + li * 4, P.ld * 4}, n);
+        return Obj::end(acc, n);
+    } else {
+        return Obj::eval(GroupedView{xout + li * 4, P.ld * 4}, n);
+    }
 }
 
 // end of a particle's pass in synchronous mode: pbest cost + flag byte (:417-419), running arg-min
@@ -203,7 +237,7 @@ __device__ __forceinline__ void pso_finish_particle(const PsoDev &P, long long l
     const double cs = sanitize_cost(c);
     if (cs < best.c) {
         best.c = cs;
-        best.i = P.first + li;
+        best.i = pso_gidx(P, li);
     }
 }
 
@@ -243,7 +277,7 @@ template <bool CG = true>
 __device__ __forceinline__ void write_record(const PsoDev &P, double cost, long long gidx, const double *src)
 {
     const bool none = gidx == kNoIndex || gidx < 0;
-    const long long li = none ? 0 : gidx - P.first;
+    const long long li = none ? 0 : pso_lidx(P, gidx);
     if (!src && !none) src = ((CG ? __ldcg(P.pbflag + li) : P.pbflag[li]) & 2u) ? P.pb : P.x;
     if (threadIdx.x == 0) {
         P.send[REC_COST] = cost;
@@ -362,7 +396,7 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(PSO_BLOCK) p
         const long long li = g * PSO_GROUP + threadIdx.x;
         double c = dinf();
         if (li < P.nloc) {
-            const long long gi = P.first + li;
+            const long long gi = pso_gidx(P, li);
             ObjAcc acc;
             if constexpr (Obj::streaming) Obj::begin(acc, n);
             for (int q = 0; q < nq; ++q) {
@@ -416,33 +450,44 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(PSO_BLOCK) p
 // The reference updates gbest INSIDE the init loop (:376-380), pushing the old gbest cost on the stall ring at
 // every record low, in particle order.  Which positions are record lows is an exclusive prefix-min problem:
 // particle i pushes e_i = min(seed, c_0..c_{i-1}) iff c_i < e_i.  One CTA walks the per-tile minima (1024 tiles
-// per scan), then only the tiles that contain a record low (O(log N) of them for random costs).  Output: number
-// of pushes and the last <= 50 pushed values in order, appended to this rank's record.
+// per scan), then only the tiles that contain a record low (O(log N) of them for random costs).
+// One kernel for both distributions.  Contiguous blocks: the rank walks its own tiles, seeded with f(x0) and the minima
+// of the lower ranks (their records).  Tile-cyclic: the rank walks ALL global tiles in order -- their minima were gathered
+// from every rank (gm_all) -- and opens only the flagged tiles it owns.  Either way it reports how many pushes its own
+// particles made and the last <= 50 of them with the pushing particle's global index; pso_init_apply_kernel merges the
+// ranks' lists by that position.
 __global__ void __launch_bounds__(1024) pso_ring_scan_kernel(const PsoDev P)
 {
     __shared__ double s_scan_d[33];
     __shared__ int s_scan_i[33];
     __shared__ long long s_list[1024];
     __shared__ double s_seedlist[1024];
-    __shared__ double s_ring[EQS_STALL_WINDOW];
+    __shared__ double s_ring[EQS_STALL_WINDOW], s_rpos[EQS_STALL_WINDOW];
     __shared__ double s_seed;
     const int tid = threadIdx.x;
     const long long R = record_doubles(P.n);
     if (tid == 0) {
         double seed = P.ctrl->Gc; // f(x0), :358
-        for (int r = 0; r < P.rank; ++r) { // particles of lower ranks come first in the reference's order
-            const double *rec = P.recv + r * R;
-            if (rec[REC_IDX] >= 0.0 && rec[REC_COST] < seed) seed = rec[REC_COST];
-        }
+        if (!P.cyclic)
+            for (int r = 0; r < P.rank; ++r) { // particles of lower ranks come first in the reference's order
+                const double *rec = P.recv + r * R;
+                if (rec[REC_IDX] >= 0.0 && rec[REC_COST] < seed) seed = rec[REC_COST];
+            }
         s_seed = seed;
     }
-    if (tid < EQS_STALL_WINDOW) s_ring[tid] = dinf();
+    if (tid < EQS_STALL_WINDOW) {
+        s_ring[tid] = dinf();
+        s_rpos[tid] = -1.0;
+    }
     __syncthreads();
     double running = s_seed;
     long long count = 0;
-    const long long ngroups = (P.nloc + PSO_GROUP - 1) / PSO_GROUP;
-    for (long long g0 = 0; g0 < ngroups; g0 += 1024) {
-        const double gm = (g0 + tid < ngroups) ? P.group_min[g0 + tid] : dinf();
+    // tiles in the reference's order: this rank's own (contiguous) or every rank's (cyclic)
+    const long long ntiles = P.cyclic ? (P.ntotal + PSO_GROUP - 1) / PSO_GROUP : (P.nloc + PSO_GROUP - 1) / PSO_GROUP;
+    for (long long g0 = 0; g0 < ntiles; g0 += 1024) {
+        const long long T = g0 + tid;
+        double gm = dinf();
+        if (T < ntiles) gm = P.cyclic ? P.gm_all[(T % P.world) * P.tiles_per_rank + T / P.world] : P.group_min[T];
         double chunk_min;
         double ex = block_exclusive_scan(gm, dinf(), OpMin(), s_scan_d, chunk_min);
         ex = ex < running ? ex : running;
@@ -450,12 +495,14 @@ __global__ void __launch_bounds__(1024) pso_ring_scan_kernel(const PsoDev P)
         int nflag;
         const int pos = block_exclusive_scan(flagged, 0, OpAddI(), s_scan_i, nflag);
         if (flagged) {
-            s_list[pos] = g0 + tid;
+            s_list[pos] = T;
             s_seedlist[pos] = ex;
         }
         __syncthreads();
         for (int q = 0; q < nflag; ++q) {
-            const long long li = s_list[q] * PSO_GROUP + tid;
+            const long long Tq = s_list[q];
+            if (P.cyclic && Tq % P.world != P.rank) continue; // another rank's particles (uniform over the block)
+            const long long li = (P.cyclic ? Tq / P.world : Tq) * PSO_GROUP + tid;
             const double gseed = s_seedlist[q];
             const double c = (tid < PSO_GROUP && li < P.nloc) ? sanitize_cost(P.cost[li]) : dinf();
             double dummy;
@@ -464,15 +511,20 @@ __global__ void __launch_bounds__(1024) pso_ring_scan_kernel(const PsoDev P)
             const int rec = c < e;
             int tot;
             const long long rk = count + block_exclusive_scan(rec, 0, OpAddI(), s_scan_i, tot);
-            if (rec && rk >= count + tot - EQS_STALL_WINDOW) s_ring[rk % EQS_STALL_WINDOW] = e;
+            if (rec && rk >= count + tot - EQS_STALL_WINDOW) {
+                s_ring[rk % EQS_STALL_WINDOW] = e;
+                s_rpos[rk % EQS_STALL_WINDOW] = (double)pso_gidx(P, li);
+            }
             count += tot;
             __syncthreads();
         }
         running = chunk_min < running ? chunk_min : running;
     }
+    __syncthreads();
     if (tid < EQS_STALL_WINDOW) {
         const long long kept = count < EQS_STALL_WINDOW ? count : EQS_STALL_WINDOW;
         P.send[REC_RING + tid] = tid < kept ? s_ring[(count - kept + tid) % EQS_STALL_WINDOW] : dinf();
+        P.send[REC_RPOS + tid] = tid < kept ? s_rpos[(count - kept + tid) % EQS_STALL_WINDOW] : -1.0;
     }
     if (tid == 0) P.send[REC_PUSHES] = (double)count;
 }
@@ -488,16 +540,34 @@ __global__ void pso_init_apply_kernel(const PsoDev P)
         const int win = best_record(P.recv, P.world, R, bc);
         const bool improved = win >= 0 && bc < c->Gc;
         if (improved) c->Gc = bc;
-        long long g = 0;
+        // every rank kept its own last <= 50 pushes in position order; the last 50 of ALL pushes are the 50 largest
+        // positions of their union (a push among the global last 50 is among its own rank's last 50), merged from the
+        // back.  Push number p (0-based, global) goes to ring slot p % 50 like CircularArray::push (:24-46).
+        long long total = 0;
+        double *recv = P.recv; // word 3 of every record (padding) counts the entries of that rank still to be merged
         for (int r = 0; r < P.world; ++r) {
-            const double *rec = P.recv + r * R;
-            const long long K = (long long)rec[REC_PUSHES];
-            const long long kept = K < EQS_STALL_WINDOW ? K : EQS_STALL_WINDOW;
-            g += K - kept;
-            for (long long j = 0; j < kept; ++j, ++g) c->ring[g % EQS_STALL_WINDOW] = rec[REC_RING + j];
+            const long long K = (long long)recv[r * R + REC_PUSHES];
+            total += K;
+            recv[r * R + 3] = (double)(K < EQS_STALL_WINDOW ? K : EQS_STALL_WINDOW);
         }
-        c->ring_i = g % EQS_STALL_WINDOW;
-        c->improvements = g;
+        const long long m = total < EQS_STALL_WINDOW ? total : EQS_STALL_WINDOW;
+        for (long long j = m - 1; j >= 0; --j) {
+            int pick = -1;
+            double ppos = -1.0;
+            for (int r = 0; r < P.world; ++r) {
+                const int left = (int)recv[r * R + 3];
+                if (left > 0 && recv[r * R + REC_RPOS + left - 1] > ppos) {
+                    ppos = recv[r * R + REC_RPOS + left - 1];
+                    pick = r;
+                }
+            }
+            if (pick < 0) break;
+            const int left = (int)recv[pick * R + 3];
+            c->ring[(total - m + j) % EQS_STALL_WINDOW] = recv[pick * R + REC_RING + left - 1];
+            recv[pick * R + 3] = (double)(left - 1);
+        }
+        c->ring_i = total % EQS_STALL_WINDOW;
+        c->improvements = total;
         c->stalled = stall_test(c, P.tol);
         s_winner = improved ? win : -1;
     }
@@ -540,6 +610,9 @@ __global__ void __launch_bounds__(PSO_BLOCK, EQS_PSO_MINB) pso_step_kernel(const
     }
 }
 
+// (Per-thread L2 prefetches -- prefetch.global.L2 / CCTL.E.PF2 of exactly the sectors the thread loads 1, 2 or 4 batches
+// later, next particle included -- were built and measured in round 2 and are much slower: C4 0.81 / 0.72 / 0.62 of measured
+// HBM against 0.88 without, C2 0.81 / 0.71 / 0.62 against 0.88.  profiles/r02_sweep.md section 3.)
 // (A variant of this kernel that streams the population through a two-stage shared-memory ring with per-thread cp.async
 // was built and measured in round 2 -- bit-identical, but slower: 0.64-0.87 of measured HBM on C2 and 0.59-0.67 on C4
 // against 0.88 / 0.82 here, because a 16-byte LDGSTS per lane doubles the L2 sector requests and the ring's LDS / LDGSTS

@@ -49,7 +49,9 @@ struct PsoDev {
     PsoCtrl *ctrl;
     double *part_cost;              // [grid] per-block partial min-loc
     long long *part_idx;
-    double *group_min;              // [ceil(nloc/GROUP)] per-tile minimum of the init costs
+    double *group_min;              // [tiles per rank] per-tile minimum of the init costs
+    double *gm_all;                 // cyclic distribution: every rank's group_min, [world][tiles_per_rank]
+    long long tiles_per_rank;       // cyclic distribution: ceil(ceil(ntotal / GROUP) / world)
     double *send, *recv;            // exchange records: [R], [world][R]
     char *mailbox;                  // peer-memory exchange (common.cuh): this rank's mailbox, or nullptr
     char *const *peers;             // device table of every rank's mailbox as mapped on this GPU
@@ -60,12 +62,40 @@ struct PsoDev {
     long long replay_t0;            // iteration index of replay block 0
     int n, world, rank;
     int sync;                       // synchronous mode: role-swapping buffers, flags in pbflag
+    // Which particles a rank holds.  0: the contiguous block [first, first + nloc) (synchronous mode, single rank).
+    // 1: TILE-CYCLIC -- global tile T (PSO_GROUP consecutive particles) lives on rank T % world as local tile T / world.
+    // Sequential-exact mode over several ranks needs it: the reference's order is the global index order, a window of
+    // that order must keep EVERY rank busy, and with contiguous blocks it would lie inside one rank's block.
+    int cyclic;
     double w, c1, c2, tol;
     PhiloxKey key;
 };
 
 constexpr int PSO_BLOCK = 256;
-constexpr int PSO_GROUP = 256; // particles per init tile = granularity of the ring scan
+constexpr int PSO_GROUP = 256; // particles per init tile = granularity of the ring scan and of the cyclic distribution
+constexpr int PSO_GROUP_LOG2 = 8;
+static_assert((1 << PSO_GROUP_LOG2) == PSO_GROUP, "tile size");
+
+// global index of local particle li / local index of owned global particle g / owned particles with global index < g
+__host__ __device__ inline long long pso_gidx(const PsoDev &P, long long li)
+{
+    return P.cyclic ? ((((li >> PSO_GROUP_LOG2) * P.world + P.rank) << PSO_GROUP_LOG2) | (li & (PSO_GROUP - 1))) : P.first + li;
+}
+__host__ __device__ inline long long pso_lidx(const PsoDev &P, long long g)
+{
+    return P.cyclic ? ((((g >> PSO_GROUP_LOG2) / P.world) << PSO_GROUP_LOG2) | (g & (PSO_GROUP - 1))) : g - P.first;
+}
+__host__ __device__ inline long long pso_lcount(const PsoDev &P, long long g)
+{
+    long long c;
+    if (P.cyclic) {
+        const long long row = (long long)PSO_GROUP * P.world, r = g / row, rem = g % row, t = rem >> PSO_GROUP_LOG2;
+        c = r * PSO_GROUP + (P.rank < t ? PSO_GROUP : (P.rank == t ? (rem & (PSO_GROUP - 1)) : 0));
+    } else {
+        c = g - P.first;
+    }
+    return c < 0 ? 0 : (c > P.nloc ? P.nloc : c);
+}
 constexpr int PSO_SMALL_BLOCK = 512; // K8: threads of the single-CTA whole-solve kernel
 constexpr int PSO_SMALL_MAX = 2048;  // K8: largest population it takes (4 particles per thread)
 
@@ -86,6 +116,7 @@ public:
     int read_gbest(double *g, double *cost, int64_t *iters, int32_t *stalled, int64_t *improvements);
     int read_state(double *x, double *v, double *pb, double *pbc);
     int read_ring(double *ring, int64_t *ring_i);
+    int local_indices(int64_t *gidx);
     int get_record(double *rec);
     int set_records(const double *recs);
     int solve(const double *x0, double *out_x, eqs_report *rep);
@@ -117,6 +148,7 @@ private:
     int exchange();
     int launch_init_eval();
     int launch_ring_scan();
+    int gather_tile_minima();
     int launch_init_apply();
     int launch_step();
     int launch_step_apply();

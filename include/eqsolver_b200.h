@@ -140,7 +140,8 @@ int eqs_ctx_comm_init(eqs_ctx *ctx, int rank, int world, const void *id128);
 int eqs_ctx_rank(const eqs_ctx *ctx, int *rank, int *world);
 /* contiguous index blocks per rank (keeps the reference's particle order); pure host arithmetic */
 int eqs_shard_range(int64_t count, int world, int rank, int64_t *first, int64_t *local);
-/* doubles in one exchange record for dimension n: cost, index, pushes, pad, ring tail[50], x[n] */
+/* doubles in one exchange record for dimension n: cost, index, pushes, pad, ring tail[50], the global indices of the
+ * particles that pushed the tail[50], x[n] */
 int64_t eqs_record_doubles(int32_t n);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */

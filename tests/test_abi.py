@@ -38,7 +38,7 @@ def test_host_only_entry_points():
         covered += l
     assert covered == 1000003
     from eqsolver_b200 import _ffi
-    assert _ffi.lib().eqs_record_doubles(32) == 4 + 50 + 32
+    assert _ffi.lib().eqs_record_doubles(32) == 4 + 50 + 50 + 32
 
 
 def test_new_rejects_bad_bounds_like_the_reference():

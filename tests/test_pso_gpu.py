@@ -146,6 +146,34 @@ def test_philox_parity_per_iteration(ctx, objective, exact, mode):
         compare_state(run, o, exact, f"pass {t}")
 
 
+@pytest.mark.parametrize("objective", [E.Objective.RASTRIGIN, E.Objective.ACKLEY])
+@pytest.mark.parametrize("mode", [E.PsoMode.SYNCHRONOUS, E.PsoMode.SEQUENTIAL_EXACT])
+@pytest.mark.parametrize("n,N", [(8, 3000), (13, 700)])
+def test_cosine_arguments_out_of_range_in_some_particles(ctx, objective, mode, n, N):
+    """The step kernels test the cosine's argument range once per particle (devmath.cuh: DEFER) and evaluate a particle
+    that failed it a second time through the scalar path.  One coordinate with bounds of +-3e5 puts |2 pi x| beyond the
+    polynomial's 8e5 in about half of the particles (and in gbest's neighbourhood); the others never leave the fast path.
+    Both kinds must agree with the oracle's glibc cosine like any other Rastrigin / Ackley run."""
+    lower, upper = [-5.0] * n, [5.0] * n
+    lower[5], upper[5] = -3.0e5, 3.0e5  # in a full 4-coordinate group for n = 8 and n = 13
+    if n == 13:
+        lower[12], upper[12] = -2.0e5, 4.0e5  # and in the ragged last group
+    g = (E.ParticleSwarm.new(objective, lower, upper).with_particle_count(N).with_iter_max(50).with_tol(0.0)
+         .with_seed(99).with_mode(mode))
+    o = O.Pso(int(objective), lower, upper, particle_count=N, iter_max=50, tol=0.0, mode=int(mode), seed=99)
+    x0 = np.full(n, 1.0)
+    run = g.with_context(ctx).start(x0)
+    o.init(x0)
+    compare_state(run, o, False, "init")
+    x = run.state()[0]
+    far = (np.abs(2 * np.pi * x) >= 8.0e5).any(axis=1)
+    assert 0.2 < far.mean() < 0.9  # the population really is a mix of both paths
+    for t in range(5):
+        run.step(1)
+        assert o.step() == 0
+        compare_state(run, o, False, f"pass {t}")
+
+
 @pytest.mark.parametrize("mode", [E.PsoMode.SYNCHRONOUS, E.PsoMode.SEQUENTIAL_EXACT])
 def test_replay_mode_host_draws(ctx, mode):
     """Replay: identical HOST-generated draws (numpy Philox4x64, unrelated to the device generator) fed to both."""
