@@ -88,6 +88,7 @@ SYMBOLS = {
     "eqs_pso_read_state": (C.c_int, [_vp, dp, dp, dp, dp]),
     "eqs_pso_read_ring": (C.c_int, [_vp, dp, i64p]),
     "eqs_pso_local_range": (C.c_int, [_vp, i64p, i64p]),
+    "eqs_pso_local_indices": (C.c_int, [_vp, i64p]),
     "eqs_pso_init_local": (C.c_int, [_vp, dp, C.c_int32]),
     "eqs_pso_init_apply": (C.c_int, [_vp]),
     "eqs_pso_step_local": (C.c_int, [_vp, dp]),

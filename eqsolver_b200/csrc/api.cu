@@ -569,6 +569,15 @@ int eqs_pso_local_range(eqs_pso *h, int64_t *first, int64_t *local)
     EQS_BOUNDARY_CATCH
 }
 
+int eqs_pso_local_indices(eqs_pso *h, int64_t *gidx)
+{
+    EQS_BOUNDARY_TRY
+    H_OR_FAIL(h);
+    if (!gidx) return EQS_ERR_INCORRECT_INPUT;
+    return h->s.local_indices(gidx);
+    EQS_BOUNDARY_CATCH
+}
+
 int eqs_pso_init_local(eqs_pso *h, const double *x0, int32_t phase)
 {
     EQS_BOUNDARY_TRY

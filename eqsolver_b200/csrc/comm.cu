@@ -95,7 +95,7 @@ int p2p_setup(Ctx *ctx, Comm *c, int rank, int world)
     NcclApi &a = nccl();
     cudaStream_t s = ctx->stream;
     EQS_CUDA(ctx, cudaMalloc(&c->mailbox, MB_BYTES));
-    EQS_CUDA(ctx, cudaMemsetAsync(c->mailbox, 0, MB_REC, s));
+    EQS_CUDA(ctx, cudaMemsetAsync(c->mailbox, 0, MB_BYTES, s)); // header (counters, flags) and the tags of the LL region
     cudaIpcMemHandle_t mine;
     EQS_CUDA(ctx, cudaIpcGetMemHandle(&mine, c->mailbox));
     unsigned char *d_h = nullptr;

@@ -191,7 +191,13 @@ int comm_allgather_f64(Ctx *ctx, const double *send, double *recv, int64_t count
 constexpr size_t MB_SEQ = 0, MB_TIMEOUT = 8, MB_FLAG = 256, MB_REC = 4096;
 constexpr int MB_MAX_WORLD = 16;
 constexpr long long MB_REC_CAP = REC_X + 12800 + 2; // doubles per record slot (n <= 12800)
-constexpr size_t MB_BYTES = MB_REC + 2ull * MB_MAX_WORLD * MB_REC_CAP * sizeof(double);
+// A second region for the LOW-LATENCY exchanges (ll_* below): [2][world][MB_LL_CAP] 8-byte words, each word = 32 bits of
+// payload under a 32-bit tag (the exchange number), so that data and "it has arrived" travel in ONE store: no fence, no
+// flag, one NVLink one-way latency instead of store + fence round trip + flag.
+constexpr size_t MB_LLSEQ = 16;
+constexpr size_t MB_LL = MB_REC + 2ull * MB_MAX_WORLD * MB_REC_CAP * sizeof(double);
+constexpr long long MB_LL_CAP = 2 * (2 + 12800) + 4; // two words per double
+constexpr size_t MB_BYTES = MB_LL + 2ull * MB_MAX_WORLD * MB_LL_CAP * sizeof(unsigned long long);
 // returns false when the context has no peer mailboxes (single rank, IPC unavailable, or EQS_P2P=0)
 bool comm_p2p(Ctx *ctx, char **mailbox, char *const **d_peers);
 // How long a kernel waits in a mailbox for a peer before it gives up (the solve then fails with ExternalError instead of
@@ -279,6 +285,68 @@ __device__ __forceinline__ const unsigned long long *mailbox_allgather(char *mai
     __syncthreads();
     if (tid == 0) *seq_p = s;
     return reinterpret_cast<const unsigned long long *>(mailbox + MB_REC) + (size_t)slot * world * MB_REC_CAP;
+}
+
+// ---- low-latency exchange (the protocol NCCL calls LL): a double travels as two 8-byte words {tag, low half} and
+// {tag, high half}; an aligned 8-byte store arrives whole, so a receiver that sees the tag of THIS exchange in a word has
+// the payload of this exchange.  Every rank runs the same sequence of exchanges on a context (counter in its mailbox),
+// two slots deep like mailbox_allgather: a rank can be one exchange ahead of a peer, never two, because it needs that
+// peer's words of exchange s+1, which the peer sends only after it has read what it wanted of exchange s.
+struct LLExchange {
+    char *mailbox;
+    char *const *peers;
+    int rank, world, slot;
+    unsigned tag;
+    unsigned long long seq;
+};
+// all threads of the calling CTA; ends with a barrier.  ll_end (one thread, after the last ll_get) closes the exchange.
+__device__ __forceinline__ LLExchange ll_begin(char *mailbox, char *const *peers, int rank, int world)
+{
+    __shared__ unsigned long long s_llseq;
+    if (threadIdx.x == 0) s_llseq = *reinterpret_cast<unsigned long long *>(mailbox + MB_LLSEQ) + 1;
+    __syncthreads();
+    LLExchange x;
+    x.mailbox = mailbox;
+    x.peers = peers;
+    x.rank = rank;
+    x.world = world;
+    x.seq = s_llseq;
+    x.slot = (int)(x.seq & 1ull);
+    x.tag = (unsigned)(x.seq % 0xffffffffull) + 1u; // never 0 (the mailbox starts zeroed)
+    return x;
+}
+__device__ __forceinline__ void ll_end(const LLExchange &x) { *reinterpret_cast<unsigned long long *>(x.mailbox + MB_LLSEQ) = x.seq; }
+// double number d of this rank's record, to every peer
+__device__ __forceinline__ void ll_put(const LLExchange &x, int d, double v)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)x.tag << 32;
+    const unsigned long long w0 = t | (b & 0xffffffffull), w1 = t | (b >> 32);
+    for (int r = 0; r < x.world; ++r) {
+        if (r == x.rank) continue;
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(x.peers[r] + MB_LL) +
+                                  ((size_t)x.slot * x.world + x.rank) * MB_LL_CAP + 2 * d;
+        asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+    }
+}
+// double number d of rank r's record (r != this rank), from this rank's own mailbox; false after timeout_ns without it
+__device__ __forceinline__ bool ll_get(const LLExchange &x, int r, int d, double &v, long long timeout_ns)
+{
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(x.mailbox + MB_LL) +
+                                    ((size_t)x.slot * x.world + r) * MB_LL_CAP + 2 * d;
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0;; ++spins) {
+        unsigned long long w0, w1;
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+        if ((unsigned)(w0 >> 32) == x.tag && (unsigned)(w1 >> 32) == x.tag) {
+            v = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+            return true;
+        }
+        if ((spins & 31u) == 31u) {
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if ((long long)(now - t0) > timeout_ns) return false;
+        }
+    }
 }
 
 __device__ __forceinline__ double sanitize_cost(double c) { return (c != c) ? __longlong_as_double(0x7ff0000000000000LL) : c; }

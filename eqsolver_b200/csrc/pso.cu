@@ -333,20 +333,52 @@ __device__ __forceinline__ void pso_apply_step(const PsoDev &P, const double *re
 }
 
 // ---- the exchange fused into the step kernel (one kernel per pass at any world size) ---------------------------
-// Called by the LAST CTA of the step kernel once P.send holds this rank's record: all-gather of the records over the
-// peer mailboxes (common.cuh: mailbox_allgather), then the same gbest selection as pso_step_apply_kernel.
+// Called by the LAST CTA of the step kernel once P.send holds this rank's record.  Only (cost, index, position) matter in
+// a step; they go to every peer with the low-latency protocol of common.cuh (ll_*: payload and arrival in one 8-byte
+// store, one NVLink one-way trip; the flag protocol of mailbox_allgather needs stores, a system fence's round trip and a
+// flag store: 7 us per pass on two GPUs against 3), then the same gbest selection as pso_step_apply_kernel.
 __device__ __forceinline__ void pso_p2p_exchange_apply(const PsoDev &P)
 {
+    __shared__ int s_bad, s_wr;
     const long long R = record_doubles(P.n);
-    const unsigned long long *slots = mailbox_allgather(P.mailbox, P.peers, P.rank, P.world,
-                                                        reinterpret_cast<const unsigned long long *>(P.send), R,
-                                                        P.p2p_timeout_ns, &P.ctrl->p2p_timeout);
-    const double *src = reinterpret_cast<const double *>(slots);
-    for (int r = 0; r < P.world; ++r)
-        for (long long i = threadIdx.x; i < R; i += blockDim.x) P.recv[r * R + i] = __ldcv(src + r * MB_REC_CAP + i);
+    const int tid = threadIdx.x, world = P.world, n = P.n;
+    if (tid == 0) s_bad = 0;
+    const LLExchange X = ll_begin(P.mailbox, P.peers, P.rank, world); // barrier inside: P.send (write_record) is complete
+    const bool have = P.send[REC_IDX] >= 0.0;
+    const int nd = have ? 2 + n : 2;
+    for (int d = tid; d < nd; d += blockDim.x)
+        ll_put(X, d, d == 0 ? P.send[REC_COST] : (d == 1 ? P.send[REC_IDX] : P.send[REC_X + d - 2]));
+    if (tid < 2 * world) { // every rank's (cost, index)
+        const int r = tid >> 1, j = tid & 1;
+        double v = j ? P.send[REC_IDX] : P.send[REC_COST];
+        if (r != P.rank && !ll_get(X, r, j, v, P.p2p_timeout_ns)) {
+            s_bad = 1;
+            v = j ? -1.0 : dinf();
+        }
+        P.recv[r * R + (j ? REC_IDX : REC_COST)] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double bc;
+        s_wr = best_record(P.recv, world, R, bc);
+    }
+    __syncthreads();
+    const int wr = s_wr;
+    if (wr >= 0) { // only the winner's position is needed
+        for (int d = tid; d < n; d += blockDim.x) {
+            double v = P.send[REC_X + d];
+            if (wr != P.rank && !ll_get(X, wr, 2 + d, v, P.p2p_timeout_ns)) s_bad = 1;
+            P.recv[wr * R + REC_X + d] = v;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        ll_end(X);
+        if (s_bad) P.ctrl->p2p_timeout = 1;
+    }
     __threadfence_block();
     __syncthreads();
-    pso_apply_step(P, P.recv, P.world);
+    pso_apply_step(P, P.recv, world);
 }
 
 __device__ __forceinline__ void load_gbest(const PsoDev &P, double *sG)
@@ -382,6 +414,7 @@ template <class Obj> __global__ void pso_x0_kernel(const PsoDev P)
     c->seq_commit_buf = 0;
     c->seq_round = 0ULL;
     c->seq_barrier = 0u;
+    c->seq_xdone = 0ULL;
     c->seq_slot[0] = c->seq_slot[1] = c->seq_slot[2] = ~0ULL;
 }
 
@@ -774,16 +807,94 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
     __syncthreads();
 }
 
+// Several ranks (tile-cyclic distribution, pso.cuh): every rank runs this kernel on its share of the SAME global window,
+// with the same replicated loop state.  The LAST CTA of a rank to finish its share of the round (ticket on the arrival
+// counter: no separate grid barrier) sends (cost, first improving global index, its speculated position) to the other
+// ranks with the low-latency protocol of common.cuh (ll_*: one NVLink one-way trip, no fence, no flag), takes the lowest
+// index of all ranks and publishes (cost, index, position) in local memory; every CTA of the rank waits for that.
+__device__ __forceinline__ void pso_seq_exchange(const PsoDev &P, const double *xb, unsigned long long round)
+{
+    __shared__ unsigned long long s_loc;
+    __shared__ double s_hdr[MB_MAX_WORLD][2];
+    __shared__ int s_wr, s_bad;
+    PsoCtrl *ctrl = P.ctrl;
+    const int tid = threadIdx.x, world = P.world, n = P.n;
+    if (tid == 0) {
+        unsigned long long w;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(&ctrl->seq_slot[round % 3]) : "memory");
+        s_loc = w;
+        s_bad = 0;
+        // the slot of round r+2: its last readers (this CTA, round r-1) are done, its next writers (round r+2) wait for
+        // the publication of rounds r and r+1, which come after this store
+        ctrl->seq_slot[(round + 2) % 3] = ~0ULL;
+    }
+    const LLExchange X = ll_begin(P.mailbox, P.peers, P.rank, world); // barrier inside: s_loc is visible
+    const bool have = s_loc != ~0ULL;
+    const long long li = have ? pso_lidx(P, (long long)s_loc) : 0;
+    // this rank's record: [0] cost, [1] global index (-1 = none), [2 .. 2+n) position (only with an index)
+    const int nd = have ? 2 + n : 2;
+    for (int d = tid; d < nd; d += blockDim.x) {
+        double v;
+        if (d == 0) v = have ? __ldcg(P.cost + li) : dinf();
+        else if (d == 1) v = have ? (double)(long long)s_loc : -1.0;
+        else v = __ldcg(xb + goff(P, (d - 2) >> 2, li) + ((d - 2) & 3));
+        ll_put(X, d, v);
+        if (d < 2) s_hdr[P.rank][d] = v;
+    }
+    if (tid < 2 * world && (tid >> 1) != P.rank) { // the peers' (cost, index)
+        double v = 0.0;
+        if (!ll_get(X, tid >> 1, tid & 1, v, P.p2p_timeout_ns)) s_bad = 1;
+        s_hdr[tid >> 1][tid & 1] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int wr = -1;
+        double bi = 0.0;
+        for (int r = 0; r < world; ++r) {
+            const double idx = s_hdr[r][1];
+            if (idx >= 0.0 && (wr < 0 || idx < bi)) {
+                wr = r;
+                bi = idx;
+            }
+        }
+        s_wr = s_bad ? -1 : wr;
+    }
+    __syncthreads();
+    const int wr = s_wr;
+    if (wr >= 0) { // the winner's position: from the mailbox, or this rank's own particle
+        for (int d = tid; d < n; d += blockDim.x) {
+            double v = 0.0;
+            if (wr == P.rank) v = __ldcg(xb + goff(P, d >> 2, li) + (d & 3));
+            else if (!ll_get(X, wr, 2 + d, v, P.p2p_timeout_ns)) s_bad = 1;
+            P.recv[2 + d] = v;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        ll_end(X);
+        if (s_bad) ctrl->p2p_timeout = 1;
+        P.recv[0] = wr >= 0 ? s_hdr[wr][0] : dinf();
+        P.recv[1] = s_bad ? -2.0 : (wr >= 0 ? s_hdr[wr][1] : -1.0); // -2: a peer never arrived, every CTA leaves the loop
+        __threadfence();
+        const unsigned long long done = round + 1;
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&ctrl->seq_xdone), "l"(done) : "memory");
+    }
+}
+
 template <class Obj, bool REPLAY>
 __global__ void __launch_bounds__(PSO_BLOCK) pso_seqp_kernel(const PsoDev P)
 {
     extern __shared__ double sG[];
     __shared__ MinLoc s_red[32];
     __shared__ SeqLocal S;
-    __shared__ unsigned long long s_first;
+    __shared__ long long s_first;   // first improving GLOBAL index of the round, -1 = none, -2 = abort (peer timeout)
+    __shared__ double s_first_cost;
+    __shared__ int s_last;
     PsoCtrl *ctrl = P.ctrl;
     const int tid = threadIdx.x;
-    const long long N = P.nloc;
+    const long long N = P.ntotal;   // the loop state below is in GLOBAL particle indices
+    const bool multi = P.world > 1;
     if (tid == 0) { // every CTA reads the same control block: nothing writes it until the kernel's last lines
         S.Gc = ctrl->Gc;
         for (int j = 0; j < EQS_STALL_WINDOW; ++j) S.ring[j] = ctrl->ring[j];
@@ -806,7 +917,7 @@ __global__ void __launch_bounds__(PSO_BLOCK) pso_seqp_kernel(const PsoDev P)
     load_gbest(P, sG); // ends with a barrier: S is visible
     unsigned int arrivals = 0;
     const long long stride = (long long)gridDim.x * blockDim.x, gtid = (long long)blockIdx.x * blockDim.x + tid;
-    // particle li is always handled by thread li mod stride, so a particle's pending commit precedes its speculation
+    // local particle li is always handled by thread li mod stride, so a particle's pending commit precedes its speculation
     auto first_at = [&](long long lo) {
         long long r = (gtid - lo) % stride;
         if (r < 0) r += stride;
@@ -818,10 +929,11 @@ __global__ void __launch_bounds__(PSO_BLOCK) pso_seqp_kernel(const PsoDev P)
         const int cbuf = S.commit_buf, parity = S.parity;
         const double Gc = S.Gc;
         const unsigned long long round = S.round;
-        if (clo <= chi) { // :417-419 for the particles the previous round made final
+        if (clo <= chi) { // :417-419 for the particles the previous round made final (this rank's share of [clo, chi])
             const double *src = cbuf ? P.x2 : P.x;
             const int nq = (P.n + 3) >> 2;
-            for (long long li = first_at(clo); li <= chi; li += stride) {
+            const long long l1 = pso_lcount(P, chi + 1);
+            for (long long li = first_at(pso_lcount(P, clo)); li < l1; li += stride) {
                 const double c = P.cost[li];
                 if (c < P.pbc[li]) {
                     P.pbc[li] = c;
@@ -832,42 +944,68 @@ __global__ void __launch_bounds__(PSO_BLOCK) pso_seqp_kernel(const PsoDev P)
                 }
             }
         }
-        if (!active) break; // the same decision in every CTA; the pending commit above was the last thing to do
+        if (!active) break; // the same decision in every CTA (of every rank); the pending commit above was the last thing to do
         const uint32_t t = (uint32_t)S.iter;
         const long long wend = start + W < N ? start + W : N;
         const double *xa = parity ? P.x2 : P.x, *va = parity ? P.v2 : P.v;
         double *xb = parity ? P.x : P.x2, *vb = parity ? P.v : P.v2;
         MinLoc first{0.0, kNoIndex}; // min over the index only
-        for (long long li = first_at(start); li < wend; li += stride) {
+        const long long s1 = pso_lcount(P, wend);
+        for (long long li = first_at(pso_lcount(P, start)); li < s1; li += stride) {
             const double cost = pso_move<Obj, REPLAY>(P, t, li, sG, xa, va, P.pb, xb, vb, true);
             P.cost[li] = cost;
             if (cost < P.pbc[li] && cost < Gc && li < first.i) first.i = li; // :417,:420 (nested; see pso_spec_kernel)
         }
         const MinLoc b = block_minloc(first, s_red);
-        if (tid == 0 && b.i != kNoIndex) atomicMin(&ctrl->seq_slot[round % 3], (unsigned long long)b.i);
-        grid_barrier(&ctrl->seq_barrier, arrivals);
+        if (tid == 0 && b.i != kNoIndex) atomicMin(&ctrl->seq_slot[round % 3], (unsigned long long)pso_gidx(P, b.i));
+        if (multi) { // arrive; the last CTA of this rank talks to the other ranks, everybody waits for what it publishes
+            __threadfence();
+            __syncthreads();
+            arrivals += gridDim.x;
+            if (tid == 0) s_last = atomicAdd(&ctrl->seq_barrier, 1u) == arrivals - 1;
+            __syncthreads();
+            if (s_last) pso_seq_exchange(P, xb, round);
+        } else {
+            grid_barrier(&ctrl->seq_barrier, arrivals);
+        }
         if (tid == 0) {
-            unsigned long long w;
-            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(&ctrl->seq_slot[round % 3]) : "memory");
-            s_first = w;
+            if (multi) {
+                unsigned long long seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(&ctrl->seq_xdone) : "memory");
+                } while (seen < round + 1);
+                s_first = (long long)__ldcg(P.recv + 1);
+                s_first_cost = __ldcg(P.recv);
+            } else {
+                unsigned long long w;
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(&ctrl->seq_slot[round % 3]) : "memory");
+                s_first = w == ~0ULL ? -1 : (long long)w;
+                s_first_cost = w == ~0ULL ? 0.0 : __ldcg(P.cost + w);
+            }
             // the slot of round r+2: its last readers (round r-1) are behind this barrier, its next writers (round r+2)
             // are behind the NEXT barrier, which this thread reaches only after the store
-            if (blockIdx.x == 0) ctrl->seq_slot[(round + 2) % 3] = ~0ULL;
+            if (!multi && blockIdx.x == 0) ctrl->seq_slot[(round + 2) % 3] = ~0ULL;
         }
         __syncthreads();
-        const unsigned long long istar = s_first;
-        const bool found = istar != ~0ULL;
-        if (found) // gbest <- the improving particle's speculated position (buffer B), into this CTA's copy
-            for (int d = tid; d < P.n; d += blockDim.x) sG[d] = __ldcg(xb + goff(P, d >> 2, (long long)istar) + (d & 3));
+        const long long istar = s_first;
+        if (istar == -2) break; // a peer rank never reached the exchange: p2p_timeout is set, the host reports it
+        const bool found = istar >= 0;
+        if (found) { // gbest <- the improving particle's speculated position, into this CTA's copy
+            if (multi) {
+                for (int d = tid; d < P.n; d += blockDim.x) sG[d] = __ldcg(P.recv + 2 + d);
+            } else {
+                for (int d = tid; d < P.n; d += blockDim.x) sG[d] = __ldcg(xb + goff(P, d >> 2, istar) + (d & 3));
+            }
+        }
         if (tid == 0) {
-            const long long hi = found ? (long long)istar : wend - 1;
+            const long long hi = found ? istar : wend - 1;
             S.commit_lo = start;
             S.commit_hi = hi;
             S.commit_buf = parity ^ 1;
             if (found) { // :420-425
                 S.ring[S.ring_i] = S.Gc;
                 S.ring_i = (S.ring_i + 1) % EQS_STALL_WINDOW;
-                S.Gc = __ldcg(P.cost + istar);
+                S.Gc = s_first_cost;
                 S.improvements += 1;
             }
             if (hi + 1 >= N) { // the pass is complete
@@ -1094,6 +1232,22 @@ int PsoSolver::create(const eqs_pso_params *p)
     D.n = n;
     D.world = world;
     D.rank = rank;
+    // peer mailboxes (NVLink, CUDA IPC): the fused exchange of the synchronous step and of the sequential rounds
+    char *mb = nullptr;
+    char *const *peers = nullptr;
+    const bool p2p = !manual_ && world > 1 && record_doubles(n) <= MB_REC_CAP && comm_p2p(ctx_, &mb, &peers);
+    // Sequential-exact mode over several ranks: tile-cyclic distribution + device-driven rounds (pso_seqp_kernel); without
+    // peer memory (or with EQS_PSO_SEQ_HOST=1) the host-driven whole-suffix rounds on contiguous blocks
+    D.cyclic = p->mode == EQS_PSO_SEQUENTIAL_EXACT && p2p && !getenv("EQS_PSO_SEQ_HOST");
+    D.tiles_per_rank = 0;
+    if (D.cyclic) {
+        const int64_t ntiles = (p->particle_count + PSO_GROUP - 1) / PSO_GROUP;
+        const int64_t owned = ntiles > rank ? (ntiles - rank + world - 1) / world : 0;
+        nloc = owned * PSO_GROUP;
+        if (owned > 0 && (ntiles - 1) % world == rank) nloc -= ntiles * PSO_GROUP - p->particle_count; // the ragged last tile
+        first = (int64_t)rank * PSO_GROUP; // global index of local particle 0 (informational: see local_indices)
+        D.tiles_per_rank = std::max<int64_t>((ntiles + world - 1) / world, 1);
+    }
     D.first = first;
     D.nloc = nloc;
     D.ntotal = p->particle_count;
@@ -1113,7 +1267,7 @@ int PsoSolver::create(const eqs_pso_params *p)
     const size_t mat = (size_t)nq * 4 * D.ld * sizeof(double);
     const size_t vec = (size_t)D.ld * sizeof(double);
     const size_t R = (size_t)record_doubles(n) * sizeof(double);
-    const long long ngroups = std::max<long long>((nloc + PSO_GROUP - 1) / PSO_GROUP, 1);
+    const long long ngroups = std::max<long long>(std::max<long long>((nloc + PSO_GROUP - 1) / PSO_GROUP, D.tiles_per_rank), 1);
     const int max_grid = 64 * std::max(ctx_->sm_count, 1);
     // one arena: plan the offsets, allocate once, then bind the pointers
     size_t off = 0;
@@ -1129,6 +1283,7 @@ int PsoSolver::create(const eqs_pso_params *p)
     const size_t o_ctrl = plan(sizeof(PsoCtrl));
     const size_t o_pc = plan(max_grid * sizeof(double)), o_pi = plan(max_grid * sizeof(long long));
     const size_t o_gm = plan(ngroups * sizeof(double));
+    const size_t o_gma = D.cyclic ? plan((size_t)world * D.tiles_per_rank * sizeof(double)) : 0;
     const size_t o_send = plan(R);
     const bool own_recv = !(world == 1 && !manual_);
     const size_t o_recv = own_recv ? plan(R * world) : o_send;
@@ -1150,21 +1305,23 @@ int PsoSolver::create(const eqs_pso_params *p)
     D.part_cost = (double *)(base + o_pc);
     D.part_idx = (long long *)(base + o_pi);
     D.group_min = (double *)(base + o_gm);
+    D.gm_all = D.cyclic ? (double *)(base + o_gma) : nullptr;
     D.send = (double *)(base + o_send);
     D.recv = (double *)(base + o_recv);
     max_grid_ = max_grid;
     D.mailbox = nullptr;
     D.peers = nullptr;
     fused_exchange_ = false;
-    if (!manual_ && world > 1 && D.sync && record_doubles(n) <= MB_REC_CAP) {
-        char *mb = nullptr;
-        char *const *peers = nullptr;
-        if (comm_p2p(ctx_, &mb, &peers)) {
-            D.mailbox = mb;
-            D.peers = peers;
-            D.p2p_timeout_ns = comm_p2p_timeout_ns();
-            fused_exchange_ = true;
-        }
+    if (p2p && (D.sync || D.cyclic)) {
+        D.mailbox = mb;
+        D.peers = peers;
+        D.p2p_timeout_ns = comm_p2p_timeout_ns();
+        fused_exchange_ = D.sync;
+    }
+    if (D.cyclic) { // tiles this rank does not have (ragged end of the cyclic deal) never hold a record low
+        std::vector<double> inf((size_t)ngroups, HUGE_VAL);
+        EQS_CUDA(ctx_, cudaMemcpyAsync(D.group_min, inf.data(), inf.size() * sizeof(double), cudaMemcpyHostToDevice, ctx_->stream));
+        EQS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
     }
     EQS_CUDA(ctx_, cudaMemcpyAsync(lo, lower_.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx_->stream));
     EQS_CUDA(ctx_, cudaMemcpyAsync(hi, upper_.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx_->stream));
@@ -1177,8 +1334,8 @@ int PsoSolver::create(const eqs_pso_params *p)
     EQS_CUDA(ctx_, cudaEventCreate(&ev1_));
     // sequential mode on one rank beyond the single-CTA kernel's reach: device-driven windowed rounds
     // (EQS_PSO_SEQ_HOST=1 keeps the host-driven whole-suffix rounds, which ranks > 1 always use)
-    seq_windowed_ = p->mode == EQS_PSO_SEQUENTIAL_EXACT && d_.world == 1 && !manual_ && d_.nloc > PSO_SMALL_MAX &&
-                    !getenv("EQS_PSO_SEQ_HOST");
+    seq_windowed_ = p->mode == EQS_PSO_SEQUENTIAL_EXACT &&
+                    (d_.cyclic || (d_.world == 1 && !manual_ && d_.nloc > PSO_SMALL_MAX && !getenv("EQS_PSO_SEQ_HOST")));
     return EQS_OK;
 }
 
@@ -1249,6 +1406,13 @@ int PsoSolver::launch_ring_scan()
     return EQS_OK;
 }
 
+// tile-cyclic distribution: the ordered ring scan walks the tiles of ALL ranks, so every rank needs every rank's minima
+int PsoSolver::gather_tile_minima()
+{
+    if (!d_.cyclic) return EQS_OK;
+    return comm_allgather_f64(ctx_, d_.group_min, d_.gm_all, d_.tiles_per_rank, ctx_->stream);
+}
+
 int PsoSolver::launch_init_apply()
 {
     pso_init_apply_kernel<<<1, 128, 0, ctx_->stream>>>(d_);
@@ -1279,6 +1443,7 @@ int PsoSolver::init(const double *x0)
     if (manual_) return ctx_->fail(EQS_ERR_INCORRECT_INPUT, "exchange = MANUAL: use the split-phase calls");
     EQS_TRY(init_local(x0, 0));
     EQS_TRY(exchange());
+    EQS_TRY(gather_tile_minima());
     EQS_TRY(init_local(x0, 1));
     EQS_TRY(exchange());
     return init_apply();
@@ -1375,11 +1540,15 @@ int PsoSolver::sequential_windowed(int64_t iters)
     // a round costs about 4 us beyond its particles (grid barrier, ramp-up and tail of the wave; a launch per round cost
     // 11 -- swept on C2: 1 / 2.5 / 4 / 8 us give 0.447 / 0.402 / 0.386 / 0.416 ms per pass, profiles/r02_sweep.md) and a
     // particle (40n + 16) B of HBM traffic at ~5.7 TB/s
-    const long long wave = (long long)grid_seqw_ * PSO_BLOCK;
-    long long wmin = std::min<long long>(4096, wave), wmax = std::max<long long>(d_.nloc, wmin), w0 = std::min(wave, wmax);
-    double round_us = 4.0;
+    // Several ranks: the window is in GLOBAL particles and every rank works on 1 / world of it, a round also pays one
+    // NVLink round trip of the peer mailboxes (EQS_PSO_SEQ_ROUND_US, swept on 2 GPUs: profiles/r02_sweep.md section 4).
+    // The window policy must be the same on every rank: it only uses quantities all ranks agree on.
+    const int world = d_.world;
+    const long long wave = (long long)ctx_->sm_count * 2 * PSO_BLOCK * world;
+    long long wmin = std::min<long long>(4096LL * world, wave), wmax = std::max<long long>(d_.ntotal, wmin), w0 = std::min(wave, wmax);
+    double round_us = world > 1 ? 6.0 : 4.0;
     if (const char *e = getenv("EQS_PSO_SEQ_ROUND_US")) round_us = std::max(0.1, atof(e));
-    const double wscale = 2.0 * round_us * 5.7e6 / (40.0 * d_.n + 16.0);
+    const double wscale = 2.0 * round_us * 5.7e6 * world / (40.0 * d_.n + 16.0);
     if (const char *e = getenv("EQS_PSO_SEQ_WINDOW")) wmin = wmax = w0 = std::max<long long>(1, atoll(e));
     pso_seq_arm_kernel<<<1, 1, 0, ctx_->stream>>>(d_, (long long)iters, wmin, wmax, w0, wscale);
     launches_++;
@@ -1536,6 +1705,13 @@ int PsoSolver::read_ring(double *ring, int64_t *ring_i)
     EQS_TRY(fetch_ctrl());
     if (ring) memcpy(ring, h_ctrl_->ring, sizeof(h_ctrl_->ring));
     if (ring_i) *ring_i = h_ctrl_->ring_i;
+    return EQS_OK;
+}
+
+// global index of every local particle, in local order (what read_state's rows are)
+int PsoSolver::local_indices(int64_t *gidx)
+{
+    for (long long li = 0; li < d_.nloc; ++li) gidx[li] = pso_gidx(d_, li);
     return EQS_OK;
 }
 

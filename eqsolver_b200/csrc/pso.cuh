@@ -38,6 +38,7 @@ struct PsoCtrl {
     unsigned long long seq_round;   // rounds so far (picks the slot below)
     unsigned long long seq_slot[3]; // first improving particle of round r in slot r % 3 (atomicMin; ~0 = none)
     unsigned int seq_barrier;       // arrivals at the grid barrier of the current launch of pso_seqp_kernel
+    unsigned long long seq_xdone;   // several ranks: rounds whose cross-rank result CTA 0 has published in recv (monotonic)
 };
 
 struct PsoDev {

@@ -385,6 +385,13 @@ class PsoRun:
         self.ctx.check(_ffi.lib().eqs_pso_read_state(self._h, _p(x), _p(v), _p(pb), _p(pbc)))
         return x, v, pb, pbc
 
+    def local_indices(self) -> np.ndarray:
+        """Global index of every local particle, in the row order of state(): first .. first + local - 1, except in
+        sequential-exact mode over several ranks (tiles of 256 particles dealt round-robin over the ranks)."""
+        idx = np.empty(self.local, dtype=np.int64)
+        self.ctx.check(_ffi.lib().eqs_pso_local_indices(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64))))
+        return idx
+
     def pbest_costs(self) -> np.ndarray:
         """Only the pbest costs of this rank's particles (state() also moves 3 n-vectors per particle)."""
         pbc = np.empty(self.local)

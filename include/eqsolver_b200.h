@@ -187,6 +187,11 @@ int eqs_pso_read_gbest(eqs_pso *h, double *g /*[n] or NULL*/, double *cost, int6
 int eqs_pso_read_state(eqs_pso *h, double *x, double *v, double *pbest, double *pbest_cost);
 int eqs_pso_read_ring(eqs_pso *h, double *ring /*[50]*/, int64_t *ring_i);
 int eqs_pso_local_range(eqs_pso *h, int64_t *first, int64_t *local);
+/* global index of every local particle, in the row order of eqs_pso_read_state: gidx [local].  Contiguous blocks
+ * (first .. first + local - 1) except in sequential-exact mode over several ranks, which deals tiles of 256 consecutive
+ * particles round-robin: global tile T lives on rank T % world (the windows of the reference's particle order,
+ * particle_swarm.rs:399-427, then keep every rank busy). */
+int eqs_pso_local_indices(eqs_pso *h, int64_t *gidx);
 /* split-phase protocol for EQS_EXCHANGE_MANUAL (virtual ranks; also how the NCCL path is sequenced):
  *   init: init_local(phase 0) -> gather records -> init_local(phase 1) -> gather records -> init_apply
  *   step: step_local -> gather records -> step_apply

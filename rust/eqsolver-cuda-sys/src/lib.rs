@@ -162,6 +162,7 @@ extern "C" {
                               pbest_cost: *mut c_double) -> c_int;
     pub fn eqs_pso_read_ring(h: *mut eqs_pso, ring: *mut c_double, ring_i: *mut i64) -> c_int;
     pub fn eqs_pso_local_range(h: *mut eqs_pso, first: *mut i64, local: *mut i64) -> c_int;
+    pub fn eqs_pso_local_indices(h: *mut eqs_pso, gidx: *mut i64) -> c_int;
     pub fn eqs_pso_init_local(h: *mut eqs_pso, x0: *const c_double, phase: i32) -> c_int;
     pub fn eqs_pso_init_apply(h: *mut eqs_pso) -> c_int;
     pub fn eqs_pso_step_local(h: *mut eqs_pso, replay_step: *const c_double) -> c_int;

@@ -67,21 +67,59 @@ def main():
                 o.step()
         run.close()
 
-    # ---- ParticleSwarm, sequential-exact across ranks (speculate-and-repair with a global first-index exchange) ---
-    n, N, iters = 5, 2003, 4
-    lower, upper, x0 = [-5.0] * n, [10.0] * n, np.full(n, 3.0)
-    ps = (E.ParticleSwarm.new(E.Objective.ROSENBROCK, lower, upper).with_particle_count(N).with_tol(0.0).with_seed(7)
-          .with_mode(E.PsoMode.SEQUENTIAL_EXACT).with_context(ctx))
-    run = ps.start(x0)
-    o = O.Pso(O.ROSENBROCK, lower, upper, particle_count=N, tol=0.0, mode=O.SEQUENTIAL, seed=7)
-    o.init(x0)
-    for t in range(iters):
-        run.step(1)
-        o.step()
-        g, c, it, _, _ = run.gbest()
-        assert np.array_equal(g.view(np.uint64), o.gbest().view(np.uint64)) and c == o.gbest_cost(), f"seq pass {t}"
-        assert np.array_equal(run.ring()[0].view(np.uint64), o.ring()[0].view(np.uint64))
-    run.close()
+    # ---- ParticleSwarm, sequential-exact across ranks: tile-cyclic distribution, device-driven windowed rounds with the
+    # first-improving index exchanged over the peer mailboxes (pso_seqp_kernel); EQS_PSO_SEQ_HOST=1: the host-driven
+    # whole-suffix rounds on contiguous blocks.  Every particle's state against the UNSHARDED oracle, bit for bit. ------
+    def seq_case(obj, n, N, steps, seed, window=None, host=False, exact=True):
+        for k, v in (("EQS_PSO_SEQ_WINDOW", window), ("EQS_PSO_SEQ_HOST", "1" if host else None)):
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+        lower, upper, x0 = [-5.0] * n, [10.0] * n, np.full(n, 3.0)
+        ps = (E.ParticleSwarm.new(obj, lower, upper).with_particle_count(N).with_tol(0.0).with_seed(seed)
+              .with_mode(E.PsoMode.SEQUENTIAL_EXACT).with_context(ctx))
+        run = ps.start(x0)
+        o = O.Pso(int(obj), lower, upper, particle_count=N, tol=0.0, mode=O.SEQUENTIAL, seed=seed)
+        o.init(x0)
+        idx = run.local_indices()
+        what = f"seq {obj.name} n={n} N={N} window={window} host={host}"
+        assert idx.size == run.local and (np.diff(idx) > 0).all(), what
+        t_idx = torch.full((N,), -1, dtype=torch.int64, device="cuda")
+        counts = torch.zeros(N, dtype=torch.int64, device="cuda")
+        counts[torch.from_numpy(idx).cuda()] += 1
+        dist.all_reduce(counts)
+        assert bool((counts == 1).all()), what + ": the ranks' index sets do not partition 0..N-1"
+        done = 0
+        for k in [0] + list(steps):
+            if k:
+                run.step(k)
+                for _ in range(k):
+                    o.step()
+                done += k
+            g, c, it, _, imp = run.gbest()
+            eq = (lambda a, b: np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(b).view(np.uint64))) \
+                if exact else (lambda a, b: np.allclose(a, b, rtol=1e-12, atol=1e-12))
+            assert eq(g, o.gbest()) and eq(np.array([c]), np.array([o.gbest_cost()])), f"{what} gbest after {done} passes"
+            assert it == o.iters(), what
+            assert eq(run.ring()[0], o.ring()[0]) and run.ring()[1] == o.ring()[1], f"{what} ring after {done} passes"
+            x, v, pb, pbc = run.state()
+            ox, ov, opb, opbc = o.state()
+            for a, bb, nm in ((x, ox[idx], "x"), (v, ov[idx], "v"), (pb, opb[idx], "pbest"), (pbc, opbc[idx], "pbest cost")):
+                assert eq(a, bb), f"{what} {nm} after {done} passes, rank {rank}"
+            same_everywhere(g, "gbest")
+        run.close()
+        os.environ.pop("EQS_PSO_SEQ_WINDOW", None)
+        os.environ.pop("EQS_PSO_SEQ_HOST", None)
+
+    seq_case(E.Objective.ROSENBROCK, 5, 2003, [1, 1, 2], seed=7)                 # 8 tiles, the last one ragged
+    seq_case(E.Objective.ROSENBROCK, 5, 2003, [1, 3], seed=7, window=300)        # windows that straddle the ranks' tiles
+    seq_case(E.Objective.SPHERE, 4, 256 * world + 1, [2, 2], seed=3, window=100) # one rank holds a 1-particle tile
+    seq_case(E.Objective.SPHERE, 3, 200, [3], seed=5)                            # fewer tiles than ranks: empty ranks
+    seq_case(E.Objective.USER, 6, 70001, [1, 2], seed=11)                        # default window policy, 274 tiles
+    seq_case(E.Objective.ROSENBROCK, 9, 40000, [2], seed=13, window=5000)
+    seq_case(E.Objective.RASTRIGIN, 8, 9000, [2], seed=17, exact=False)
+    seq_case(E.Objective.ROSENBROCK, 5, 2003, [1, 1], seed=7, host=True)         # the fallback path still works
 
     # ---- whole solve through the builder, stall exit on every rank at the same pass -------------------------------
     ps = (E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * 2, [1.0] * 2).with_particle_count(64 * world).with_tol(1e-3)
@@ -150,10 +188,13 @@ def main():
         g, c, it, _, _ = run.gbest()
         assert np.array_equal(g.view(np.uint64), o.gbest().view(np.uint64)) and c == o.gbest_cost() and it == 3, what
         assert np.array_equal(run.ring()[0].view(np.uint64), o.ring()[0].view(np.uint64)) and run.ring()[1] == o.ring()[1], what
-        first, local_n = E.shard_range(N, world, rank)
-        if local_n > 0:
+        idx = run.local_indices()  # contiguous blocks (synchronous) or tiles dealt round-robin (sequential-exact)
+        if mode == E.PsoMode.SYNCHRONOUS:
+            first, local_n = E.shard_range(N, world, rank)
+            assert idx.tolist() == list(range(first, first + local_n)), what
+        if idx.size > 0:
             for a, b in zip(run.state(), o.state()):
-                b = np.ascontiguousarray(b[first:first + local_n])
+                b = np.ascontiguousarray(b[idx])
                 assert np.array_equal(np.ascontiguousarray(a).view(np.uint64), b.view(np.uint64)), what
         run.close()
     for case in range(8):

@@ -148,6 +148,7 @@ def test_null_handles_are_refused_not_dereferenced():
         'eqs_measure_pattern': (null, 32, 100, None), 'eqs_measure_fp64': (null, None),
         'eqs_device_cos': (null, None, 1, None), 'eqs_pso_last_step_ms': (null, None, None),
         'eqs_pso_read_ring': (null, None, None), 'eqs_pso_local_range': (null, None, None),
+        'eqs_pso_local_indices': (null, None),
         'eqs_pso_init_local': (null, None, 0), 'eqs_pso_init_apply': (null,), 'eqs_pso_step_local': (null, None),
         'eqs_pso_step_apply': (null,), 'eqs_pso_get_record': (null, None), 'eqs_pso_set_records': (null, None),
         'eqs_ce_last_step_ms': (null, None, None), 'eqs_ce_read_elites': (null, None, None),
