@@ -492,6 +492,52 @@ def parity_check(b: Bench, workload: str):
     return {"ok": ok, "what": what, "seconds": time.monotonic() - t_start, **detail}
 
 
+def parity_check_sequential(b: Bench):
+    """The reference's own semantics (sequential-exact gbest, particle_swarm.rs:399-427) sharded over the ranks -- tiles of
+    256 particles dealt round-robin, device-driven windowed rounds with the first-improving index exchanged over the peer
+    mailboxes -- against the same run on one GPU.  Collective: every rank calls it."""
+    E = b.E
+    t_start = time.monotonic()
+    obj, n, per_gpu, lo, hi, x0v, _ = PSO_WORKLOADS["c2"]
+    N, passes = (1 << 17) * b.world + 77, 6          # a ragged last tile
+    x0 = np.full(n, x0v)
+    run = b.pso("c2", N, passes, mode=E.PsoMode.SEQUENTIAL_EXACT).start(x0)
+    run.step(passes)
+    run.sync()
+    g, gc, it, _, imp = run.gbest()
+    ring, ring_i = run.ring()
+    idx = run.local_indices()
+    sums = b.gather_i64(bits_checksum(run.pbest_costs()), 3)
+    counts = b.gather_i64(np.array([idx.size, int(idx.sum()) if idx.size else 0], dtype=np.int64), 2)
+    run.close()
+    ok, detail = True, {}
+    if b.rank == 0:
+        ref = b.pso("c2", N, passes, ctx=b.ctx1, mode=E.PsoMode.SEQUENTIAL_EXACT).start(x0)
+        ref.step(passes)
+        ref.sync()
+        rg, rgc, rit, _, rimp = ref.gbest()
+        rring, rring_i = ref.ring()
+        pbc = ref.pbest_costs()
+        ref.close()
+        tile = np.arange(N) // 256
+        owners = [np.nonzero(tile % b.world == r)[0] for r in range(b.world)]   # global tile T lives on rank T mod world
+        want = np.concatenate([bits_checksum(pbc[o]) for o in owners])
+        want_counts = np.concatenate([[o.size, int(o.sum())] for o in owners]).astype(np.int64)
+        bits = lambda a: np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+        checks = {"gbest_bit_equal": bool(np.array_equal(bits(g), bits(rg))) and gc == rgc,
+                  "ring_bit_equal": bool(np.array_equal(bits(ring), bits(rring))) and ring_i == rring_i,
+                  "improvements_equal": imp == rimp, "passes_equal": it == rit == passes,
+                  "index_sets_equal": bool(np.array_equal(counts, want_counts)),
+                  "pbest_cost_checksums_equal": bool(np.array_equal(sums, want))}
+        ok = all(checks.values())
+        detail = dict(checks, gbest_cost=gc, gbest_improvements=int(imp))
+    ok = b.agree(ok)
+    what = (f"ParticleSwarm {obj.lower()} n={n}, {N} particles over {b.world} GPUs, {passes} passes in the reference's "
+            f"sequential-exact semantics (tile-cyclic distribution, device-driven rounds): gbest, stall ring, improvement "
+            f"count and per-rank pbest-cost checksums, bit for bit against the same run on one GPU")
+    return {"ok": ok, "what": what, "seconds": time.monotonic() - t_start, **detail}
+
+
 def also_measured(b: Bench, headline: str, fp64_peak: float):
     """The other BASELINE configurations at this N (per-GPU shapes, weak scaling), outside the headline's timed region:
     device-resident, CUDA events on the library stream, max over ranks.  Collective: every rank calls it."""
@@ -512,6 +558,19 @@ def also_measured(b: Bench, headline: str, fp64_peak: float):
             out[wl] = {"value": per_gpu * b.world * passes / (ms * 1e-3), "unit": "particle-evals/s",
                        "ms_per_pass": ms / passes, "launches_per_pass": launches / passes, "passes": passes,
                        "particles_per_gpu": per_gpu, "n": n, "roofline": pso_roofline(wl, n, per_gpu, ms / passes)}
+    if b.world > 1:
+        # C2 in the reference's sequential-gbest semantics over all ranks (weak scaling: 2^20 particles per GPU)
+        n, per_gpu, passes = 32, 1 << 20, 30
+        run = b.pso("c2", per_gpu * b.world, 10 ** 6, mode=E.PsoMode.SEQUENTIAL_EXACT).start(np.zeros(n))
+        ms, launches, _, _ = b.timed(run, 3, passes)
+        imp = run.gbest()[4]
+        run.close()
+        out["c2_sequential_exact_sharded"] = {
+            "value": per_gpu * b.world * passes / (ms * 1e-3), "unit": "particle-evals/s", "ms_per_pass": ms / passes,
+            "launches_per_pass": launches / passes, "passes": passes, "particles_per_gpu": per_gpu,
+            "gbest_improvements": int(imp), "roofline": pso_roofline("c2", n, per_gpu, ms / passes),
+            "how": "tiles of 256 particles dealt round-robin over the ranks; one persistent kernel per rank, the first "
+                   "improving index of every round exchanged over the NVLink mailboxes"}
     if b.rank == 0:
         # single-GPU items, on rank 0's unsharded context
         if headline != "c1":   # C1: 1000 particles, 2-D -- one CTA runs the passes back to back (latency-bound, no roofline)
@@ -677,6 +736,7 @@ def main():
         pc = {"headline": parity_check(b, wl)}
         other = "c2" if is_ce else "c3"      # the other half of the metric: a CrossEntropy (or ParticleSwarm) pass
         pc[other] = parity_check(b, other)
+        pc["c2_sequential_exact"] = parity_check_sequential(b)
         line["parity_check"] = all(v["ok"] for v in pc.values())
         line["parity_detail"] = pc
         failed = not line["parity_check"]

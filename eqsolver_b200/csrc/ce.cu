@@ -12,7 +12,7 @@
 //                      :255,299-302  mu, sigma <- new; iter += 1; loop condition for the next pass
 // A pass is EIGHT launches.  Every step that needs all ranks' data (key range, histogram of a level, moment sums) is done
 // by the LAST CTA of the kernel that produced this rank's share: it all-gathers the shares over the peer-memory
-// mailboxes (common.cuh: mailbox_allgather; nothing to gather on one rank) and applies them, so no collective and no
+// mailboxes (common.cuh: ll_allgather_u64; nothing to gather on one rank) and applies them, so no collective and no
 // extra kernel sits between the stages.  The same device functions also run as separate PHASES with the exchange done
 // outside (virtual ranks driven by a test harness, NCCL when peer mapping is unavailable).
 #include <algorithm>
@@ -195,10 +195,14 @@ struct Gathered {
 // one CTA, fused modes: `words` words at `send` (global memory, complete) from every rank
 __device__ __forceinline__ Gathered ce_gather(const CeDev &P, int fused, const unsigned long long *send, long long words)
 {
-    if (fused == CE_FUSED_P2P) {
-        const unsigned long long *slots =
-            mailbox_allgather(P.mailbox, P.peers, P.rank, P.world, send, words, P.p2p_timeout_ns, &P.ctrl->p2p_timeout);
-        return Gathered{slots, MB_REC_CAP, P.world};
+    if (fused == CE_FUSED_P2P) { // low-latency protocol (common.cuh: ll_*), into the receive buffers of the phased mode
+        const bool hist = send == P.hsend;
+        unsigned long long *recv = hist ? P.hrecv : reinterpret_cast<unsigned long long *>(P.mrecv);
+        const long long stride = hist ? CE_BINS : P.n;
+        if (!ll_allgather_u64(P.mailbox, P.peers, P.rank, P.world, send, words, recv, stride, P.p2p_timeout_ns))
+            P.ctrl->p2p_timeout = 1;
+        __syncthreads();
+        return Gathered{recv, stride, P.world};
     }
     return Gathered{send, 0, 1};
 }
@@ -903,7 +907,7 @@ public:
             char *const *peers = nullptr;
             if (world == 1) {
                 fused_ = CE_FUSED_LOCAL;
-            } else if ((size_t)std::max(n, CE_BINS) <= (size_t)MB_REC_CAP && comm_p2p(ctx_, &mb, &peers)) {
+            } else if (2 * (size_t)std::max(n, CE_BINS) <= (size_t)MB_LL_CAP && comm_p2p(ctx_, &mb, &peers)) {
                 d_.mailbox = mb;
                 d_.peers = peers;
                 fused_ = CE_FUSED_P2P;

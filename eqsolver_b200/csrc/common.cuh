@@ -184,19 +184,16 @@ int comm_init(Ctx *ctx, int rank, int world, const void *id128);
 void comm_destroy(Ctx *ctx);
 int comm_allgather_f64(Ctx *ctx, const double *send, double *recv, int64_t count_per_rank, cudaStream_t s);
 
-// ---- peer-memory mailboxes (NVLink / NVSwitch, CUDA IPC): the fused exchange of the ParticleSwarm step kernel ----
-// One mailbox per rank, mapped into every peer: [seq u64 | flags [2][world] u64 | records [2][world][MB_REC_CAP] f64].
-// A rank's last CTA stores its record into slot (exchange number & 1, my rank) of EVERY mailbox, release-stores the
-// exchange number into the matching flag, and acquire-waits until its own mailbox holds that number from every peer.
-constexpr size_t MB_SEQ = 0, MB_TIMEOUT = 8, MB_FLAG = 256, MB_REC = 4096;
+// ---- peer-memory mailboxes (NVLink / NVSwitch, CUDA IPC): the exchanges fused into the kernels ----------------------
+// One mailbox per rank, mapped into every peer: [exchange counter u64 | pad to 4 KB | words [2][world][MB_LL_CAP] u64].
+// Every 8-byte word carries 32 bits of payload under a 32-bit tag (the exchange number), so data and "it has arrived"
+// travel in ONE store: no fence, no flag, one NVLink one-way latency (ll_* below; NCCL calls this protocol LL).  The flag
+// protocol this replaced in round 2 -- plain stores, __threadfence_system, a release store of the exchange number, an
+// acquire spin -- paid the fence's NVLink round trip before the flag could leave: 7 us per exchange on two GPUs against 3
+// (profiles/r02_sweep.md section 4).
+constexpr size_t MB_LLSEQ = 0, MB_LL = 4096;
 constexpr int MB_MAX_WORLD = 16;
-constexpr long long MB_REC_CAP = REC_X + 12800 + 2; // doubles per record slot (n <= 12800)
-// A second region for the LOW-LATENCY exchanges (ll_* below): [2][world][MB_LL_CAP] 8-byte words, each word = 32 bits of
-// payload under a 32-bit tag (the exchange number), so that data and "it has arrived" travel in ONE store: no fence, no
-// flag, one NVLink one-way latency instead of store + fence round trip + flag.
-constexpr size_t MB_LLSEQ = 16;
-constexpr size_t MB_LL = MB_REC + 2ull * MB_MAX_WORLD * MB_REC_CAP * sizeof(double);
-constexpr long long MB_LL_CAP = 2 * (2 + 12800) + 4; // two words per double
+constexpr long long MB_LL_CAP = 2 * (2 + 12800) + 4; // two words per 8-byte value: (cost, index, n <= 12800 coordinates)
 constexpr size_t MB_BYTES = MB_LL + 2ull * MB_MAX_WORLD * MB_LL_CAP * sizeof(unsigned long long);
 // returns false when the context has no peer mailboxes (single rank, IPC unavailable, or EQS_P2P=0)
 bool comm_p2p(Ctx *ctx, char **mailbox, char *const **d_peers);
@@ -222,76 +219,18 @@ constexpr size_t kSmemOptIn = 32 * 1024;
 #define EQS_CHECK(cond) ((void)0)
 #endif
 
-// system-scope flag accesses of the mailbox protocol
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// spin until *flag == expect; false when timeout_ns of wall-clock time passed first (the clock is read every 32 polls)
-__device__ __forceinline__ bool mailbox_wait(const unsigned long long *flag, unsigned long long expect, long long timeout_ns)
-{
-    unsigned long long t0 = 0;
-    for (unsigned spins = 0;; ++spins) {
-        if (ld_acquire_sys(flag) == expect) return true;
-        if ((spins & 31u) == 31u) {
-            const unsigned long long now = globaltimer_ns();
-            if (t0 == 0) t0 = now;
-            else if ((long long)(now - t0) > timeout_ns) return false;
-        }
-    }
-}
-
-// ALLGATHER OVER THE MAILBOXES, executed by ONE CTA (all of its threads call): `words` 8-byte words at `send` (memory
-// this CTA may read: its own shared memory, or global memory that is complete for it) go into slot (exchange number & 1,
-// my rank) of EVERY rank's mailbox over NVLink; the exchange number is release-stored into the matching flags; then the
-// CTA acquire-waits until its own mailbox holds that number from every peer.  Returns the slot array of this exchange in
-// the rank's own mailbox: rank r's words start at result + r * MB_REC_CAP (read them with __ldcv: written by peers).
-// Every rank runs the same sequence of exchanges on a context, two slots deep: a rank can be at most one exchange ahead
-// of its slowest peer (it needs that peer's flag for exchange s+1, which the peer only sets after it has consumed s).
-// No deadlock: a CTA only ever waits for kernels running on OTHER GPUs.  *timed_out is set when a peer never arrived.
-__device__ __forceinline__ const unsigned long long *mailbox_allgather(char *mailbox, char *const *peers, int rank, int world,
-                                                                       const unsigned long long *send, long long words,
-                                                                       long long timeout_ns, int *timed_out)
-{
-    const int tid = threadIdx.x;
-    unsigned long long *seq_p = reinterpret_cast<unsigned long long *>(mailbox + MB_SEQ);
-    const unsigned long long s = *seq_p + 1;
-    const int slot = (int)(s & 1ull);
-    __syncthreads(); // `send` complete, everyone has read seq
-    for (int r = 0; r < world; ++r) {
-        unsigned long long *dst = reinterpret_cast<unsigned long long *>(peers[r] + MB_REC) + ((size_t)slot * world + rank) * MB_REC_CAP;
-        for (long long i = tid; i < words; i += blockDim.x) dst[i] = send[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < world) {
-        unsigned long long *theirs = reinterpret_cast<unsigned long long *>(peers[tid] + MB_FLAG) + slot * world + rank;
-        st_release_sys(theirs, s);
-        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(mailbox + MB_FLAG) + slot * world + tid;
-        if (!mailbox_wait(mine, s, timeout_ns)) *timed_out = 1;
-    }
-    __syncthreads();
-    if (tid == 0) *seq_p = s;
-    return reinterpret_cast<const unsigned long long *>(mailbox + MB_REC) + (size_t)slot * world * MB_REC_CAP;
-}
-
-// ---- low-latency exchange (the protocol NCCL calls LL): a double travels as two 8-byte words {tag, low half} and
-// {tag, high half}; an aligned 8-byte store arrives whole, so a receiver that sees the tag of THIS exchange in a word has
-// the payload of this exchange.  Every rank runs the same sequence of exchanges on a context (counter in its mailbox),
-// two slots deep like mailbox_allgather: a rank can be one exchange ahead of a peer, never two, because it needs that
-// peer's words of exchange s+1, which the peer sends only after it has read what it wanted of exchange s.
+// ---- low-latency exchange: a double travels as two 8-byte words {tag, low half} and {tag, high half}; an aligned 8-byte
+// store arrives whole, so a receiver that sees the tag of THIS exchange in a word has the payload of this exchange.  Every
+// rank runs the same sequence of exchanges on a context (counter in its mailbox), two slots deep: a rank can be one
+// exchange ahead of a peer, never two, because it needs that peer's words of exchange s+1, which the peer sends only
+// after it has read what it wanted of exchange s.  No deadlock: a CTA only ever waits for kernels running on OTHER GPUs,
+// and gives up after timeout_ns (the solve then fails with ExternalError instead of hanging the GPU).
 struct LLExchange {
     char *mailbox;
     char *const *peers;
@@ -316,10 +255,10 @@ __device__ __forceinline__ LLExchange ll_begin(char *mailbox, char *const *peers
     return x;
 }
 __device__ __forceinline__ void ll_end(const LLExchange &x) { *reinterpret_cast<unsigned long long *>(x.mailbox + MB_LLSEQ) = x.seq; }
-// double number d of this rank's record, to every peer
-__device__ __forceinline__ void ll_put(const LLExchange &x, int d, double v)
+// 8-byte value number d of this rank's record, to every peer
+__device__ __forceinline__ void ll_put_u64(const LLExchange &x, long long d, unsigned long long b)
 {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)x.tag << 32;
+    const unsigned long long t = (unsigned long long)x.tag << 32;
     const unsigned long long w0 = t | (b & 0xffffffffull), w1 = t | (b >> 32);
     for (int r = 0; r < x.world; ++r) {
         if (r == x.rank) continue;
@@ -328,25 +267,85 @@ __device__ __forceinline__ void ll_put(const LLExchange &x, int d, double v)
         asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
     }
 }
-// double number d of rank r's record (r != this rank), from this rank's own mailbox; false after timeout_ns without it
-__device__ __forceinline__ bool ll_get(const LLExchange &x, int r, int d, double &v, long long timeout_ns)
+__device__ __forceinline__ void ll_put(const LLExchange &x, int d, double v) { ll_put_u64(x, d, (unsigned long long)__double_as_longlong(v)); }
+// one look at value number d of rank r's record in this rank's own mailbox: true when both halves carry this exchange's tag
+__device__ __forceinline__ bool ll_peek_u64(const LLExchange &x, int r, long long d, unsigned long long &b)
 {
     const unsigned long long *src = reinterpret_cast<const unsigned long long *>(x.mailbox + MB_LL) +
                                     ((size_t)x.slot * x.world + r) * MB_LL_CAP + 2 * d;
+    unsigned long long w0, w1;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+    b = (w1 << 32) | (w0 & 0xffffffffull);
+    return (unsigned)(w0 >> 32) == x.tag && (unsigned)(w1 >> 32) == x.tag;
+}
+// value number d of rank r's record (r != this rank); false after timeout_ns without it
+__device__ __forceinline__ bool ll_get_u64(const LLExchange &x, int r, long long d, unsigned long long &b, long long timeout_ns)
+{
     unsigned long long t0 = 0;
     for (unsigned spins = 0;; ++spins) {
-        unsigned long long w0, w1;
-        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
-        if ((unsigned)(w0 >> 32) == x.tag && (unsigned)(w1 >> 32) == x.tag) {
-            v = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
-            return true;
-        }
+        if (ll_peek_u64(x, r, d, b)) return true;
         if ((spins & 31u) == 31u) {
             const unsigned long long now = globaltimer_ns();
             if (t0 == 0) t0 = now;
             else if ((long long)(now - t0) > timeout_ns) return false;
         }
     }
+}
+__device__ __forceinline__ bool ll_get(const LLExchange &x, int r, int d, double &v, long long timeout_ns)
+{
+    unsigned long long b = 0;
+    const bool ok = ll_get_u64(x, r, d, b, timeout_ns);
+    v = __longlong_as_double((long long)b);
+    return ok;
+}
+
+// ALLGATHER with the LL protocol, executed by ONE CTA (all of its threads call): `words` 8-byte words at `send` (global
+// memory, complete for this CTA) from every rank into recv[r * stride + i] (this rank's local memory; its own words are
+// copied).  A thread looks at four of its words per trip before it waits for any of them, so the loads overlap.  Ends with
+// a barrier; false (in every thread) when a peer's words did not arrive within timeout_ns.
+__device__ __forceinline__ bool ll_allgather_u64(char *mailbox, char *const *peers, int rank, int world,
+                                                 const unsigned long long *send, long long words, unsigned long long *recv,
+                                                 long long stride, long long timeout_ns)
+{
+    __shared__ int s_ll_bad;
+    if (threadIdx.x == 0) s_ll_bad = 0;
+    const LLExchange X = ll_begin(mailbox, peers, rank, world);
+    for (long long i = threadIdx.x; i < words; i += blockDim.x) {
+        const unsigned long long v = __ldcg(send + i);
+        ll_put_u64(X, i, v);
+        recv[rank * stride + i] = v;
+    }
+    constexpr int U = 4;
+    const long long total = words * (world - 1);
+    for (long long base = threadIdx.x; base < total; base += (long long)blockDim.x * U) {
+        unsigned long long b[U];
+        bool ok[U];
+        int rr[U];
+        long long ii[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long idx = base + (long long)u * blockDim.x;
+            ok[u] = true;
+            if (idx < total) {
+                const int pr = (int)(idx / words);
+                rr[u] = pr < rank ? pr : pr + 1;
+                ii[u] = idx % words;
+                ok[u] = ll_peek_u64(X, rr[u], ii[u], b[u]);
+            } else {
+                rr[u] = -1;
+                ii[u] = 0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (rr[u] < 0) continue;
+            if (!ok[u] && !ll_get_u64(X, rr[u], ii[u], b[u], timeout_ns)) s_ll_bad = 1;
+            recv[rr[u] * stride + ii[u]] = b[u];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) ll_end(X);
+    return s_ll_bad == 0;
 }
 
 __device__ __forceinline__ double sanitize_cost(double c) { return (c != c) ? __longlong_as_double(0x7ff0000000000000LL) : c; }

@@ -335,8 +335,8 @@ __device__ __forceinline__ void pso_apply_step(const PsoDev &P, const double *re
 // ---- the exchange fused into the step kernel (one kernel per pass at any world size) ---------------------------
 // Called by the LAST CTA of the step kernel once P.send holds this rank's record.  Only (cost, index, position) matter in
 // a step; they go to every peer with the low-latency protocol of common.cuh (ll_*: payload and arrival in one 8-byte
-// store, one NVLink one-way trip; the flag protocol of mailbox_allgather needs stores, a system fence's round trip and a
-// flag store: 7 us per pass on two GPUs against 3), then the same gbest selection as pso_step_apply_kernel.
+// store, one NVLink one-way trip; round 1's flag protocol needed stores, a system fence's round trip and a flag store:
+// 7 us per pass on two GPUs against 3), then the same gbest selection as pso_step_apply_kernel.
 __device__ __forceinline__ void pso_p2p_exchange_apply(const PsoDev &P)
 {
     __shared__ int s_bad, s_wr;
@@ -1235,7 +1235,7 @@ int PsoSolver::create(const eqs_pso_params *p)
     // peer mailboxes (NVLink, CUDA IPC): the fused exchange of the synchronous step and of the sequential rounds
     char *mb = nullptr;
     char *const *peers = nullptr;
-    const bool p2p = !manual_ && world > 1 && record_doubles(n) <= MB_REC_CAP && comm_p2p(ctx_, &mb, &peers);
+    const bool p2p = !manual_ && world > 1 && 2 * (2 + (long long)n) <= MB_LL_CAP && comm_p2p(ctx_, &mb, &peers);
     // Sequential-exact mode over several ranks: tile-cyclic distribution + device-driven rounds (pso_seqp_kernel); without
     // peer memory (or with EQS_PSO_SEQ_HOST=1) the host-driven whole-suffix rounds on contiguous blocks
     D.cyclic = p->mode == EQS_PSO_SEQUENTIAL_EXACT && p2p && !getenv("EQS_PSO_SEQ_HOST");

@@ -47,6 +47,12 @@ class Run:
         self.b, self.n, self.total, self.last = b, n, 0, 0
         ctx = b.ctx or Context()
         self.first, self.local = shard_range(b.count, ctx.world, ctx.rank)
+        self.idx = np.arange(self.first, self.first + self.local, dtype=np.int64)
+        if b.mode == "SEQUENTIAL_EXACT" and ctx.world > 1:   # tiles of 256 particles dealt round-robin over the ranks
+            allp = np.arange(b.count, dtype=np.int64)
+            self.idx = allp[(allp // 256) % ctx.world == ctx.rank]
+            self.local = self.idx.size
+    def local_indices(self): return self.idx
     def step(self, k=1, *a):
         os.write(1, b"library chatter on fd 1\n")      # what NCCL does with NCCL_DEBUG set
         self.total += k; self.last = k
@@ -54,7 +60,7 @@ class Run:
     def last_step_ms(self): return 0.25 * self.last, self.last
     def gbest(self): return np.zeros(self.n), 17.5, self.total, 0, 3
     def ring(self): return np.full(50, np.inf), 0
-    def pbest_costs(self): return 0.5 * np.arange(self.first, self.first + self.local)
+    def pbest_costs(self): return 0.5 * self.idx
     def state(self): return np.zeros(self.n), np.ones(self.n), self.total, 1
     def elites(self):
         idx = np.arange(self.first, self.first + self.local, dtype=np.int64)
@@ -63,7 +69,7 @@ class Run:
 
 
 class Builder:
-    def __init__(self, kind): self.kind, self.iter_max, self.count, self.k, self.ctx = kind, 50, 100, 10, None
+    def __init__(self, kind): self.kind, self.iter_max, self.count, self.k, self.ctx, self.mode = kind, 50, 100, 10, None, None
     def __getattr__(self, name):
         if not name.startswith("with_"): raise AttributeError(name)
         def setter(v=None):
@@ -71,6 +77,7 @@ class Builder:
             if name in ("with_particle_count", "with_sample_size", "with_sample_count"): self.count = v
             if name == "with_importance_selection_size": self.k = v
             if name == "with_context": self.ctx = v
+            if name == "with_mode": self.mode = v
             return self
         return setter
     def start(self, x0): return Run(self, len(x0))
@@ -176,17 +183,18 @@ def test_product_arm_two_ranks_over_gloo(tmp_path):
     assert d["config"]["particles_total"] == 2 * d["config"]["particles_per_gpu"]
     assert "cpu_baseline" not in d                                                      # N = 1 only
     # the sharded-vs-unsharded check ran for both halves of the metric and is in the line
-    assert d["parity_check"] is True and set(d["parity_detail"]) == {"headline", "c3"}
+    assert d["parity_check"] is True and set(d["parity_detail"]) == {"headline", "c3", "c2_sequential_exact"}
     assert d["parity_detail"]["headline"]["pbest_cost_checksums_equal"] and d["parity_detail"]["c3"]["elite_set_equal"]
-    assert set(d["also"]) >= {"c4", "c3", "c5", "c1", "c2_sequential_exact"}           # every N carries the other configs
+    assert d["parity_detail"]["c2_sequential_exact"]["index_sets_equal"] and d["parity_detail"]["c2_sequential_exact"]["ok"]
+    assert set(d["also"]) >= {"c4", "c3", "c5", "c1", "c2_sequential_exact", "c2_sequential_exact_sharded"}   # every N carries the other configs
 
 
 def test_parity_failure_takes_every_rank_out(tmp_path):
     """A sharded result that differs from the unsharded run: rank 0 still prints its line (parity_check false), and EVERY
     rank exits non-zero -- nobody hangs in a barrier."""
     script = tmp_path / "bench_dry_run_driver.py"
-    broken = DRIVER.replace("def pbest_costs(self): return 0.5 * np.arange(self.first, self.first + self.local)",
-                            "def pbest_costs(self): return 0.5 * np.arange(self.first, self.first + self.local) + (self.b.ctx.world > 1)")
+    broken = DRIVER.replace("def pbest_costs(self): return 0.5 * self.idx",
+                            "def pbest_costs(self): return 0.5 * self.idx + (self.b.ctx.world > 1)")
     assert broken != DRIVER
     script.write_text(f"ROOT = {ROOT!r}\n" + broken)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
