@@ -20,6 +20,9 @@
 #include <new>
 
 #define EQS_COS_TABLE 1 // issue-bound sample kernels: constant-operand cos (devmath.cuh)
+#ifndef EQS_CE_COS_DEFER // 1: the objective's range test once per sample instead of once per trip (devmath.cuh: DEFER)
+#define EQS_CE_COS_DEFER 1
+#endif
 #define EQS_DEVMATH_TABLES // Box-Muller's logarithm reads its tables from shared memory (devmath.cuh: log_unit_tab)
 #include "common.cuh"
 #include "objectives.cuh"
@@ -135,6 +138,7 @@ __device__ __forceinline__ double ce_sample_cost(const CeDev &P, uint32_t t, lon
         for (int d = 0; d < n; ++d) Obj::feed(acc, smu[d] + ssig[d] * z[d], d);
     } else {
         int d = 0;
+        unsigned hi_max = 0; // the objective's deferred range test (devmath.cuh: eqs_cos_vec DEFER), looked at once per sample
         constexpr int V = EQS_CE_DIMS; // coordinates per trip: V/2 Philox blocks and Box-Muller pairs in flight
         for (; d + V <= n; d += V) {
             double z[V], x[V];
@@ -143,13 +147,20 @@ __device__ __forceinline__ double ce_sample_cost(const CeDev &P, uint32_t t, lon
                 normal_pair(philox_draw(P.key, STREAM_CE, t, gi, (uint32_t)((d + j) >> 1)), z[j], z[j + 1]);
 #pragma unroll
             for (int j = 0; j < V; ++j) x[j] = smu[d + j] + ssig[d + j] * z[j];
-            objective_feed_vec<Obj, V>(acc, x, d);
+            if constexpr (EQS_CE_COS_DEFER) objective_feed_vec_defer<Obj, V>(acc, x, d, hi_max);
+            else objective_feed_vec<Obj, V>(acc, x, d);
         }
         for (; d < n; d += 2) {
             double z0, z1;
             normal_pair(philox_draw(P.key, STREAM_CE, t, gi, (uint32_t)(d >> 1)), z0, z1);
             Obj::feed(acc, smu[d] + ssig[d] * z0, d);
             if (d + 1 < n) Obj::feed(acc, smu[d + 1] + ssig[d + 1] * z1, d + 1);
+        }
+        if (EQS_CE_COS_DEFER && hi_max >= kCosHiLimit) {
+            // some coordinate was outside the fast cosine's range (never on sane inputs): the sums hold garbage.  The sample
+            // is a pure function of its counters: draw it again and feed it through the scalar path, whose cosine is total.
+            Obj::begin(acc, n);
+            ce_sample_coords<false>(P, t, gi, smu, ssig, [&](double x, int dd) { Obj::feed(acc, x, dd); });
         }
     }
     return Obj::end(acc, n);
