@@ -1,14 +1,11 @@
 set -x
-D=gpurun_out/r02w; mkdir -p $D
-V=$PWD/eqsolver_b200/lib/variants
+D=gpurun_out/r02z; mkdir -p $D
+timeout 1500 python -m pytest tests/test_ce_gpu.py tests/test_ce_select_gpu.py tests/test_random_shapes_gpu.py -m gpu -x -q > $D/pytest.log 2>&1; echo "pytest rc=$?"
+tail -n 4 $D/pytest.log
 for rep in 1 2; do
-for v in main cenodefer cemb3 ced2mb3 ced2mb4; do
-  L=$V/libeqsolver_b200_$v.so; [ $v = main ] && L=$PWD/eqsolver_b200/lib/libeqsolver_b200.so
-  EQS_B200_LIBRARY=$L timeout 300 python benchmarks/ce_bench.py --no-peaks > $D/c3_${v}_$rep.json 2>> $D/err.log
-  EQS_B200_LIBRARY=$L timeout 300 python benchmarks/ce_bench.py --dim 1024 --samples 8388608 --objective ROSENBROCK --iters 5 --warmup 2 --no-peaks > $D/c5_${v}_$rep.json 2>> $D/err.log
+timeout 300 python benchmarks/ce_bench.py --no-peaks > $D/ce_c3_$rep.json 2>> $D/err.log
+timeout 300 python benchmarks/ce_bench.py --dim 1024 --samples 8388608 --objective ROSENBROCK --iters 5 --warmup 2 --no-peaks > $D/ce_c5_$rep.json 2>> $D/err.log
 done
-done
-for f in $D/c*_*.json; do echo -n "$f "; python -c "
-import sys,json
-d=json.loads(open('$f').read().strip().splitlines()[-1]); print('%.4f ms/pass %.4e/s' % (d['ms_per_pass'], d['sample_evals_per_s']))
-"; done
+timeout 300 python benchmarks/ce_bench.py --iters 4 --warmup 2 --no-peaks > $D/plain_c3.log 2>&1 &&
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ce_sample_kernel -s 3 -c 1 -o $D/ce_sample_c3 python benchmarks/ce_bench.py --iters 4 --warmup 2 --no-peaks > $D/ncu_c3.log 2>&1
+grep -h sample_evals $D/ce_*.json

@@ -70,6 +70,8 @@ struct CeCtrl {
     int bad_sigma;                // the loop would go on with a non-finite sigma: the reference panics in Normal::new (:259)
     int p2p_timeout;              // a peer never showed up in a fused exchange
     unsigned int ticket;          // last-CTA ticket of the fused kernels (left at 0 by each of them)
+    unsigned int sample_ticket;   // the same for the sample kernel's work counter (every mode)
+    unsigned long long work_next; // sample kernel: first local sample nobody has taken yet (left at 0 by the kernel)
 };
 
 struct CeDev {
@@ -364,8 +366,20 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK, EQ
     load_mu_sigma(P, smu, ssig);
     unsigned long long klo = ~0ULL, khi = 0ULL;
     unsigned int nan = 0u;
-    for (long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x; li < P.nloc;
-         li += (long long)gridDim.x * blockDim.x) {
+    // Work is handed out dynamically, 32 samples (one per lane) at a time.  With a fixed grid-stride assignment the warps of
+    // a scheduler do not advance at the same rate in this issue-bound kernel: the favoured ones finish early and the tail
+    // runs with 1-2 warps per scheduler (ncu: 13.3 of 16 warps active on average, profiles/r02y_ncu_ce_sample_c3.csv).
+    // A sample's cost depends on its index only, so who computes it changes nothing.  The next chunk is requested before
+    // the current one is computed: the atomic's latency is never waited for.
+    const int lane = threadIdx.x & 31;
+    unsigned long long next = 0;
+    if (lane == 0) next = atomicAdd(&c->work_next, 32ULL);
+    for (;;) {
+        const long long base = (long long)__shfl_sync(0xffffffffu, next, 0);
+        if (base >= P.nloc) break;
+        if (lane == 0) next = atomicAdd(&c->work_next, 32ULL);
+        const long long li = base + lane;
+        if (li >= P.nloc) continue;
         const long long gi = P.first + li;
         double cost;
         if constexpr (Obj::streaming) {
@@ -409,8 +423,22 @@ template <class Obj, bool REPLAY> __global__ void __launch_bounds__(CE_BLOCK, EQ
         }
         if (nan) atomicAdd(&P.hsend[2], (unsigned long long)nan);
     }
-    if (fused == CE_PHASED) return;
-    if (ce_last_block(c, gridDim.x)) ce_select_begin(P, ce_gather(P, fused, P.hsend, 4));
+    // the last CTA to finish leaves the work counter at 0 for the next pass (a ticket of its own: the phased mode joins
+    // its stages on the host and must not touch the fused kernels' ticket protocol)
+    __shared__ int s_last_sample;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last_sample = atomicAdd(&c->sample_ticket, 1u) == gridDim.x - 1;
+        if (s_last_sample) {
+            c->sample_ticket = 0u;
+            c->work_next = 0ULL;
+        }
+    }
+    __syncthreads();
+    if (fused == CE_PHASED || !s_last_sample) return;
+    __threadfence();
+    ce_select_begin(P, ce_gather(P, fused, P.hsend, 4));
 }
 
 // K5, levels A and B: histogram of the current level over ALL keys of this rank; level B (`compact`) also copies the keys

@@ -53,6 +53,11 @@ namespace {
 #ifndef EQS_PSO_MINB
 #define EQS_PSO_MINB 2
 #endif
+// groups per load batch in the persistent sequential-exact kernel: a round there is latency-bound (every thread moves at
+// most one particle per round: n / (4 UQ) dependent load batches), not bandwidth-bound
+#ifndef EQS_PSO_SEQ_UQ
+#define EQS_PSO_SEQ_UQ EQS_PSO_UQ
+#endif
 // 1: the objective takes the 4 * UQ coordinates of a load batch at once, after the batch's stores, instead of 4 at a time
 // between them (measured on one box, profiles/r02_sweep.md section 3: C2 0.866 -> 0.892, C4 0.875 -> 0.881 of measured HBM)
 #ifndef EQS_PSO_FEED_BATCH
@@ -193,7 +198,7 @@ __device__ __forceinline__ void pso_groups(const PsoDev &P, uint32_t t, long lon
 }
 
 // all dimensions of one particle; returns its new cost
-template <class Obj, bool REPLAY>
+template <class Obj, bool REPLAY, int UQ = EQS_PSO_UQ>
 __device__ __forceinline__ double pso_move(const PsoDev &P, uint32_t t, long long li, const double *sG, const double *xin,
                                            const double *vin, const double *pbin, double *xout, double *vout, bool load_pb)
 {
@@ -201,7 +206,6 @@ __device__ __forceinline__ double pso_move(const PsoDev &P, uint32_t t, long lon
     ObjAcc acc;
     unsigned hi_max = 0;
     if constexpr (Obj::streaming) Obj::begin(acc, n);
-    constexpr int UQ = EQS_PSO_UQ;
     int q = 0;
     for (; q + UQ <= nfull; q += UQ) {
         pso_groups<Obj, REPLAY, UQ>(P, t, li, q, sG, acc, xin, vin, pbin, xout, vout, load_pb, hi_max);
@@ -952,7 +956,7 @@ __global__ void __launch_bounds__(PSO_BLOCK) pso_seqp_kernel(const PsoDev P)
         MinLoc first{0.0, kNoIndex}; // min over the index only
         const long long s1 = pso_lcount(P, wend);
         for (long long li = first_at(pso_lcount(P, start)); li < s1; li += stride) {
-            const double cost = pso_move<Obj, REPLAY>(P, t, li, sG, xa, va, P.pb, xb, vb, true);
+            const double cost = pso_move<Obj, REPLAY, EQS_PSO_SEQ_UQ>(P, t, li, sG, xa, va, P.pb, xb, vb, true);
             P.cost[li] = cost;
             if (cost < P.pbc[li] && cost < Gc && li < first.i) first.i = li; // :417,:420 (nested; see pso_spec_kernel)
         }

@@ -589,15 +589,29 @@ def test_concurrent_solves_from_threads(ctx):
 def test_full_size_c4_properties(ctx):
     """BASELINE config 4 at its per-GPU size (Ackley n=256, 2^21 particles = 12.9 GB of state): size-independent
     properties of the synchronous pass."""
-    n, N = 256, 1 << 21
-    ps = (E.ParticleSwarm.new(E.Objective.ACKLEY, [-32.768] * n, [32.768] * n).with_particle_count(N).with_tol(0.0)
-          .with_seed(1729).with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx))
+    n, N, lo, hi, seed = 256, 1 << 21, -32.768, 32.768, 1729
+    ps = (E.ParticleSwarm.new(E.Objective.ACKLEY, [lo] * n, [hi] * n).with_particle_count(N).with_tol(0.0)
+          .with_seed(seed).with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx))
     run = ps.start(np.full(n, 30.0))
     g, c_prev, _, _, _ = run.gbest()
     pbc_prev = run.pbest_costs()
     f0 = O.objective(O.ACKLEY, np.full(n, 30.0))
     assert c_prev == min(pbc_prev.min(), f0)
+    # A sample of particles is carried through the same passes in the ORACLE's arithmetic, from nothing but the draw
+    # contract and the gbest positions the device reports (the 13 GB of state stay on the device): init :361-389, update
+    # :406-413 in rustc's evaluation order, objective, pbest test :417-419.  Checked against the device's pbest costs.
+    sample = np.random.default_rng(4).integers(0, N, 24)
+    mine = {}
+    for j in sample:
+        pu, vu = O.pso_init_draws(seed, int(j), n)
+        x = pu * (hi - lo) + lo
+        dist = abs(hi - lo)
+        v = vu * (dist + dist) + (-dist)
+        mine[int(j)] = [x, v, x.copy(), O.objective(O.ACKLEY, x)]
+    for j, (x, v, pb, pc) in mine.items():
+        assert abs(pbc_prev[j] - pc) <= 1e-12 * abs(pc), f"init cost of particle {j}"
     for t in range(3):
+        g_before = g.copy()
         run.step(1)
         g, c, it, stalled, _ = run.gbest()
         pbc = run.pbest_costs()
@@ -606,6 +620,16 @@ def test_full_size_c4_properties(ctx):
         assert c <= pbc.min() and (c == pbc.min() or c == f0)       # gbest cost = the best cost seen
         assert abs(O.objective(O.ACKLEY, g) - c) <= 1e-12 * c       # the gbest cost is f(gbest position)
         assert np.all(np.isfinite(pbc))
+        for j, st in mine.items():
+            x, v, pb, pc = st
+            rp, rg = O.pso_step_draws(seed, t, j, n)
+            v = 0.5 * v + 1.0 * rp * (pb - x) + 1.0 * rg * (g_before - x)
+            x = x + v
+            cost = O.objective(O.ACKLEY, x)
+            if cost < pc:
+                pb, pc = x.copy(), cost
+            st[:] = [x, v, pb, pc]
+            assert abs(pbc[j] - pc) <= 1e-12 * abs(pc), f"pbest cost of particle {j} after pass {t}"
         c_prev, pbc_prev = c, pbc
     run.close()
 
