@@ -581,7 +581,7 @@ def also_measured(b: Bench, headline: str, fp64_peak: float):
             out["c1"] = {"value": N * 1000 / (ms * 1e-3), "unit": "particle-evals/s", "us_per_pass": ms, "passes": 1000,
                          "launches": launches, "bound": "latency (state fits one SM; no roofline claim)"}
             run.close()
-        # C2 in the reference's sequential-gbest semantics (pso_seqw_kernel)
+        # C2 in the reference's sequential-gbest semantics (pso_seqp_kernel)
         n, N = 32, 1 << 20
         run = b.pso("c2", N, 10 ** 6, ctx=b.ctx1, mode=E.PsoMode.SEQUENTIAL_EXACT).start(np.zeros(n))
         run.step(3); run.sync(); run.step(40); run.sync()

@@ -1,8 +1,10 @@
 """One process per GPU: bootstrap of the NCCL communicator the kernel library uses for its per-iteration exchange.
 
 torch.distributed is plumbing only (rendezvous, shipping the 128-byte NCCL unique id, barriers, max-over-ranks of
-timings); the data path -- one record of 54+n doubles per rank per ParticleSwarm pass, a histogram or n doubles per
-CrossEntropy phase -- goes through the library's own communicator on its own stream (csrc/comm.cu).
+timings); the data path -- (cost, index, position) of one particle per rank per ParticleSwarm pass or sequential round, a
+histogram or n doubles per CrossEntropy stage -- is moved by the kernels themselves over the peer-memory mailboxes set up
+in eqs_ctx_comm_init (csrc/comm.cu, csrc/common.cuh: ll_*), or by the library's own NCCL communicator where peer mapping is
+unavailable.
 """
 from __future__ import annotations
 
