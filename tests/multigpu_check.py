@@ -220,6 +220,31 @@ def main():
             np.testing.assert_allclose(sg, osg, rtol=1e-11, atol=1e-12 * scale, err_msg=what)
         crun.close()
 
+    # ---- a peer that never shows up: the rank that waits in its kernel gives up after EQS_P2P_TIMEOUT_S and the call fails
+    # with ExternalError; nothing hangs.  Last thing on this context: its exchange counters are out of step afterwards. ----
+    if os.environ.get("EQS_P2P", "1") != "0":
+        dist.barrier()
+        os.environ["EQS_P2P_TIMEOUT_S"] = "2"
+        n = 4
+        run = (E.ParticleSwarm.new(E.Objective.SPHERE, [-1.0] * n, [1.0] * n).with_particle_count(4096 * world).with_tol(0.0)
+               .with_seed(3).with_mode(E.PsoMode.SYNCHRONOUS).with_context(ctx)).start(np.full(n, 0.5))
+        run.step(1)
+        run.sync()
+        dist.barrier()
+        if rank == 0:   # only rank 0 enqueues the next pass
+            import time
+            t0 = time.monotonic()
+            try:
+                run.step(1)
+                run.gbest()
+                raise AssertionError("a pass without its peers must fail")
+            except E.ExternalError as e:
+                assert "peer" in str(e), str(e)
+            waited = time.monotonic() - t0
+            assert 1.5 < waited < 15.0, waited
+        dist.barrier()
+        os.environ.pop("EQS_P2P_TIMEOUT_S", None)
+
     dist.barrier()
     if rank == 0:
         print(f"multigpu_check OK on {world} GPUs")
