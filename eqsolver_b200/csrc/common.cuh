@@ -199,7 +199,7 @@ constexpr size_t MB_BYTES = MB_LL + 2ull * MB_MAX_WORLD * MB_LL_CAP * sizeof(uns
 bool comm_p2p(Ctx *ctx, char **mailbox, char *const **d_peers);
 // How long a kernel waits in a mailbox for a peer before it gives up (the solve then fails with ExternalError instead of
 // hanging the GPU): EQS_P2P_TIMEOUT_S seconds, default 20.  All ranks must therefore enqueue the same pass within that
-// time of each other ("co-scheduling").
+// time of each other ("Co-scheduling").
 long long comm_p2p_timeout_ns();
 
 // Dynamic shared memory beyond this many bytes is requested with cudaFuncAttributeMaxDynamicSharedMemorySize.  The

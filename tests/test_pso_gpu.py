@@ -635,7 +635,7 @@ def test_full_size_c4_properties(ctx):
 
 
 def test_user_objective_hook(ctx, tmp_path):
-    """INTEGRATION.md §4: a user objective is a CUDA header named at build time (EQS_USER_OBJECTIVE_HEADER).  Build a
+    """INTEGRATION.md §5: a user objective is a CUDA header named at build time (EQS_USER_OBJECTIVE_HEADER).  Build a
     library variant whose api.cu carries a custom streaming functor and evaluate it through eqs_objective_eval."""
     import ctypes as C
     import subprocess
