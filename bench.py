@@ -370,7 +370,16 @@ class Bench:
         self.barrier()
         t1 = time.monotonic()
         ms, launches = run.last_step_ms()
+        self.last_ms_by_rank = self.gather_f64(ms)      # every rank's own device time of the same K passes
         return self.reduce(ms, "MAX"), launches, t0, t1
+
+    def gather_f64(self, v: float):
+        if self.world == 1:
+            return [v]
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=DEVICE)
+        parts = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(parts, t)
+        return [float(p.item()) for p in parts]
 
 
 def pso_roofline(workload: str, n: int, per_gpu: int, ms_per_pass: float, pattern=None):
@@ -559,6 +568,25 @@ def also_measured(b: Bench, headline: str, fp64_peak: float):
                        "ms_per_pass": ms / passes, "launches_per_pass": launches / passes, "passes": passes,
                        "particles_per_gpu": per_gpu, "n": n, "roofline": pso_roofline(wl, n, per_gpu, ms / passes)}
     if b.world > 1:
+        # Every GPU of the job ALONE on the per-GPU shape, all at the same time, no exchange (each rank on its own
+        # unsharded context): what separates "N x one GPU" from the sharded figures above is partly the exchange and partly
+        # that the ranks wait for the slowest GPU of the box in every pass -- this shows the latter.
+        for wl, warm, passes in (("c2", 5, 40), ("c3", 3, 20)):
+            run = b.start(wl, warm + passes, ctx=b.ctx1, world=1)
+            run.step(warm)
+            run.sync()
+            b.barrier()
+            run.step(passes)
+            run.sync()
+            ms, _ = run.last_step_ms()
+            run.close()
+            per = b.gather_f64(ms / passes)
+            per_gpu = (CE_WORKLOADS[wl] if wl in CE_WORKLOADS else PSO_WORKLOADS[wl])[2]
+            out[wl + "_solo_by_rank"] = {"ms_per_pass": per, "slowest_over_fastest": max(per) / min(per),
+                                         "n_times_slowest": per_gpu * b.world / (max(per) * 1e-3),
+                                         "unit": "sample-evals/s" if wl in CE_WORKLOADS else "particle-evals/s",
+                                         "what": "each rank runs the per-GPU shape unsharded on its own GPU, all ranks at "
+                                                 "once; n_times_slowest = what a sharded pass could reach with a free exchange"}
         # C2 in the reference's sequential-gbest semantics over all ranks (weak scaling: 2^20 particles per GPU)
         n, per_gpu, passes = 32, 1 << 20, 30
         run = b.pso("c2", per_gpu * b.world, 10 ** 6, mode=E.PsoMode.SEQUENTIAL_EXACT).start(np.zeros(n))
@@ -643,6 +671,7 @@ def main():
     # rank 0 forks nvidia-smi BEFORE the barrier: nothing but the enqueue of the passes happens behind it
     ms, launches, t0, t1 = b.timed(run, args.warmup, args.steps,
                                    before_barrier=(lambda: sampler.append(ClockSampler(local))) if rank == 0 else None)
+    ms_by_rank = [m / args.steps for m in b.last_ms_by_rank]
     window = "timed region"
     # collective decision (the extra passes contain the per-pass exchange): every rank must take the same branch
     if b.reduce(1.0 if (t1 - t0) < 0.6 else 0.0, "MAX") > 0.5:
@@ -708,7 +737,9 @@ def main():
 
     line = {
         "metric": unit, "value": value, "unit": unit, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "ms_per_step_by_rank": ms_by_rank,   # each rank's own CUDA-event time; ms_per_step is their maximum
+        "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict({"workload": desc, "n": n, "units_per_gpu": per_gpu, "units_total": N,
                         "particles_per_gpu": per_gpu, "particles_total": N,

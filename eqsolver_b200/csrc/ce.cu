@@ -201,7 +201,9 @@ struct Gathered {
     const unsigned long long *p;
     long long stride;
     int world;
-    __device__ __forceinline__ unsigned long long operator()(int r, long long i) const { return __ldcv(p + r * stride + i); }
+    // L2 loads (the words were written by other CTAs, by this CTA's other threads, or by the NCCL kernel before this one):
+    // they overlap, where volatile loads complete one after the other (32 of them per thread on 8 ranks)
+    __device__ __forceinline__ unsigned long long operator()(int r, long long i) const { return __ldcg(p + r * stride + i); }
     __device__ __forceinline__ double f64(int r, long long i) const { return __longlong_as_double((long long)(*this)(r, i)); }
 };
 
@@ -708,6 +710,9 @@ __device__ __forceinline__ void ce_sigma_apply(const CeDev &P, Gathered g)
     }
 }
 
+// chunks of CE_CHUNK elites that hold this rank's elites (at least one, so that a rank without elites still writes a zero)
+__device__ __forceinline__ int ce_live_chunks(long long ne) { return ne > 0 ? (int)((ne + CE_CHUNK - 1) / CE_CHUNK) : 1; }
+
 // per-dimension partial sums over a chunk of elites; mode 0: sum x, mode 1: sum (x - mu_new)^2 (:283-293).  Fused modes:
 // the last CTA adds the chunks in chunk order, gathers the ranks' sums and applies them (mean, or sigma + loop control).
 __global__ void __launch_bounds__(CE_BLOCK) ce_rowsum_kernel(const CeDev P, int mode, int fused)
@@ -717,32 +722,39 @@ __global__ void __launch_bounds__(CE_BLOCK) ce_rowsum_kernel(const CeDev P, int 
     if (!c->active) return;
     const long long ne = c->n_elite_local;
     const int d = blockIdx.y;
-    const long long j0 = (long long)blockIdx.x * CE_CHUNK, j1 = j0 + CE_CHUNK < ne ? j0 + CE_CHUNK : ne;
+    // The chunks are those of the elites this rank ACTUALLY holds (ce_live_chunks), walked by however many CTA columns the
+    // host launched: the buffers are sized for the worst case (all k elites on one rank), the grid for twice the expected
+    // share -- sized by the capacity, a pass over 8 ranks spent more time in empty CTAs than in the exchange.
+    const int nact = ce_live_chunks(ne);
     const double m = mode ? P.mu_new[d] : 0.0;
-    double acc = 0.0;
-    for (long long j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
-        const double v = P.Ex[(long long)d * P.kld + j];
-        if (mode) {
-            const double e = v - m;
-            acc += e * e;
-        } else {
-            acc += v;
+    for (int ch = blockIdx.x; ch < nact; ch += gridDim.x) {
+        const long long j0 = (long long)ch * CE_CHUNK, j1 = j0 + CE_CHUNK < ne ? j0 + CE_CHUNK : ne;
+        double acc = 0.0;
+        for (long long j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+            const double v = P.Ex[(long long)d * P.kld + j];
+            if (mode) {
+                const double e = v - m;
+                acc += e * e;
+            } else {
+                acc += v;
+            }
         }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int w = 0; w < CE_BLOCK / 32; ++w) s += s_w[w];
-        P.part[(long long)d * P.nchunks + blockIdx.x] = s;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        __syncthreads(); // s_w of the previous chunk has been read
+        if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < CE_BLOCK / 32; ++w) s += s_w[w];
+            P.part[(long long)d * P.nchunks + ch] = s;
+        }
     }
     if (fused == CE_PHASED) return;
     if (!ce_last_block(c, gridDim.x * gridDim.y)) return;
     for (int dd = threadIdx.x; dd < P.n; dd += blockDim.x) {
         double s = 0.0;
-        for (int ch = 0; ch < P.nchunks; ++ch) s += __ldcg(P.part + (long long)dd * P.nchunks + ch);
+        for (int ch = 0; ch < nact; ++ch) s += __ldcg(P.part + (long long)dd * P.nchunks + ch);
         P.msend[dd] = s;
     }
     __threadfence();
@@ -759,7 +771,8 @@ __global__ void ce_moment_local_kernel(const CeDev P)
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= P.n) return;
     double s = 0.0;
-    for (int ch = 0; ch < P.nchunks; ++ch) s += P.part[(long long)d * P.nchunks + ch];
+    const int nact = ce_live_chunks(P.ctrl->n_elite_local);
+    for (int ch = 0; ch < nact; ++ch) s += P.part[(long long)d * P.nchunks + ch];
     P.msend[d] = s;
 }
 
@@ -1136,7 +1149,10 @@ public:
 
     void launch_rowsum(int mode, int fused)
     {
-        ce_rowsum_kernel<<<dim3(d_.nchunks, d_.n), CE_BLOCK, 0, ctx_->stream>>>(d_, mode, fused);
+        // CTA columns for twice the share of the elites a rank expects (k / world); the kernel walks whatever it really has
+        const long long expect = (d_.k + d_.world - 1) / d_.world;
+        const long long cols = std::min<long long>(d_.nchunks, (2 * expect + CE_CHUNK - 1) / CE_CHUNK + 1);
+        ce_rowsum_kernel<<<dim3((unsigned)std::max<long long>(cols, 1), d_.n), CE_BLOCK, 0, ctx_->stream>>>(d_, mode, fused);
         launches_++;
     }
 
