@@ -120,6 +120,99 @@ def _worker(rank, world, port, results):
         st, rmean, rvar = O.mc_integrate(O.GAUSSIAN, lower, upper, count, seed=9)
         assert st == 0 and cnt == count
         assert abs(mean * vol - rmean) <= 1e-13 * abs(rmean) and abs(m2 / (count - 1) * vol * vol - rvar) <= 1e-12 * rvar
+        # 5. ParticleSwarm in the reference's SEQUENTIAL semantics over the ranks, the protocol of csrc/pso.cu: pso_seqp_kernel /
+        #    pso_seq_exchange: tiles of consecutive particles dealt round-robin; the ordered ring pushes of the
+        #    init loop rebuilt from the tile minima of ALL ranks and merged by position; passes as windowed rounds whose only
+        #    exchange is (first improving global index, its cost, its position).  Modelled in numpy on the oracle's draws and
+        #    objective (the arithmetic below is the oracle's, bit for bit), against the UNSHARDED oracle.
+        TILE, n, N, W, seed = 16, 4, 1003, 150, 21           # the kernels use tiles of 256; the protocol does not care
+        lo, hi, x0 = np.full(n, -5.0), np.full(n, 10.0), np.full(n, 3.0)
+        ref = O.Pso(O.ROSENBROCK, lo, hi, particle_count=N, mode=O.SEQUENTIAL, seed=seed, tol=0.0)
+        ref.init(x0)
+        own = np.array([g for g in range(N) if (g // TILE) % world == rank])
+        f = lambda xx: O.objective(O.ROSENBROCK, xx)
+        X, V = {}, {}
+        for g in own:
+            pu, vu = O.pso_init_draws(seed, int(g), n)
+            dist_ = np.abs(hi - lo)
+            X[g], V[g] = pu * (hi - lo) + lo, vu * (dist_ + dist_) + (-dist_)
+        PB = {g: X[g].copy() for g in own}
+        PBC = {g: f(X[g]) for g in own}
+        # init, exchange 1: every rank's best (cost, index, position); lowest cost, then lowest index
+        best = min(own, key=lambda g: (PBC[g], g)) if own.size else -1
+        rec = allgather(np.concatenate([[PBC[best] if best >= 0 else np.inf, best], X[best] if best >= 0 else np.zeros(n)]))
+        # init, exchange 2: the minima of ALL tiles, walked in global order
+        ntiles = (N + TILE - 1) // TILE
+        per = (ntiles + world - 1) // world
+        gm = np.full(per, np.inf)
+        for g in own:
+            gm[(g // TILE) // world] = min(gm[(g // TILE) // world], PBC[g])
+        gm_all = allgather(gm)
+        f0 = f(x0)
+        running, pushes = f0, []                              # (position, pushed value) of this rank's record lows
+        for T in range(ntiles):
+            tmin = gm_all[T % world, T // world]
+            if tmin < running and T % world == rank:          # a tile with a record low that this rank owns
+                e = running
+                for g in range(T * TILE, min((T + 1) * TILE, N)):
+                    if PBC[g] < e:
+                        pushes.append((g, e))
+                        e = PBC[g]
+            running = min(running, tmin)
+        kept = pushes[-50:]
+        msg = np.full(1 + 100, -1.0)
+        msg[0] = len(pushes)
+        for j, (g, e) in enumerate(kept):
+            msg[1 + j], msg[51 + j] = g, e
+        allp = allgather(msg)
+        total = int(allp[:, 0].sum())
+        merged = sorted((int(allp[r, 1 + j]), allp[r, 51 + j]) for r in range(world) for j in range(50) if allp[r, 1 + j] >= 0)
+        ring = np.full(50, np.inf)
+        for back, (g, e) in enumerate(reversed(merged[-50:])):  # push number total-1-back goes to slot (number % 50)
+            ring[(total - 1 - back) % 50] = e
+        ring_i = total % 50
+        win = min(range(world), key=lambda r: (rec[r, 0], rec[r, 1] if rec[r, 1] >= 0 else np.inf))
+        G, Gc = (rec[win, 2:].copy(), rec[win, 0]) if rec[win, 1] >= 0 and rec[win, 0] < f0 else (x0.copy(), f0)
+        assert np.array_equal(ring.view(np.uint64), ref.ring()[0].view(np.uint64)) and ring_i == ref.ring()[1], "seq init ring"
+        assert np.array_equal(G.view(np.uint64), ref.gbest().view(np.uint64)) and Gc == ref.gbest_cost(), "seq init gbest"
+        wins = [0] * world
+        for t in range(4):
+            start, rounds = 0, 0
+            while start < N:
+                wend = min(start + W, N)
+                spec, first = {}, -1
+                for g in own[(own >= start) & (own < wend)]:
+                    rp, rg = O.pso_step_draws(seed, t, int(g), n)
+                    v2 = 0.5 * V[g] + 1.0 * rp * (PB[g] - X[g]) + 1.0 * rg * (G - X[g])
+                    x2 = X[g] + v2
+                    spec[g] = (x2, v2, f(x2))
+                    if first < 0 and spec[g][2] < PBC[g] and spec[g][2] < Gc:
+                        first = g                             # own is ascending: the first hit is the lowest index
+                got = allgather(np.concatenate([[first, spec[first][2] if first >= 0 else np.inf],
+                                                spec[first][0] if first >= 0 else np.zeros(n)]))
+                hits = [r for r in range(world) if got[r, 0] >= 0]
+                wr = min(hits, key=lambda r: got[r, 0]) if hits else -1
+                end = int(got[wr, 0]) if wr >= 0 else wend - 1
+                for g in own[(own >= start) & (own <= end)]:  # final: commit, pbest test (:413-419)
+                    X[g], V[g], c = spec[g]
+                    if c < PBC[g]:
+                        PB[g], PBC[g] = X[g].copy(), c
+                if wr >= 0:                                   # :420-425
+                    wins[wr] += 1
+                    ring[ring_i] = Gc
+                    ring_i = (ring_i + 1) % 50
+                    G, Gc = got[wr, 2:].copy(), got[wr, 1]
+                start, rounds = end + 1, rounds + 1
+            ref.step()
+            rx, rv, rpb, rpbc = ref.state()
+            for g in own:
+                assert np.array_equal(X[g].view(np.uint64), rx[g].view(np.uint64)), f"seq x {g} pass {t}"
+                assert np.array_equal(V[g].view(np.uint64), rv[g].view(np.uint64)), f"seq v {g} pass {t}"
+                assert np.array_equal(PB[g].view(np.uint64), rpb[g].view(np.uint64)) and PBC[g] == rpbc[g], f"seq pbest {g} pass {t}"
+            assert np.array_equal(G.view(np.uint64), ref.gbest().view(np.uint64)) and Gc == ref.gbest_cost(), f"seq gbest pass {t}"
+            assert np.array_equal(ring.view(np.uint64), ref.ring()[0].view(np.uint64)) and ring_i == ref.ring()[1], f"seq ring {t}"
+            assert rounds >= (N + W - 1) // W
+        assert all(w > 0 for w in wins), wins                 # gbest moved through particles of every rank
         results[rank] = "ok"
     except Exception as e:  # surface the failure to the parent
         import traceback
