@@ -1245,12 +1245,11 @@ int PsoSolver::create(const eqs_pso_params *p)
     D.cyclic = p->mode == EQS_PSO_SEQUENTIAL_EXACT && p2p && !getenv("EQS_PSO_SEQ_HOST");
     D.tiles_per_rank = 0;
     if (D.cyclic) {
-        const int64_t ntiles = (p->particle_count + PSO_GROUP - 1) / PSO_GROUP;
-        const int64_t owned = ntiles > rank ? (ntiles - rank + world - 1) / world : 0;
-        nloc = owned * PSO_GROUP;
-        if (owned > 0 && (ntiles - 1) % world == rank) nloc -= ntiles * PSO_GROUP - p->particle_count; // the ragged last tile
+        long long cn = 0, per = 1;
+        pso_cyclic_shard(p->particle_count, world, rank, &cn, &per);
+        nloc = cn;
+        D.tiles_per_rank = per;
         first = (int64_t)rank * PSO_GROUP; // global index of local particle 0 (informational: see local_indices)
-        D.tiles_per_rank = std::max<int64_t>((ntiles + world - 1) / world, 1);
     }
     D.first = first;
     D.nloc = nloc;

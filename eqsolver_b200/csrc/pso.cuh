@@ -97,6 +97,18 @@ __host__ __device__ inline long long pso_lcount(const PsoDev &P, long long g)
     }
     return c < 0 ? 0 : (c > P.nloc ? P.nloc : c);
 }
+// tile-cyclic distribution, host side: how many of `count` particles rank `rank` of `world` holds, and how many tiles a
+// rank holds at most (the stride of the gathered tile minima)
+inline void pso_cyclic_shard(long long count, int world, int rank, long long *nloc, long long *tiles_per_rank)
+{
+    const long long ntiles = (count + PSO_GROUP - 1) / PSO_GROUP;
+    const long long owned = ntiles > rank ? (ntiles - rank + world - 1) / world : 0;
+    long long n = owned * PSO_GROUP;
+    if (owned > 0 && (ntiles - 1) % world == rank) n -= ntiles * PSO_GROUP - count; // the ragged last tile
+    *nloc = n;
+    const long long per = (ntiles + world - 1) / world;
+    *tiles_per_rank = per > 1 ? per : 1;
+}
 constexpr int PSO_SMALL_BLOCK = 512; // K8: threads of the single-CTA whole-solve kernel
 constexpr int PSO_SMALL_MAX = 2048;  // K8: largest population it takes (4 particles per thread)
 

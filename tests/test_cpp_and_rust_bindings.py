@@ -32,6 +32,19 @@ def test_cpp_builder_on_gpu():
     assert r.returncode == 0 and "gpu tests ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_tile_cyclic_distribution_helpers_on_the_host():
+    """csrc/pso.cuh: pso_gidx / pso_lidx / pso_lcount / pso_cyclic_shard, the index arithmetic of the sequential-exact mode
+    over several ranks, as a host program (the functions are __host__ __device__): the ranks' index sets partition 0..N-1
+    for N around the tile size and up to 2^18, worlds 1..9; local order is global order; window cuts count right."""
+    from eqsolver_b200 import build as kbuild
+    exe = os.path.join(ROOT, "build", "test_cyclic")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call([kbuild._nvcc(), "-std=c++20", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-x", "cu",
+                           os.path.join(ROOT, "tests", "cpp", "test_cyclic.cu"), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "cyclic distribution ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_rust_extern_block_matches_header():
     """rust/eqsolver-cuda-sys cannot be compiled here (no cargo); at least its symbol set must equal the header's."""
     from test_abi import header_symbols
