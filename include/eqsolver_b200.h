@@ -186,6 +186,8 @@ int eqs_pso_read_gbest(eqs_pso *h, double *g /*[n] or NULL*/, double *cost, int6
 /* particle-major [local][n] like the reference's Vec<Particle>; any pointer may be NULL */
 int eqs_pso_read_state(eqs_pso *h, double *x, double *v, double *pbest, double *pbest_cost);
 int eqs_pso_read_ring(eqs_pso *h, double *ring /*[50]*/, int64_t *ring_i);
+/* first global index and number of the particles this rank holds; they are the block first .. first + local - 1 except
+ * in the tile-cyclic distribution described below, where only `local` is meaningful */
 int eqs_pso_local_range(eqs_pso *h, int64_t *first, int64_t *local);
 /* global index of every local particle, in the row order of eqs_pso_read_state: gidx [local].  Contiguous blocks
  * (first .. first + local - 1) except in sequential-exact mode over several ranks, which deals tiles of 256 consecutive
